@@ -1,0 +1,342 @@
+#!/usr/bin/env python
+"""bench.py -- RANSAC hypotheses/s on BASELINE config C2 (fit_plane + fit_sphere + fit_cylinder,
+1M-point synthetic cloud, 10k hypotheses each) on N x B200, beside the CPU reference path.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+One step = the three fits (30 000 hypotheses per GPU; probability = 1.0 so that every hypothesis
+is evaluated, ransac.h:601-606).  For N > 1 (torchrun, one rank per GPU) the hypothesis batch
+grows with N (10k per primitive per GPU: weak scaling); rank r scores its shard of the SAME
+global sample table and one NCCL all-gather of the inlier counts per fit lets every rank replay
+the identical ordered scan.
+
+Printed JSON (one line, rank 0):
+  value     hypotheses/s, cloud resident in HBM (m3d_ransac_fit_cloud), CUDA-event timed
+  e2e       the same through the host-buffer C-ABI entry point (m3d_ransac_fit): pinned host
+            cloud -> H2D, fit, inlier indices -> D2H, all inside the timed region
+  roofline  the scoring kernel against the HBM roofline (compulsory bytes 24*N + 64*H per launch,
+            SURVEY.md §8d) -- and `roofline_alu`, the roofline that actually binds it
+  cpu_baseline  the oracle's OpenMP restatement of the reference loop on the box's host cores
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_POINTS = 1_000_000
+H_PER_PRIM = 10_000
+THR = 0.01
+SEED = 20240917
+KINDS = (0, 1, 2)  # plane, sphere, cylinder
+FLOPS_PER_UNIT = {0: 8, 1: 10, 2: 24}      # SURVEY.md §8(d), fp64 ops of the reference as written
+FAST_FFMA_PER_UNIT = {0: 3, 1: 4, 2: 8}    # fp32 FMA-pipe ops of the scoring kernel's inner loop
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured", d
+    return 6650.0, "fallback", {}
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons while the timed region runs"""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                for nm, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def reference_arm(args, rank, world):
+    """The reference's own CPU algorithm (OpenMP loop of ransac.h:571-614, restated in oracle/) on
+    the host cores: each step = a bounded sample of the C2 workload (H_cpu hypotheses per primitive
+    on the full 1M-point cloud, including the per-hypothesis O(N) SelectByIndex pass)."""
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import orc
+    from misc3d_b200 import synth
+    orc.build()
+    xyz, nrm = synth.make_c2(N_POINTS, SEED)
+    cores = orc.omp_threads()
+    # calibrate the sample so one step is a few seconds of CPU work
+    t0 = time.perf_counter()
+    orc.ransac_fit(orc.PLANE, xyz, None, thr=THR, max_it=cores, prob=1.0, seed=1, omp=True, faithful=True)
+    per_hyp = (time.perf_counter() - t0) / cores
+    h_cpu = int(min(H_PER_PRIM, max(cores, round(1.5 / max(per_hyp, 1e-6) / cores) * cores)))
+
+    def step(seed):
+        for kind in KINDS:
+            orc.ransac_fit(kind, xyz, nrm if kind == 2 else None, thr=THR, max_it=h_cpu, prob=1.0, seed=seed,
+                           omp=True, faithful=True)
+
+    for w in range(args.warmup):
+        step(100 + w)
+    t0 = time.perf_counter()
+    for s in range(args.steps):
+        step(200 + s)
+    dt = time.perf_counter() - t0
+    value = 3 * h_cpu * args.steps / dt
+    sample = (f"{h_cpu} hypotheses per primitive per step (of {H_PER_PRIM}) on the full {N_POINTS}-point cloud, "
+              f"OpenMP loop incl. the per-hypothesis O(N) SelectByIndex pass, {cores} threads")
+    print(json.dumps({
+        "impl": "reference", "metric": "ransac_hypotheses_per_sec", "value": value, "unit": "hypotheses/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "C2: fit_plane+fit_sphere+fit_cylinder, 1M-point cloud, 10k hypotheses each "
+                               "(bounded sample per step)", "n_points": N_POINTS, "threshold": THR,
+                   "probability": 1.0, "hypotheses_per_primitive_per_step": h_cpu},
+        "cpu_baseline": {"value": value, "unit": "hypotheses/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "hypotheses/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "point_hypotheses_per_sec": value * N_POINTS,
+    }))
+
+
+def cpu_baseline(xyz, nrm, budget_s=12.0):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import orc
+    orc.build()
+    cores = orc.omp_threads()
+    t0 = time.perf_counter()
+    orc.ransac_fit(orc.PLANE, xyz, None, thr=THR, max_it=cores, prob=1.0, seed=1, omp=True, faithful=True)
+    per_hyp = (time.perf_counter() - t0) / cores
+    h_cpu = int(min(H_PER_PRIM, max(cores, round(budget_s / 3 / max(per_hyp, 1e-6) / cores) * cores)))
+    res = {}
+    for faithful in (True, False):
+        t0 = time.perf_counter()
+        for kind in KINDS:
+            orc.ransac_fit(kind, xyz, nrm if kind == 2 else None, thr=THR, max_it=h_cpu, prob=1.0, seed=3, omp=True,
+                           faithful=faithful)
+        res[faithful] = 3 * h_cpu / (time.perf_counter() - t0)
+        if not faithful:
+            break
+    return {"value": res[True], "unit": "hypotheses/s", "cores": cores, "kind": "port",
+            "sample": f"{h_cpu} of {H_PER_PRIM} hypotheses per primitive on the full {N_POINTS}-point cloud; oracle "
+                      f"OpenMP loop (ransac.h:571-614) incl. the per-hypothesis O(N) SelectByIndex pass",
+            "lean_value": res.get(False), "lean_note": "same without the SelectByIndex mask pass"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        reference_arm(args, rank, world)
+        return
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import torch.distributed as dist
+    from misc3d_b200 import capi, synth
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    xyz, nrm = synth.make_c2(N_POINTS, SEED)
+    stream = torch.cuda.current_stream()
+    ctx = capi.Context(local_rank, stream=stream.cuda_stream)
+    if world > 1:
+        ids = [capi.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        ctx.init_nccl(ids[0], rank, world)
+    H = H_PER_PRIM * world  # weak scaling: 10k hypotheses per primitive per GPU
+
+    # pinned host copies (e2e leg) and the HBM-resident clouds (value leg)
+    h_xyz = torch.from_numpy(xyz).pin_memory()
+    h_nrm = torch.from_numpy(nrm).pin_memory()
+    np_xyz, np_nrm = h_xyz.numpy(), h_nrm.numpy()
+    cloud = ctx.upload(np_xyz, np_nrm)
+    inl_buf = np.empty(N_POINTS, dtype=np.uint64)
+    flush = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident(seed):
+        out = []
+        for kind in KINDS:
+            rc, model, inl, st = ctx.ransac_fit_cloud(kind, cloud, THR, H, 1.0, seed=seed + kind, inl_buf=inl_buf)
+            out.append((rc, len(inl), st))
+        return out
+
+    def step_e2e(seed):
+        d2h = 0
+        for kind in KINDS:
+            rc, model, inl, st = ctx.ransac_fit(kind, np_xyz, np_nrm if kind == 2 else None, THR, H, 1.0,
+                                                seed=seed + kind)
+            d2h += inl.nbytes + 4 * H
+        return d2h
+
+    # ---------------------------------------------------------------- value: resident cloud
+    for w in range(args.warmup):
+        step_resident(1000 + w)
+    clocks = ClockSampler(local_rank)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    score_ms = {k: [] for k in KINDS}
+    fit_ms = {k: [] for k in KINDS}
+    resolves = 0
+    launches0 = ctx.launches
+    barrier()
+    for s in range(args.steps):
+        flush.fill_(s & 0xFF)  # L2 flush between timed iterations (not timed)
+        barrier()
+        ev[s][0].record(stream)
+        res = step_resident(2000 + 3 * s)
+        ev[s][1].record(stream)
+        for kind, (rc, n_inl, st) in zip(KINDS, res):
+            score_ms[kind].append(st["score_ms"])
+            fit_ms[kind].append(st["device_ms"])
+            resolves += st["exact_resolves"]
+    barrier()
+    launches = ctx.launches - launches0
+    clk = clocks.stop()
+    total_ms = float(sum(a.elapsed_time(b) for a, b in ev))
+    t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    value = 3.0 * H * args.steps / (total_ms * 1e-3)
+
+    # ---------------------------------------------------------------- e2e: host buffers through the C-ABI
+    for w in range(2):
+        step_e2e(3000 + w)
+    barrier()
+    e2e_t0 = time.perf_counter()
+    d2h = 0
+    for s in range(args.steps):
+        d2h = step_e2e(4000 + 3 * s)
+    barrier()
+    e2e_s = time.perf_counter() - e2e_t0
+    t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = 3.0 * H * args.steps / float(t.item())
+    h2d = 3 * xyz.nbytes + nrm.nbytes + (3 + 4 + 2) * 4 * H  # three cloud uploads (+normals once) + sample tables
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---------------------------------------------------------------- roofline of the dominant kernel
+    hbm_peak, which, pk = peaks()
+    ffma_peak = ctx.probe_fp32_ffma()  # FFMA lane-ops/s measured on this device
+    h_local = H // world  # hypotheses one launch scores on this rank
+    per_kind = {}
+    tot_score = sum(np.mean(score_ms[k]) for k in KINDS)
+    for k, name in zip(KINDS, ("plane", "sphere", "cylinder")):
+        ms = float(np.mean(score_ms[k]))
+        units = float(N_POINTS) * h_local
+        per_kind[name] = {"score_kernel_ms": ms, "fit_ms": float(np.mean(fit_ms[k])),
+                          "point_hypotheses_per_sec": units / (ms * 1e-3),
+                          "stream_equiv_GBps": 24.0 * units / (ms * 1e-3) / 1e9,
+                          "ref_fp64_flops_per_sec": FLOPS_PER_UNIT[k] * units / (ms * 1e-3),
+                          "ffma_frac_of_measured": FAST_FFMA_PER_UNIT[k] * units / (ms * 1e-3) / ffma_peak}
+    compulsory = sum(24.0 * N_POINTS + 64.0 * h_local for _ in KINDS)
+    ach = compulsory / (tot_score * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "score_kernel_traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "kernel": "score_kernel (plane+sphere+cylinder launches of one step)",
+                "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": traffic,
+                "peak_source": f"{which} (MEASURED_PEAKS.json hbm_gbs)" if which == "measured" else "fallback",
+                "algorithmic_bytes": "compulsory 24*N + 64*H per launch (SURVEY.md 8d); the kernel is FP32-issue "
+                                     "bound, not HBM bound: see roofline_alu",
+                "stream_equiv_GBps": 24.0 * N_POINTS * h_local * 3 / (tot_score * 1e-3) / 1e9}
+    ffma_ops = sum(FAST_FFMA_PER_UNIT[k] * float(N_POINTS) * h_local for k in KINDS)
+    roofline_alu = {"bound": "fp32-fma-pipe", "achieved": ffma_ops / (tot_score * 1e-3) / 1e12,
+                    "peak": ffma_peak / 1e12, "unit": "TFFMA/s",
+                    "frac": ffma_ops / (tot_score * 1e-3) / ffma_peak,
+                    "note": "FFMA lane-ops of the inner loop (3/4/8 per point-hypothesis) over the FFMA rate measured "
+                            "by m3d_probe_fp32_ffma on this device; compares/counters use the remaining issue slots"}
+
+    cpu = None if args.no_cpu else cpu_baseline(xyz, nrm)
+    line = {
+        "metric": "ransac_hypotheses_per_sec", "value": value, "unit": "hypotheses/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+f64",
+        "data": "synthetic",
+        "config": {"workload": "C2: fit_plane+fit_sphere+fit_cylinder on one 1M-point synthetic cloud, "
+                               f"{H_PER_PRIM} hypotheses per primitive per GPU, probability 1.0 (no early exit)",
+                   "n_points": N_POINTS, "hypotheses_per_primitive": H, "threshold": THR,
+                   "l2": "512 MiB flush write between timed steps", "sharding": f"hypotheses over {world} rank(s)"},
+        "point_hypotheses_per_sec": value * N_POINTS,
+        "e2e": {"value": e2e_value, "unit": "hypotheses/s", "h2d_bytes_per_step": int(h2d),
+                "d2h_bytes_per_step": int(d2h), "api": "m3d_ransac_fit (host buffers, pinned)"},
+        "gpu_launches": int(launches),
+        "clocks": clk,
+        "roofline": roofline, "roofline_alu": roofline_alu, "per_primitive": per_kind,
+        "exact_resolves_per_step": resolves / args.steps,
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

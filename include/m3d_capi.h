@@ -1,0 +1,232 @@
+/*
+ * m3d_capi.h -- C-ABI of libm3d_b200.so: the B200 (sm_100a) implementation of
+ * Misc3D's RANSAC primitive fitting / iterative plane segmentation /
+ * correspondence matching / correspondence-RANSAC registration hot path.
+ *
+ * The reference (yuecideng/Misc3D) has no FFI layer for this path: its boundary
+ * is a C++ class API plus a pybind11 module.  Every entry point below states
+ * the reference interface it replaces (paths relative to the reference tree).
+ * A C++ facade with the reference's class names sits on top of this ABI in
+ * include/misc3d/ and the pybind11 shim in python/ keeps the `misc3d` module
+ * signatures.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; every buffer is caller-owned; the library
+ *    never returns owned memory except opaque handles with a matching *_free;
+ *  - blocking calls; one m3d_ctx per host thread (a ctx owns a CUDA stream,
+ *    its scratch arena and, optionally, a NCCL communicator);
+ *  - return value: M3D_OK (0) or a negative m3d_status; no exceptions cross
+ *    the ABI; m3d_last_error() gives a human-readable message;
+ *  - every function that computes needs a CUDA device: there is NO CPU
+ *    fallback (M3D_ERR_CUDA is returned when no device is usable);
+ *  - point clouds are N x 3 float64 AoS, exactly the memory of the reference's
+ *    std::vector<Eigen::Vector3d> (open3d::geometry::PointCloud::points_);
+ *    descriptors are dim x count float64 column-major (Eigen::MatrixXd /
+ *    open3d Feature::data_); indices are size_t (std::vector<size_t>).
+ */
+#ifndef M3D_CAPI_H_
+#define M3D_CAPI_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define M3D_ABI_VERSION 1
+
+typedef enum m3d_status {
+    M3D_OK = 0,
+    M3D_ERR_INVALID_ARG = -1,    /* null pointer, bad enum, bad capacity                       */
+    M3D_ERR_TOO_FEW_POINTS = -2, /* reference: LogError "Can not fit model due to lack of points"
+                                    (ransac.h:510-513), registration <3 points
+                                    (transform_estimation.cpp:130-133) -> throws               */
+    M3D_ERR_PROBABILITY = -3,    /* reference: SetProbability throws (ransac.h:482-487)        */
+    M3D_ERR_NO_NORMALS = -4,     /* reference: fit_cylinder without normals throws
+                                    (py_common.cpp:50-52, ransac.h:356-359)                    */
+    M3D_ERR_CUDA = -5,           /* CUDA runtime / no device / launch failure                  */
+    M3D_ERR_NCCL = -6,           /* NCCL not loadable or a collective failed                   */
+    M3D_ERR_NO_INLIERS = -7,     /* segmentation round with zero inliers (reference loops
+                                    forever)                              */
+    M3D_ERR_CAPACITY = -8,       /* an output capacity given by the caller is too small        */
+    M3D_ERR_INTERNAL = -9        /* self-check failed (fast count != exact count)              */
+} m3d_status;
+
+typedef enum m3d_primitive { M3D_PLANE = 0, M3D_SPHERE = 1, M3D_CYLINDER = 2 } m3d_primitive;
+
+/* reference: misc3d::registration::MatchMethod (correspondence_matching.h:14-17).  Both values
+ * run the exact brute-force search on the GPU (equal to FLANN up to ties, a superset in quality
+ * of ANNOY); ties resolve to the lowest index. */
+typedef enum m3d_match_method { M3D_MATCH_FLANN = 0, M3D_MATCH_ANNOY = 1 } m3d_match_method;
+
+typedef struct m3d_ctx m3d_ctx;     /* stream + scratch + (optional) communicator */
+typedef struct m3d_cloud m3d_cloud; /* a point cloud resident in HBM              */
+
+/* ------------------------------------------------------------------ context */
+int m3d_abi_version(void);
+/* number of visible CUDA devices (0 when there is no driver / GPU); never fails */
+int m3d_device_count(void);
+int m3d_ctx_create(int device, m3d_ctx **out);
+/* same, but all work is enqueued on a caller-owned cudaStream_t (e.g. torch's current stream) so
+ * that the caller can time it with events recorded on that stream */
+int m3d_ctx_create_on_stream(int device, void *cuda_stream, m3d_ctx **out);
+void m3d_ctx_destroy(m3d_ctx *ctx);
+const char *m3d_last_error(const m3d_ctx *ctx);
+/* cudaStream_t the context launches on */
+void *m3d_ctx_stream(const m3d_ctx *ctx);
+/* kernels launched by this context since creation (bench.py's gpu_launches) */
+uint64_t m3d_ctx_launch_count(const m3d_ctx *ctx);
+/* measured fp32 FFMA issue rate of the device (FFMA lane-operations per second): the ALU roofline
+ * denominator bench.py reports beside the HBM one */
+int m3d_probe_fp32_ffma(m3d_ctx *ctx, double *ffma_per_s);
+
+/* -------- multi-GPU: hypothesis sharding.  rank r scores hypotheses
+ * [r*ceil(H/R), (r+1)*ceil(H/R)) of the SAME global sample table; one all-gather of the per-
+ * hypothesis inlier counts; then every rank replays the identical ordered scan, so results do
+ * not depend on R. */
+#define M3D_NCCL_ID_BYTES 128
+int m3d_nccl_unique_id(char id[M3D_NCCL_ID_BYTES]);
+int m3d_ctx_init_nccl(m3d_ctx *ctx, const char id[M3D_NCCL_ID_BYTES], int rank, int world);
+/* alternative exchange for callers that own the communicator (torch.distributed): the callback
+ * must all-gather `bytes_per_rank` bytes from every rank's `send` into `recv` (rank-major);
+ * both are DEVICE pointers valid on the ctx stream when on_device != 0, host pointers otherwise. */
+typedef int (*m3d_allgather_fn)(void *user, const void *send, void *recv, size_t bytes_per_rank,
+                                int on_device);
+int m3d_ctx_set_exchange(m3d_ctx *ctx, m3d_allgather_fn fn, void *user, int on_device, int rank,
+                         int world);
+
+/* -------------------------------------------------------------- RANSAC fit */
+typedef struct m3d_ransac_params {
+    double threshold;       /* FitModel(threshold, ...) ransac.h:506                         */
+    uint64_t max_iteration; /* SetMaxIteration (ransac.h:495), default 1000 (ransac.h:461)   */
+    double probability;     /* SetProbability (ransac.h:482), default 0.9999 (ransac.h:462); */
+                            /* 1.0 disables the adaptive early exit (ransac.h:601-610)       */
+    uint32_t seed;          /* seed of the mt19937 sample stream; the reference seeds from   */
+                            /* std::random_device (utils.h:74-77)                            */
+    uint32_t flags;         /* M3D_FLAG_*                                                    */
+} m3d_ransac_params;
+
+#define M3D_FLAG_EXACT_ONLY 1u /* score with the fp64 reference-order kernel only (slow; debug) */
+#define M3D_FLAG_NO_REFIT 2u   /* skip RefineModel's GeneralFit (model_out = minimal model)     */
+
+typedef struct m3d_ransac_stats {
+    uint64_t best_index;     /* loop index i of the winning minimal model                      */
+    uint64_t best_count;     /* its inlier count in EvaluateModel (ransac.h:626-654)           */
+    double best_rmse;        /* error / sqrt(count) (ransac.h:650)                             */
+    uint64_t iterations_run; /* `count` printed by ransac.h:616-619                            */
+    uint64_t stop_index;     /* first i skipped by ransac.h:573 (== max_iteration if none)     */
+    uint64_t evaluated;      /* hypotheses the GPU actually scored (>= stop_index)             */
+    uint64_t exact_resolves; /* point-hypothesis pairs decided by the fp64 reference-order path */
+    int32_t found;           /* 1 if any hypothesis ever became best                           */
+    int32_t refit_ok;        /* GeneralFit's return value (ransac.h:548)                       */
+    float device_ms;         /* CUDA-event time of the whole fit on the ctx stream             */
+    float score_ms;          /* CUDA-event time of the scoring kernel(s) alone                 */
+} m3d_ransac_stats;
+
+/* Replaces RANSAC<Estimator,Model,Sampler>::{SetPointCloud, SetProbability, SetMaxIteration,
+ * FitModel} (include/misc3d/common/ransac.h:469-516) and therefore FitPlane / FitSphere /
+ * FitCylinder of python/py_common.cpp:11-67.
+ *   xyz      n x 3 float64 host;  nrm n x 3 float64 host or NULL (required for M3D_CYLINDER)
+ *   model_out  8 doubles (4 used for plane/sphere, 7 for cylinder; rest zero)
+ *   inl_out    capacity n (may be NULL to skip the copy), ascending; *n_inl always written
+ * returns 1 = FitModel true, 0 = FitModel false (no model / GeneralFit failed), <0 = m3d_status */
+int m3d_ransac_fit(m3d_ctx *ctx, int kind, const double *xyz, const double *nrm, size_t n,
+                   const m3d_ransac_params *p, double *model_out, size_t *inl_out, size_t *n_inl,
+                   m3d_ransac_stats *stats);
+
+/* The same against a cloud already resident in HBM (what SetPointCloud's deep copy,
+ * ransac.h:469-475, becomes). */
+int m3d_cloud_upload(m3d_ctx *ctx, const double *xyz, const double *nrm, size_t n, m3d_cloud **out);
+/* d_xyz / d_nrm are DEVICE pointers (n x 3 float64); they are copied, not adopted */
+int m3d_cloud_from_device(m3d_ctx *ctx, const double *d_xyz, const double *d_nrm, size_t n,
+                          m3d_cloud **out);
+void m3d_cloud_free(m3d_cloud *cloud);
+size_t m3d_cloud_size(const m3d_cloud *cloud);
+int m3d_ransac_fit_cloud(m3d_ctx *ctx, int kind, const m3d_cloud *cloud,
+                         const m3d_ransac_params *p, double *model_out, size_t *inl_out,
+                         size_t *n_inl, m3d_ransac_stats *stats);
+
+/* Building blocks (also what the parity tests probe one by one).
+ * models: rows x 8 doubles, valid: rows bytes, counts: rows uint64 (all host).
+ * m3d_score_samples: MinimalFit (ransac.h:138-162 / 239-294 / 354-417) of every row of a caller-
+ * supplied sample table (rows x k uint32, draw order; the kernel re-orders each row ascending as
+ * SelectByIndex does, ransac.h:578) + EvaluateModel's inlier count (ransac.h:626-654). */
+int m3d_score_samples(m3d_ctx *ctx, int kind, const m3d_cloud *cloud, const uint32_t *samples,
+                      size_t rows, double threshold, uint32_t flags, double *models,
+                      uint8_t *valid, uint64_t *counts);
+/* EvaluateModel for one explicit model: count and sum of distances (parallel fp64 sum, or the
+ * reference's sequential index-order sum when sequential != 0). */
+int m3d_evaluate_model(m3d_ctx *ctx, int kind, const m3d_cloud *cloud, const double *model,
+                       double threshold, int sequential, uint64_t *count, double *err);
+
+/* host-only helpers (no GPU needed) --------------------------------------------------------- */
+/* utils.h:81-97 RandomSampler<size_t>::operator() on an mt19937(seed) stream: rows x k, draw order */
+void m3d_sample_table(uint32_t seed, size_t n, int k, size_t rows, uint32_t *out);
+/* ransac.h:572-613 replayed over per-hypothesis results in loop order (the "ordered scan").
+ * counts[i] is the inlier count of hypothesis i, valid[i] MinimalFit's return value.  err may be
+ * NULL; when given, err[i] (sum of inlier distances) breaks count ties as inlier_rmse does.
+ * Fills best_index/best_count/iterations_run/stop_index/found of *st. Returns 0. */
+int m3d_ordered_scan(const uint64_t *counts, const uint8_t *valid, const double *err, size_t rows,
+                     size_t n_points, int k, double probability, uint64_t max_iteration,
+                     m3d_ransac_stats *st);
+
+/* ---------------------------------------------------- iterative segmentation */
+/* Replaces misc3d::segmentation::SegmentPlaneIterative
+ * (src/iterative_plane_segmentation.cpp:7-39; python/py_segmentation.cpp:87-96).
+ *   planes   cap_planes x 4 doubles; labels n entries = plane id or UINT64_MAX
+ *   round r uses sample seed `seed + r` (the reference constructs a new random_device-seeded
+ *   sampler per FitModel, ransac.h:570)
+ * returns M3D_OK, M3D_ERR_TOO_FEW_POINTS (reference throws from ransac.h:510-513 when < 3 points
+ * remain), M3D_ERR_NO_INLIERS, M3D_ERR_CAPACITY.  n < 3 -> M3D_OK with *n_planes = 0 (reference
+ * warns and returns {} at :14-17). */
+int m3d_segment_plane_iterative(m3d_ctx *ctx, const double *xyz, size_t n, double threshold,
+                                int max_iteration, double min_ratio, uint32_t seed,
+                                double *planes, size_t cap_planes, uint64_t *labels,
+                                size_t *n_planes, float *device_ms);
+
+/* --------------------------------------------------- correspondence matching */
+/* Replaces ANNMatcher::Match (src/correspondence_matching.cpp:52-84) / NearestSearch (:13-44);
+ * python match_correspondence (python/py_registration.cpp:73-106).
+ *   src: dim x ns, dst: dim x nd float64 column-major (host); idx0/idx1 capacity ns.
+ * Mutual nearest neighbours in ascending source index. */
+int m3d_match_correspondence(m3d_ctx *ctx, const double *src, size_t ns, const double *dst,
+                             size_t nd, int dim, int method, int n_trees, size_t *idx0,
+                             size_t *idx1, size_t *n_out, float *device_ms);
+/* one direction only: nn[i] = argmin_j |src_i - dst_j|^2 (ties -> lowest j) */
+int m3d_nearest(m3d_ctx *ctx, const double *src, size_t ns, const double *dst, size_t nd, int dim,
+                size_t *nn, float *device_ms);
+
+/* ------------------------------------------------------- RANSAC registration */
+typedef struct m3d_reg_stats {
+    uint64_t best_index;
+    uint64_t best_count;
+    double best_rmse;
+    uint64_t evaluated;  /* hypotheses that passed both checkers (before stop_index) */
+    uint64_t stop_index; /* first itr with itr >= est_k (== max_iter if none)        */
+    float device_ms;
+    float score_ms;
+} m3d_reg_stats;
+
+/* Replaces RANSACSolver::Solve (src/transform_estimation.cpp:124-164), i.e. Open3D's
+ * RegistrationRANSACBasedOnCorrespondence with TransformationEstimationPointToPoint(false),
+ * ransac_n = 3, checkers EdgeLength(edge_thr) + Distance(threshold), criteria(max_iter,
+ * confidence); python compute_transformation_ransac (python/py_registration.cpp:55-67).
+ * T_out: 16 doubles row-major.  Honours edge_thr (the reference's member is self-initialised,
+ * transform_estimation.h:126 -- documented deviation).
+ * returns 1 ok, 0 when Open3D would return its default result (m < 3 or threshold <= 0; T = I),
+ * <0 = m3d_status (M3D_ERR_TOO_FEW_POINTS when a cloud has < 3 points). */
+int m3d_ransac_registration(m3d_ctx *ctx, const double *src_xyz, size_t ns, const double *dst_xyz,
+                            size_t nd, const size_t *c0, const size_t *c1, size_t m,
+                            double threshold, int max_iter, double edge_thr, double confidence,
+                            uint32_t seed, double *T_out, m3d_reg_stats *stats);
+
+/* Replaces LeastSquareSolver::Solve = Eigen::umeyama over all pairs
+ * (src/transform_estimation.cpp:49-66).  src/dst: n x 3 float64 host. */
+int m3d_least_squares_transform(m3d_ctx *ctx, const double *src_xyz, const double *dst_xyz,
+                                size_t n, int with_scaling, double *T_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* M3D_CAPI_H_ */

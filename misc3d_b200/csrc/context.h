@@ -1,0 +1,130 @@
+/*
+ * context.h -- internal: m3d_ctx / m3d_cloud definitions, device buffers, launch accounting.
+ * Not part of the public ABI (include/m3d_capi.h).
+ */
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+
+#include "../../include/m3d_capi.h"
+
+namespace m3d {
+
+/* grow-only device / pinned-host buffer */
+template <bool HOST>
+struct Buf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        release();
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = HOST ? cudaMallocHost(&p, want) : cudaMalloc(&p, want);
+        if (e != cudaSuccess) {
+            p = nullptr;
+            cap = 0;
+            return e;
+        }
+        cap = want;
+        return cudaSuccess;
+    }
+    void release() {
+        if (p) {
+            if (HOST)
+                cudaFreeHost(p);
+            else
+                cudaFree(p);
+        }
+        p = nullptr;
+        cap = 0;
+    }
+    template <class T>
+    T *as() const {
+        return reinterpret_cast<T *>(p);
+    }
+};
+using DevBuf = Buf<false>;
+using PinBuf = Buf<true>;
+
+/* per-cloud constants the kernels read (device resident) */
+struct CloudMeta {
+    double center[3]; /* bounding-box centre; the fp32 copy of the cloud is stored relative to it */
+    double mc;        /* max |centred coordinate| over the cloud                                   */
+    double mraw;      /* max |raw coordinate|                                                      */
+    int nonfinite;    /* 1 if any coordinate is NaN/inf -> fp64 reference-order kernels only       */
+    int pad;
+};
+
+struct NcclApi; /* nccl_dl.cpp */
+
+}  // namespace m3d
+
+struct m3d_cloud {
+    m3d_ctx *ctx = nullptr;
+    size_t n = 0;
+    bool has_normals = false;
+    m3d::DevBuf xyz;   /* n x 3 f64 (reference layout)                         */
+    m3d::DevBuf nrm;   /* n x 3 f64 or empty                                   */
+    m3d::DevBuf pts32; /* n float4: centred fp32 x,y,z and |q|^2 of the centred point */
+    m3d::DevBuf meta;  /* CloudMeta                                            */
+    m3d::CloudMeta h_meta;
+};
+
+struct m3d_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int sm_count = 148;
+    uint64_t launches = 0;
+    std::string err;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+
+    /* scratch (grow-only) */
+    m3d::DevBuf d_samples, d_counts, d_counts_all, d_blk, d_part, d_small, d_inl, d_models, d_valid;
+    m3d::DevBuf d_tmp0, d_tmp1, d_tmp2, d_tmp3, d_tmp4, d_tmp5;
+    m3d::PinBuf h_samples, h_counts, h_small, h_stage;
+
+    /* sharding / exchange */
+    int rank = 0, world = 1;
+    void *nccl_comm = nullptr;
+    m3d_allgather_fn xfn = nullptr;
+    void *xuser = nullptr;
+    int x_on_device = 0;
+
+    int fail(int code, const char *fmt, ...) {
+        char buf[512];
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(buf, sizeof buf, fmt, ap);
+        va_end(ap);
+        err = buf;
+        return code;
+    }
+};
+
+#define M3D_CUDA(ctx, call)                                                                  \
+    do {                                                                                     \
+        cudaError_t e__ = (call);                                                            \
+        if (e__ != cudaSuccess)                                                              \
+            return (ctx)->fail(M3D_ERR_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call,      \
+                               cudaGetErrorString(e__));                                     \
+    } while (0)
+
+#define M3D_LAUNCHED(ctx)                                                                    \
+    do {                                                                                     \
+        (ctx)->launches++;                                                                   \
+        cudaError_t e__ = cudaGetLastError();                                                \
+        if (e__ != cudaSuccess)                                                              \
+            return (ctx)->fail(M3D_ERR_CUDA, "%s:%d kernel launch: %s", __FILE__, __LINE__,  \
+                               cudaGetErrorString(e__));                                     \
+    } while (0)
+
+namespace m3d {
+/* all-gather `bytes_per_rank` bytes per rank of device memory (NCCL or the caller's callback) */
+int exchange_allgather(m3d_ctx *ctx, const void *d_send, void *d_recv, size_t bytes_per_rank);
+}  // namespace m3d

@@ -1,0 +1,665 @@
+/*
+ * ransac.cu -- host orchestration + C-ABI of the RANSAC primitive-fitting path
+ * (reference: include/misc3d/common/ransac.h RANSAC<>::FitModel / FitModelParallel / RefineModel,
+ * src/iterative_plane_segmentation.cpp SegmentPlaneIterative).
+ *
+ * The reference loop is sequential in its semantics (adaptive early exit, strict "better"
+ * comparison in loop order).  Here hypotheses are scored in waves on the GPU; after each wave
+ * the host replays the loop's bookkeeping over the wave's inlier counts in loop order
+ * (scan.h), which reproduces best model / iteration count / stop index exactly.
+ */
+#include <algorithm>
+#include <cmath>
+#include <vector>
+
+#include "context.h"
+#include "ransac_kernels.cuh"
+#include "scan.h"
+
+using namespace m3d;
+
+namespace {
+
+constexpr uint32_t kMaxWave = 1u << 16;
+
+struct SmallDev { /* layout of ctx->d_small */
+    double model[8];    /* minimal model of the hypothesis under refinement          */
+    uint8_t valid[8];   /* its MinimalFit flag                                        */
+    RefineMid mid;      /* pass-2 output                                              */
+    RefineOut out;      /* pass-4 output                                              */
+    double seq_err;     /* seq_err_kernel output                                      */
+    unsigned long long resolves;
+    uint32_t sample[8]; /* one sample row                                             */
+};
+
+int prepare_cloud(m3d_ctx *ctx, m3d_cloud *c) {
+    const uint32_t n = (uint32_t)c->n;
+    M3D_CUDA(ctx, c->pts32.reserve(sizeof(float4) * (size_t)std::max<uint32_t>(n, 1)));
+    M3D_CUDA(ctx, c->meta.reserve(sizeof(CloudMeta)));
+    const int nb = std::max(1, std::min<int>(ctx->sm_count * 8, (int)((n + 255) / 256)));
+    M3D_CUDA(ctx, ctx->d_part.reserve(sizeof(BBoxPart) * (size_t)nb + sizeof(double) * nb));
+    BBoxPart *bp = ctx->d_part.as<BBoxPart>();
+    double *mp = reinterpret_cast<double *>(bp + nb);
+    bbox_kernel<<<nb, 256, 0, ctx->stream>>>(c->xyz.as<double>(), n, bp);
+    M3D_LAUNCHED(ctx);
+    bbox_final_kernel<<<1, 32, 0, ctx->stream>>>(bp, nb, c->meta.as<CloudMeta>());
+    M3D_LAUNCHED(ctx);
+    convert_kernel<<<nb, 256, 0, ctx->stream>>>(c->xyz.as<double>(), n, c->meta.as<CloudMeta>(),
+                                                c->pts32.as<float4>(), mp);
+    M3D_LAUNCHED(ctx);
+    convert_final_kernel<<<1, 32, 0, ctx->stream>>>(mp, nb, c->meta.as<CloudMeta>());
+    M3D_LAUNCHED(ctx);
+    M3D_CUDA(ctx, cudaMemcpyAsync(&c->h_meta, c->meta.p, sizeof(CloudMeta), cudaMemcpyDeviceToHost, ctx->stream));
+    M3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return M3D_OK;
+}
+
+int cloud_create(m3d_ctx *ctx, const double *xyz, const double *nrm, size_t n, cudaMemcpyKind kind,
+                 m3d_cloud **out) {
+    if (!ctx || !out || (n && !xyz)) return M3D_ERR_INVALID_ARG;
+    if (n >= (size_t)kInvalidBit) return ctx->fail(M3D_ERR_INVALID_ARG, "clouds of >= 2^31 points are not supported");
+    M3D_CUDA(ctx, cudaSetDevice(ctx->device));
+    m3d_cloud *c = new m3d_cloud();
+    c->ctx = ctx;
+    c->n = n;
+    c->has_normals = nrm != nullptr;
+    auto fail = [&](int rc) {
+        m3d_cloud_free(c);
+        return rc;
+    };
+    const size_t bytes = sizeof(double) * 3 * std::max<size_t>(n, 1);
+    if (c->xyz.reserve(bytes) != cudaSuccess) return fail(ctx->fail(M3D_ERR_CUDA, "cudaMalloc(%zu) failed", bytes));
+    if (nrm && c->nrm.reserve(bytes) != cudaSuccess) return fail(ctx->fail(M3D_ERR_CUDA, "cudaMalloc(%zu) failed", bytes));
+    if (n) {
+        if (cudaMemcpyAsync(c->xyz.p, xyz, sizeof(double) * 3 * n, kind, ctx->stream) != cudaSuccess)
+            return fail(ctx->fail(M3D_ERR_CUDA, "copy of the cloud failed"));
+        if (nrm && cudaMemcpyAsync(c->nrm.p, nrm, sizeof(double) * 3 * n, kind, ctx->stream) != cudaSuccess)
+            return fail(ctx->fail(M3D_ERR_CUDA, "copy of the normals failed"));
+    }
+    const int rc = prepare_cloud(ctx, c);
+    if (rc != M3D_OK) return fail(rc);
+    *out = c;
+    return M3D_OK;
+}
+
+/* ---- launch of the hot kernel for one (wave, kind) */
+template <int KIND, int THREADS, int HPT>
+int launch_score_t(m3d_ctx *ctx, const ScoreArgs &a, uint32_t ntiles) {
+    const size_t smem = (size_t)kStages * kTile * sizeof(float4) + kStages * sizeof(uint64_t);
+    M3D_CUDA(ctx, cudaFuncSetAttribute(score_kernel<KIND, THREADS, HPT>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const uint32_t hb = (a.rows + THREADS * HPT - 1) / (THREADS * HPT);
+    /* point chunks: enough CTAs for >= ~8 balanced waves over the SMs, each chunk a whole number
+     * of tiles.  Grid = hypothesis blocks x point chunks, chunks a multiple of the SM count. */
+    const uint32_t resident = (uint32_t)ctx->sm_count * (THREADS >= 256 ? 2u : 4u);
+    uint32_t chunks = std::max<uint32_t>(1, (8 * resident + hb - 1) / hb);
+    chunks = ((chunks + ctx->sm_count - 1) / ctx->sm_count) * ctx->sm_count;
+    chunks = std::min(chunks, ntiles);
+    ScoreArgs b = a;
+    b.chunk_tiles = (ntiles + chunks - 1) / chunks;
+    chunks = (ntiles + b.chunk_tiles - 1) / b.chunk_tiles;
+    dim3 grid(hb, chunks);
+    score_kernel<KIND, THREADS, HPT><<<grid, THREADS, smem, ctx->stream>>>(b);
+    M3D_LAUNCHED(ctx);
+    return M3D_OK;
+}
+
+template <int KIND>
+int launch_score(m3d_ctx *ctx, const m3d_cloud *c, ScoreArgs a, bool exact_only) {
+    const uint32_t ntiles = std::max<uint32_t>(1, (a.n + kTile - 1) / kTile);
+    if (exact_only || c->h_meta.nonfinite) {
+        const uint32_t hb = (a.rows + 127) / 128;
+        uint32_t chunks = std::min<uint32_t>(ntiles, std::max<uint32_t>(1, (4u * ctx->sm_count * 4u) / hb));
+        a.chunk_tiles = (ntiles + chunks - 1) / chunks;
+        chunks = (ntiles + a.chunk_tiles - 1) / a.chunk_tiles;
+        score_exact_kernel<KIND><<<dim3(hb, chunks), 128, 0, ctx->stream>>>(a);
+        M3D_LAUNCHED(ctx);
+        return M3D_OK;
+    }
+    if (a.rows >= 2048) return launch_score_t<KIND, 256, 2>(ctx, a, ntiles);
+    return launch_score_t<KIND, 128, 1>(ctx, a, ntiles);
+}
+
+int launch_score_kind(m3d_ctx *ctx, int kind, const m3d_cloud *c, const ScoreArgs &a, bool exact_only) {
+    switch (kind) {
+        case kPlane:
+            return launch_score<kPlane>(ctx, c, a, exact_only);
+        case kSphere:
+            return launch_score<kSphere>(ctx, c, a, exact_only);
+        default:
+            return launch_score<kCylinder>(ctx, c, a, exact_only);
+    }
+}
+
+/* ---- RefineModel passes */
+struct RefineBufs {
+    uint32_t nblk;
+    uint32_t *blk_cnt, *blk_off;
+    double *blk_part, *blk_mom;
+};
+int refine_bufs(m3d_ctx *ctx, uint32_t n, RefineBufs *rb) {
+    rb->nblk = std::max<uint32_t>(1, (n + kRBlockPts - 1) / kRBlockPts);
+    const size_t per = 2 * sizeof(uint32_t) + 14 * sizeof(double);
+    M3D_CUDA(ctx, ctx->d_blk.reserve(per * rb->nblk + 64));
+    char *p = ctx->d_blk.as<char>();
+    rb->blk_part = reinterpret_cast<double *>(p);
+    rb->blk_mom = rb->blk_part + 4 * (size_t)rb->nblk;
+    rb->blk_cnt = reinterpret_cast<uint32_t *>(rb->blk_mom + 10 * (size_t)rb->nblk);
+    rb->blk_off = rb->blk_cnt + rb->nblk;
+    return M3D_OK;
+}
+
+template <int KIND>
+int count_pass(m3d_ctx *ctx, const double *xyz, uint32_t n, const double *d_model, double thr,
+               const RefineBufs &rb, RefineMid *d_mid) {
+    refine_count_kernel<KIND><<<rb.nblk, kRB, 0, ctx->stream>>>(xyz, n, d_model, thr, rb.blk_cnt, rb.blk_part);
+    M3D_LAUNCHED(ctx);
+    refine_scan_kernel<<<1, 1024, 0, ctx->stream>>>(rb.blk_cnt, rb.blk_part, rb.nblk, rb.blk_off, d_mid);
+    M3D_LAUNCHED(ctx);
+    return M3D_OK;
+}
+template <int KIND, bool SEG>
+int write_pass(m3d_ctx *ctx, const double *xyz, uint32_t n, const double *d_model, double thr,
+               const RefineBufs &rb, const RefineMid *d_mid, unsigned long long *d_inl, RefineOut *d_out,
+               const SegArgs &seg) {
+    refine_write_kernel<KIND, SEG><<<rb.nblk, kRB, 0, ctx->stream>>>(xyz, n, d_model, thr, rb.blk_off, d_mid,
+                                                                    d_inl, rb.blk_mom, seg);
+    M3D_LAUNCHED(ctx);
+    refine_final_kernel<KIND><<<1, 256, 0, ctx->stream>>>(rb.blk_mom, rb.nblk, d_mid, d_model, d_out);
+    M3D_LAUNCHED(ctx);
+    return M3D_OK;
+}
+int count_pass_kind(m3d_ctx *ctx, int kind, const double *xyz, uint32_t n, const double *d_model, double thr,
+                    const RefineBufs &rb, RefineMid *d_mid) {
+    switch (kind) {
+        case kPlane:
+            return count_pass<kPlane>(ctx, xyz, n, d_model, thr, rb, d_mid);
+        case kSphere:
+            return count_pass<kSphere>(ctx, xyz, n, d_model, thr, rb, d_mid);
+        default:
+            return count_pass<kCylinder>(ctx, xyz, n, d_model, thr, rb, d_mid);
+    }
+}
+int write_pass_kind(m3d_ctx *ctx, int kind, const double *xyz, uint32_t n, const double *d_model, double thr,
+                    const RefineBufs &rb, const RefineMid *d_mid, unsigned long long *d_inl, RefineOut *d_out) {
+    SegArgs none{};
+    switch (kind) {
+        case kPlane:
+            return write_pass<kPlane, false>(ctx, xyz, n, d_model, thr, rb, d_mid, d_inl, d_out, none);
+        case kSphere:
+            return write_pass<kSphere, false>(ctx, xyz, n, d_model, thr, rb, d_mid, d_inl, d_out, none);
+        default:
+            return write_pass<kCylinder, false>(ctx, xyz, n, d_model, thr, rb, d_mid, d_inl, d_out, none);
+    }
+}
+int fit_rows_kind(m3d_ctx *ctx, int kind, const double *xyz, const double *nrm, const uint32_t *d_samples,
+                  uint32_t rows, double *d_models, uint8_t *d_valid) {
+    const int nb = (rows + 127) / 128;
+    switch (kind) {
+        case kPlane:
+            minimal_fit_rows_kernel<kPlane><<<nb, 128, 0, ctx->stream>>>(xyz, nrm, d_samples, rows, d_models, d_valid);
+            break;
+        case kSphere:
+            minimal_fit_rows_kernel<kSphere><<<nb, 128, 0, ctx->stream>>>(xyz, nrm, d_samples, rows, d_models, d_valid);
+            break;
+        default:
+            minimal_fit_rows_kernel<kCylinder><<<nb, 128, 0, ctx->stream>>>(xyz, nrm, d_samples, rows, d_models, d_valid);
+    }
+    M3D_LAUNCHED(ctx);
+    return M3D_OK;
+}
+int seq_err_kind(m3d_ctx *ctx, int kind, const double *xyz, const unsigned long long *d_inl,
+                 unsigned long long n_inl, const double *d_model, double *d_out) {
+    switch (kind) {
+        case kPlane:
+            seq_err_kernel<kPlane><<<1, 32, 0, ctx->stream>>>(xyz, d_inl, n_inl, d_model, d_out);
+            break;
+        case kSphere:
+            seq_err_kernel<kSphere><<<1, 32, 0, ctx->stream>>>(xyz, d_inl, n_inl, d_model, d_out);
+            break;
+        default:
+            seq_err_kernel<kCylinder><<<1, 32, 0, ctx->stream>>>(xyz, d_inl, n_inl, d_model, d_out);
+    }
+    M3D_LAUNCHED(ctx);
+    return M3D_OK;
+}
+
+/* The device view of a cloud the fit runs on (segmentation swaps these between rounds). */
+struct CloudView {
+    const double *xyz;
+    const double *nrm;
+    const float4 *pts32;
+    const CloudMeta *meta;
+    uint32_t n;
+    bool nonfinite;
+};
+
+/* one full FitModel on a device-resident cloud.  On return the minimal best model sits in
+ * d_small->model, pass 1+2 results in d_small->mid, and (when `seg` is null) the ascending
+ * inlier indices in ctx->d_inl and the refined model in d_small->out. */
+struct FitResult {
+    m3d_ransac_stats st;
+    double minimal[8];
+    double refined[8];
+    unsigned long long n_inl;
+    int ret;
+};
+
+int fit_view(m3d_ctx *ctx, int kind, const m3d_cloud *cloud_for_flags, const CloudView &v,
+             const m3d_ransac_params &p, SegArgs *seg, FitResult *res) {
+    const int k = sample_size(kind);
+    const uint64_t H = p.max_iteration;
+    const uint32_t n = v.n;
+    const bool exact_only = (p.flags & M3D_FLAG_EXACT_ONLY) != 0 || v.nonfinite;
+    memset(res, 0, sizeof *res);
+    res->st.stop_index = H;
+
+    M3D_CUDA(ctx, ctx->d_small.reserve(sizeof(SmallDev)));
+    M3D_CUDA(ctx, ctx->h_small.reserve(sizeof(SmallDev)));
+    SmallDev *ds = ctx->d_small.as<SmallDev>();
+    SmallDev *hs = ctx->h_small.as<SmallDev>();
+    RefineBufs rb;
+    if (int rc = refine_bufs(ctx, n, &rb)) return rc;
+    M3D_CUDA(ctx, ctx->d_inl.reserve(sizeof(unsigned long long) * (size_t)std::max<uint32_t>(n, 1)));
+    M3D_CUDA(ctx, cudaMemsetAsync(&ds->resolves, 0, sizeof(unsigned long long), ctx->stream));
+
+    cudaEvent_t ev_a = ctx->ev[0], ev_b = ctx->ev[1], ev_s0 = ctx->ev[2], ev_s1 = ctx->ev[3];
+    M3D_CUDA(ctx, cudaEventRecord(ev_a, ctx->stream));
+
+    SampleStream stream(p.seed, n);
+    std::vector<uint32_t> table; /* all rows drawn so far (draw order) */
+    OrderedScan scan(n, k, p.probability, H);
+    float score_ms = 0;
+    uint64_t evaluated = 0;
+
+    /* evaluates hypothesis `row` alone (tie-breaks, final best): model -> ds->model, then
+     * pass 1+2 -> ds->mid; optionally the index-order error */
+    auto eval_row = [&](uint64_t row, bool exact, uint64_t expect_cnt, double *rmse) -> int {
+        M3D_CUDA(ctx, cudaMemcpyAsync(ds->sample, &table[(size_t)row * k], sizeof(uint32_t) * k,
+                                      cudaMemcpyHostToDevice, ctx->stream));
+        if (int rc = fit_rows_kind(ctx, kind, v.xyz, v.nrm, ds->sample, 1, ds->model, ds->valid)) return rc;
+        if (int rc = count_pass_kind(ctx, kind, v.xyz, n, ds->model, p.threshold, rb, &ds->mid)) return rc;
+        if (exact) {
+            RefineOut *scratch_out = &ds->out;
+            if (int rc = write_pass_kind(ctx, kind, v.xyz, n, ds->model, p.threshold, rb, &ds->mid,
+                                         ctx->d_inl.as<unsigned long long>(), scratch_out))
+                return rc;
+            if (int rc = seq_err_kind(ctx, kind, v.xyz, ctx->d_inl.as<unsigned long long>(), expect_cnt,
+                                      ds->model, &ds->seq_err))
+                return rc;
+        }
+        M3D_CUDA(ctx, cudaMemcpyAsync(hs, ds, sizeof(SmallDev), cudaMemcpyDeviceToHost, ctx->stream));
+        M3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (hs->mid.n_inl != expect_cnt)
+            return ctx->fail(M3D_ERR_INTERNAL, "hypothesis %llu: scoring kernel counted %llu inliers, fp64 pass %llu",
+                             (unsigned long long)row, (unsigned long long)expect_cnt,
+                             (unsigned long long)hs->mid.n_inl);
+        const double e = exact ? hs->seq_err : hs->mid.err;
+        *rmse = expect_cnt ? e / std::sqrt((double)expect_cnt) : 1e10;
+        return 0;
+    };
+
+    const int R = ctx->world, rank = ctx->rank;
+    uint64_t done = 0;
+    uint32_t wave = (p.probability >= 1.0) ? kMaxWave : 256;
+    int rc_scan = 0;
+    while (done < H && !scan.stopped) {
+        const uint32_t rows = (uint32_t)std::min<uint64_t>(wave, H - done);
+        /* sample rows of this wave (host: the mt19937 stream is inherently serial) */
+        table.resize((size_t)(done + rows) * k);
+        for (uint32_t r = 0; r < rows; ++r) stream.draw(k, &table[(size_t)(done + r) * k]);
+        M3D_CUDA(ctx, ctx->h_samples.reserve(sizeof(uint32_t) * (size_t)rows * k));
+        memcpy(ctx->h_samples.p, &table[(size_t)done * k], sizeof(uint32_t) * (size_t)rows * k);
+        M3D_CUDA(ctx, ctx->d_samples.reserve(sizeof(uint32_t) * (size_t)rows * k));
+        M3D_CUDA(ctx, cudaMemcpyAsync(ctx->d_samples.p, ctx->h_samples.p, sizeof(uint32_t) * (size_t)rows * k,
+                                      cudaMemcpyHostToDevice, ctx->stream));
+        /* shard: rank r scores rows [r*S, (r+1)*S) of the wave */
+        const uint32_t S = (rows + R - 1) / R;
+        const uint32_t my0 = std::min<uint32_t>(rows, (uint32_t)rank * S);
+        const uint32_t my1 = std::min<uint32_t>(rows, my0 + S);
+        M3D_CUDA(ctx, ctx->d_counts.reserve(sizeof(uint32_t) * (size_t)S));
+        M3D_CUDA(ctx, ctx->d_counts_all.reserve(sizeof(uint32_t) * (size_t)S * R));
+        M3D_CUDA(ctx, cudaMemsetAsync(ctx->d_counts.p, 0, sizeof(uint32_t) * (size_t)S, ctx->stream));
+        M3D_CUDA(ctx, cudaEventRecord(ev_s0, ctx->stream));
+        if (my1 > my0) {
+            ScoreArgs a{};
+            a.pts32 = v.pts32;
+            a.xyz = v.xyz;
+            a.nrm = v.nrm;
+            a.meta = v.meta;
+            a.samples = ctx->d_samples.as<uint32_t>();
+            a.counts = ctx->d_counts.as<uint32_t>();
+            a.resolves = &ds->resolves;
+            a.thr = p.threshold;
+            a.n = n;
+            a.row_begin = my0;
+            a.rows = my1 - my0;
+            if (int rc = launch_score_kind(ctx, kind, cloud_for_flags, a, exact_only)) return rc;
+        }
+        M3D_CUDA(ctx, cudaEventRecord(ev_s1, ctx->stream));
+        const uint32_t *d_all = ctx->d_counts.as<uint32_t>();
+        if (R > 1) {
+            if (int rc = exchange_allgather(ctx, ctx->d_counts.p, ctx->d_counts_all.p, sizeof(uint32_t) * (size_t)S))
+                return rc;
+            d_all = ctx->d_counts_all.as<uint32_t>();
+        }
+        M3D_CUDA(ctx, ctx->h_counts.reserve(sizeof(uint32_t) * (size_t)S * R));
+        M3D_CUDA(ctx, cudaMemcpyAsync(ctx->h_counts.p, d_all, sizeof(uint32_t) * (size_t)S * R,
+                                      cudaMemcpyDeviceToHost, ctx->stream));
+        M3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        float ms = 0;
+        cudaEventElapsedTime(&ms, ev_s0, ev_s1);
+        score_ms += ms;
+        evaluated += rows;
+
+        const uint32_t *hc = ctx->h_counts.as<uint32_t>();
+        for (uint32_t r = 0; r < rows && !scan.stopped; ++r) {
+            const uint32_t raw = hc[r]; /* shards are contiguous: rank-major == row order */
+            const bool valid = (raw & kInvalidBit) == 0;
+            const uint64_t cnt = raw & ~kInvalidBit;
+            scan.step(done + r, valid, cnt, [&](uint64_t j, bool exact, double *rmse) {
+                const uint32_t rawj = (j >= done) ? hc[j - done] : 0;
+                const uint64_t cj = (j == scan.best_index && scan.found) ? scan.best_count : (uint64_t)(rawj & ~kInvalidBit);
+                const int rc = eval_row(j, exact, cj, rmse);
+                if (rc) rc_scan = rc;
+                return rc;
+            });
+            if (rc_scan) return rc_scan;
+        }
+        done += rows;
+        if (wave < kMaxWave) wave = std::min<uint32_t>(kMaxWave, wave * 4);
+    }
+    if (!scan.stopped && done >= H) {
+        /* the loop ran to max_iteration; the reference checks `count > current_iteration` only at
+         * the top of an iteration, so nothing more to do */
+    }
+    scan.fill(&res->st);
+    res->st.evaluated = evaluated;
+    res->st.score_ms = score_ms;
+
+    int ret = 0;
+    if (scan.found) {
+        /* RefineModel (ransac.h:534-549) on the winning minimal model */
+        const uint64_t bi = scan.best_index;
+        M3D_CUDA(ctx, cudaMemcpyAsync(ds->sample, &table[(size_t)bi * k], sizeof(uint32_t) * k,
+                                      cudaMemcpyHostToDevice, ctx->stream));
+        if (int rc = fit_rows_kind(ctx, kind, v.xyz, v.nrm, ds->sample, 1, ds->model, ds->valid)) return rc;
+        if (int rc = count_pass_kind(ctx, kind, v.xyz, n, ds->model, p.threshold, rb, &ds->mid)) return rc;
+        if (seg) {
+            if (int rc = write_pass<kPlane, true>(ctx, v.xyz, n, ds->model, p.threshold, rb, &ds->mid,
+                                                  ctx->d_inl.as<unsigned long long>(), &ds->out, *seg))
+                return rc;
+        } else {
+            if (int rc = write_pass_kind(ctx, kind, v.xyz, n, ds->model, p.threshold, rb, &ds->mid,
+                                         ctx->d_inl.as<unsigned long long>(), &ds->out))
+                return rc;
+        }
+        M3D_CUDA(ctx, cudaMemcpyAsync(hs, ds, sizeof(SmallDev), cudaMemcpyDeviceToHost, ctx->stream));
+        M3D_CUDA(ctx, cudaEventRecord(ev_b, ctx->stream));
+        M3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (hs->mid.n_inl != scan.best_count)
+            return ctx->fail(M3D_ERR_INTERNAL, "best hypothesis %llu: scoring kernel counted %llu inliers, fp64 pass %llu",
+                             (unsigned long long)bi, (unsigned long long)scan.best_count,
+                             (unsigned long long)hs->mid.n_inl);
+        res->n_inl = hs->mid.n_inl;
+        memcpy(res->minimal, hs->model, sizeof res->minimal);
+        const bool refit = (p.flags & M3D_FLAG_NO_REFIT) == 0;
+        memcpy(res->refined, refit ? hs->out.model : hs->model, sizeof res->refined);
+        res->st.refit_ok = refit ? hs->out.ok : 1;
+        if (!(scan.best_rmse_known && scan.best_rmse_exact && scan.best_index == bi && scan.best_rmse != 0))
+            res->st.best_rmse = hs->mid.err / std::sqrt((double)hs->mid.n_inl);
+        res->st.exact_resolves = hs->resolves;
+        ret = res->st.refit_ok;
+    } else {
+        M3D_CUDA(ctx, cudaMemcpyAsync(&hs->resolves, &ds->resolves, sizeof(unsigned long long),
+                                      cudaMemcpyDeviceToHost, ctx->stream));
+        M3D_CUDA(ctx, cudaEventRecord(ev_b, ctx->stream));
+        M3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        res->st.exact_resolves = hs->resolves;
+    }
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ev_a, ev_b);
+    res->st.device_ms = ms;
+    res->ret = ret;
+    return M3D_OK;
+}
+
+int check_params(m3d_ctx *ctx, int kind, size_t n, bool has_normals, const m3d_ransac_params *p) {
+    if (!p) return ctx->fail(M3D_ERR_INVALID_ARG, "null params");
+    if (kind < 0 || kind > 2) return ctx->fail(M3D_ERR_INVALID_ARG, "unknown primitive %d", kind);
+    if (!(p->probability > 0 && p->probability <= 1))
+        return ctx->fail(M3D_ERR_PROBABILITY, "Probability must be > 0 or <= 1.0"); /* ransac.h:483-485 */
+    if (kind == kCylinder && !has_normals)
+        return ctx->fail(M3D_ERR_NO_NORMALS, "Fit cylinder requires normals."); /* py_common.cpp:50-52 */
+    if (n < (size_t)sample_size(kind))
+        return ctx->fail(M3D_ERR_TOO_FEW_POINTS, "Can not fit model due to lack of points"); /* ransac.h:510-513 */
+    return M3D_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int m3d_cloud_upload(m3d_ctx *ctx, const double *xyz, const double *nrm, size_t n, m3d_cloud **out) {
+    return cloud_create(ctx, xyz, nrm, n, cudaMemcpyHostToDevice, out);
+}
+int m3d_cloud_from_device(m3d_ctx *ctx, const double *d_xyz, const double *d_nrm, size_t n, m3d_cloud **out) {
+    return cloud_create(ctx, d_xyz, d_nrm, n, cudaMemcpyDeviceToDevice, out);
+}
+void m3d_cloud_free(m3d_cloud *c) {
+    if (!c) return;
+    if (c->ctx) cudaStreamSynchronize(c->ctx->stream);
+    c->xyz.release();
+    c->nrm.release();
+    c->pts32.release();
+    c->meta.release();
+    delete c;
+}
+size_t m3d_cloud_size(const m3d_cloud *c) { return c ? c->n : 0; }
+
+int m3d_ransac_fit_cloud(m3d_ctx *ctx, int kind, const m3d_cloud *cloud, const m3d_ransac_params *p,
+                         double *model_out, size_t *inl_out, size_t *n_inl, m3d_ransac_stats *stats) {
+    if (!ctx || !cloud || !model_out || !n_inl) return M3D_ERR_INVALID_ARG;
+    for (int i = 0; i < 8; ++i) model_out[i] = 0;
+    *n_inl = 0;
+    if (stats) memset(stats, 0, sizeof *stats);
+    if (int rc = check_params(ctx, kind, cloud->n, cloud->has_normals, p)) return rc;
+    M3D_CUDA(ctx, cudaSetDevice(ctx->device));
+    CloudView v{cloud->xyz.as<double>(), cloud->has_normals ? cloud->nrm.as<double>() : nullptr,
+                cloud->pts32.as<float4>(), cloud->meta.as<CloudMeta>(), (uint32_t)cloud->n,
+                cloud->h_meta.nonfinite != 0};
+    FitResult res;
+    if (int rc = fit_view(ctx, kind, cloud, v, *p, nullptr, &res)) return rc;
+    if (stats) *stats = res.st;
+    if (res.st.found) {
+        /* model = refined parameters, inliers = those of the minimal model (ransac.h:621-622) */
+        for (int i = 0; i < param_count(kind); ++i) model_out[i] = res.refined[i];
+        *n_inl = (size_t)res.n_inl;
+        if (inl_out && res.n_inl) {
+            static_assert(sizeof(size_t) == sizeof(unsigned long long), "size_t must be 64-bit");
+            M3D_CUDA(ctx, cudaMemcpyAsync(inl_out, ctx->d_inl.p, sizeof(size_t) * (size_t)res.n_inl,
+                                          cudaMemcpyDeviceToHost, ctx->stream));
+            M3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        }
+    }
+    return res.ret;
+}
+
+int m3d_ransac_fit(m3d_ctx *ctx, int kind, const double *xyz, const double *nrm, size_t n,
+                   const m3d_ransac_params *p, double *model_out, size_t *inl_out, size_t *n_inl,
+                   m3d_ransac_stats *stats) {
+    if (!ctx || !model_out || !n_inl) return M3D_ERR_INVALID_ARG;
+    for (int i = 0; i < 8; ++i) model_out[i] = 0;
+    *n_inl = 0;
+    if (stats) memset(stats, 0, sizeof *stats);
+    if (int rc = check_params(ctx, kind, n, nrm != nullptr, p)) return rc;
+    m3d_cloud *c = nullptr;
+    if (int rc = m3d_cloud_upload(ctx, xyz, nrm, n, &c)) return rc;
+    const int rc = m3d_ransac_fit_cloud(ctx, kind, c, p, model_out, inl_out, n_inl, stats);
+    m3d_cloud_free(c);
+    return rc;
+}
+
+int m3d_score_samples(m3d_ctx *ctx, int kind, const m3d_cloud *cloud, const uint32_t *samples, size_t rows,
+                      double threshold, uint32_t flags, double *models, uint8_t *valid, uint64_t *counts) {
+    if (!ctx || !cloud || !samples || !counts) return M3D_ERR_INVALID_ARG;
+    if (kind < 0 || kind > 2) return ctx->fail(M3D_ERR_INVALID_ARG, "unknown primitive %d", kind);
+    if (kind == kCylinder && !cloud->has_normals) return ctx->fail(M3D_ERR_NO_NORMALS, "Fit cylinder requires normals.");
+    if (cloud->n < (size_t)sample_size(kind)) return ctx->fail(M3D_ERR_TOO_FEW_POINTS, "Can not fit model due to lack of points");
+    if (rows == 0) return M3D_OK;
+    if (rows >= (1u << 30)) return ctx->fail(M3D_ERR_INVALID_ARG, "too many rows");
+    M3D_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int k = sample_size(kind);
+    M3D_CUDA(ctx, ctx->d_samples.reserve(sizeof(uint32_t) * rows * k));
+    M3D_CUDA(ctx, ctx->d_counts.reserve(sizeof(uint32_t) * rows));
+    M3D_CUDA(ctx, ctx->h_counts.reserve(sizeof(uint32_t) * rows));
+    M3D_CUDA(ctx, ctx->d_models.reserve(sizeof(double) * 8 * rows));
+    M3D_CUDA(ctx, ctx->d_valid.reserve(rows));
+    M3D_CUDA(ctx, ctx->d_small.reserve(sizeof(SmallDev)));
+    SmallDev *ds = ctx->d_small.as<SmallDev>();
+    M3D_CUDA(ctx, cudaMemcpyAsync(ctx->d_samples.p, samples, sizeof(uint32_t) * rows * k, cudaMemcpyHostToDevice, ctx->stream));
+    M3D_CUDA(ctx, cudaMemsetAsync(ctx->d_counts.p, 0, sizeof(uint32_t) * rows, ctx->stream));
+    M3D_CUDA(ctx, cudaMemsetAsync(&ds->resolves, 0, sizeof(unsigned long long), ctx->stream));
+    ScoreArgs a{};
+    a.pts32 = cloud->pts32.as<float4>();
+    a.xyz = cloud->xyz.as<double>();
+    a.nrm = cloud->has_normals ? cloud->nrm.as<double>() : nullptr;
+    a.meta = cloud->meta.as<CloudMeta>();
+    a.samples = ctx->d_samples.as<uint32_t>();
+    a.counts = ctx->d_counts.as<uint32_t>();
+    a.resolves = &ds->resolves;
+    a.thr = threshold;
+    a.n = (uint32_t)cloud->n;
+    a.row_begin = 0;
+    a.rows = (uint32_t)rows;
+    if (int rc = launch_score_kind(ctx, kind, cloud, a, (flags & M3D_FLAG_EXACT_ONLY) != 0)) return rc;
+    if (models || valid) {
+        if (int rc = fit_rows_kind(ctx, kind, a.xyz, a.nrm, a.samples, a.rows, ctx->d_models.as<double>(),
+                                   ctx->d_valid.as<uint8_t>()))
+            return rc;
+        if (models)
+            M3D_CUDA(ctx, cudaMemcpyAsync(models, ctx->d_models.p, sizeof(double) * 8 * rows, cudaMemcpyDeviceToHost, ctx->stream));
+        if (valid) M3D_CUDA(ctx, cudaMemcpyAsync(valid, ctx->d_valid.p, rows, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    M3D_CUDA(ctx, cudaMemcpyAsync(ctx->h_counts.p, ctx->d_counts.p, sizeof(uint32_t) * rows, cudaMemcpyDeviceToHost, ctx->stream));
+    M3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    const uint32_t *hc = ctx->h_counts.as<uint32_t>();
+    for (size_t r = 0; r < rows; ++r) counts[r] = hc[r] & ~kInvalidBit;
+    return M3D_OK;
+}
+
+int m3d_evaluate_model(m3d_ctx *ctx, int kind, const m3d_cloud *cloud, const double *model, double threshold,
+                       int sequential, uint64_t *count, double *err) {
+    if (!ctx || !cloud || !model || !count) return M3D_ERR_INVALID_ARG;
+    if (kind < 0 || kind > 2) return ctx->fail(M3D_ERR_INVALID_ARG, "unknown primitive %d", kind);
+    M3D_CUDA(ctx, cudaSetDevice(ctx->device));
+    const uint32_t n = (uint32_t)cloud->n;
+    M3D_CUDA(ctx, ctx->d_small.reserve(sizeof(SmallDev)));
+    M3D_CUDA(ctx, ctx->h_small.reserve(sizeof(SmallDev)));
+    SmallDev *ds = ctx->d_small.as<SmallDev>();
+    SmallDev *hs = ctx->h_small.as<SmallDev>();
+    RefineBufs rb;
+    if (int rc = refine_bufs(ctx, n, &rb)) return rc;
+    M3D_CUDA(ctx, ctx->d_inl.reserve(sizeof(unsigned long long) * (size_t)std::max<uint32_t>(n, 1)));
+    double m8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int i = 0; i < param_count(kind); ++i) m8[i] = model[i];
+    M3D_CUDA(ctx, cudaMemcpyAsync(ds->model, m8, sizeof m8, cudaMemcpyHostToDevice, ctx->stream));
+    if (int rc = count_pass_kind(ctx, kind, cloud->xyz.as<double>(), n, ds->model, threshold, rb, &ds->mid)) return rc;
+    if (sequential) {
+        if (int rc = write_pass_kind(ctx, kind, cloud->xyz.as<double>(), n, ds->model, threshold, rb, &ds->mid,
+                                     ctx->d_inl.as<unsigned long long>(), &ds->out))
+            return rc;
+        M3D_CUDA(ctx, cudaMemcpyAsync(hs, ds, sizeof(SmallDev), cudaMemcpyDeviceToHost, ctx->stream));
+        M3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (int rc = seq_err_kind(ctx, kind, cloud->xyz.as<double>(), ctx->d_inl.as<unsigned long long>(),
+                                  hs->mid.n_inl, ds->model, &ds->seq_err))
+            return rc;
+    }
+    M3D_CUDA(ctx, cudaMemcpyAsync(hs, ds, sizeof(SmallDev), cudaMemcpyDeviceToHost, ctx->stream));
+    M3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *count = hs->mid.n_inl;
+    if (err) *err = sequential ? hs->seq_err : hs->mid.err;
+    return M3D_OK;
+}
+
+/* SegmentPlaneIterative, src/iterative_plane_segmentation.cpp:7-39 */
+int m3d_segment_plane_iterative(m3d_ctx *ctx, const double *xyz, size_t n, double threshold, int max_iteration,
+                                double min_ratio, uint32_t seed, double *planes, size_t cap_planes,
+                                uint64_t *labels, size_t *n_planes, float *device_ms) {
+    if (!ctx || !n_planes || (n && (!xyz || !labels)) || (cap_planes && !planes)) return M3D_ERR_INVALID_ARG;
+    *n_planes = 0;
+    if (device_ms) *device_ms = 0;
+    for (size_t i = 0; i < n; ++i) labels[i] = UINT64_MAX;
+    if (n < 3) return M3D_OK; /* :14-17 warning + empty result */
+    if (max_iteration < 0) max_iteration = 0;
+    M3D_CUDA(ctx, cudaSetDevice(ctx->device));
+    m3d_cloud *c = nullptr;
+    if (int rc = m3d_cloud_upload(ctx, xyz, nullptr, n, &c)) return rc;
+    struct Guard {
+        m3d_cloud *c;
+        ~Guard() { m3d_cloud_free(c); }
+    } guard{c};
+
+    /* ping-pong buffers for the shrinking cloud + original indices + labels */
+    const size_t n3 = sizeof(double) * 3 * n;
+    M3D_CUDA(ctx, ctx->d_tmp0.reserve(n3));                                  /* xyz B      */
+    M3D_CUDA(ctx, ctx->d_tmp1.reserve(sizeof(float4) * n));                  /* pts32 B    */
+    M3D_CUDA(ctx, ctx->d_tmp2.reserve(sizeof(uint32_t) * n));                /* orig A     */
+    M3D_CUDA(ctx, ctx->d_tmp3.reserve(sizeof(uint32_t) * n));                /* orig B     */
+    M3D_CUDA(ctx, ctx->d_tmp4.reserve(sizeof(unsigned long long) * n));      /* labels     */
+    M3D_CUDA(ctx, cudaMemsetAsync(ctx->d_tmp4.p, 0xff, sizeof(unsigned long long) * n, ctx->stream));
+    {
+        std::vector<uint32_t> iota(n);
+        for (size_t i = 0; i < n; ++i) iota[i] = (uint32_t)i;
+        M3D_CUDA(ctx, cudaMemcpyAsync(ctx->d_tmp2.p, iota.data(), sizeof(uint32_t) * n, cudaMemcpyHostToDevice, ctx->stream));
+        M3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    double *xyz_cur = c->xyz.as<double>(), *xyz_nxt = ctx->d_tmp0.as<double>();
+    float4 *p32_cur = c->pts32.as<float4>(), *p32_nxt = ctx->d_tmp1.as<float4>();
+    uint32_t *org_cur = ctx->d_tmp2.as<uint32_t>(), *org_nxt = ctx->d_tmp3.as<uint32_t>();
+
+    size_t count = 0, remaining = n;
+    const size_t target = (size_t)((1 - min_ratio) * (double)n); /* :28 */
+    uint32_t round = 0;
+    float total_ms = 0;
+    int status = M3D_OK;
+    while (count < target) {
+        if (remaining < 3) { /* ransac.h:510-513 throws out of the loop */
+            status = ctx->fail(M3D_ERR_TOO_FEW_POINTS, "Can not fit model due to lack of points");
+            break;
+        }
+        if (*n_planes >= cap_planes) {
+            status = ctx->fail(M3D_ERR_CAPACITY, "more than %zu planes", cap_planes);
+            break;
+        }
+        m3d_ransac_params p{};
+        p.threshold = threshold;
+        p.max_iteration = (uint64_t)max_iteration;
+        p.probability = 0.9999; /* estimator default, ransac.h:462 (SetProbability is not called, :20-21) */
+        p.seed = seed + round;
+        CloudView v{xyz_cur, nullptr, p32_cur, c->meta.as<CloudMeta>(), (uint32_t)remaining, c->h_meta.nonfinite != 0};
+        SegArgs seg{p32_cur, org_cur, xyz_nxt, p32_nxt, org_nxt, ctx->d_tmp4.as<unsigned long long>(),
+                    (unsigned long long)*n_planes};
+        FitResult res;
+        if (int rc = fit_view(ctx, kPlane, c, v, p, &seg, &res)) return rc;
+        total_ms += res.st.device_ms;
+        if (!res.st.found || res.n_inl == 0) { /* the reference would loop forever (Appendix A.12) */
+            status = ctx->fail(M3D_ERR_NO_INLIERS, "segmentation round %u found no inliers", round);
+            break;
+        }
+        for (int i = 0; i < 4; ++i) planes[4 * (*n_planes) + i] = res.refined[i];
+        (*n_planes)++;
+        count += (size_t)res.n_inl;
+        remaining -= (size_t)res.n_inl;
+        std::swap(xyz_cur, xyz_nxt);
+        std::swap(p32_cur, p32_nxt);
+        std::swap(org_cur, org_nxt);
+        round++;
+    }
+    M3D_CUDA(ctx, cudaMemcpyAsync(labels, ctx->d_tmp4.p, sizeof(uint64_t) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    M3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (device_ms) *device_ms = total_ms;
+    return status;
+}
+
+} /* extern "C" */

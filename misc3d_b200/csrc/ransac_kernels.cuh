@@ -1,0 +1,892 @@
+/*
+ * ransac_kernels.cuh -- sm_100a kernels of the RANSAC primitive-fitting path.
+ *
+ *   cloud preparation   bbox_kernel / bbox_final_kernel / convert_kernel / convert_final_kernel
+ *   hot kernel          score_kernel<KIND,THREADS,HPT>   (sample gather -> minimal solve ->
+ *                       all-point inlier count, fp32 guard-banded + fp64 reference-order resolve)
+ *   reference-order     score_exact_kernel<KIND>         (fp64 only; debug / non-finite clouds)
+ *   RefineModel         refine_count / refine_scan / refine_write / refine_final
+ *   helpers             minimal_fit_rows_kernel, seq_err_kernel
+ *
+ * Data layout in HBM: xyz  N x 3 f64 AoS (the reference's vector<Vector3d>),
+ * pts32 N x float4 {x-cx, y-cy, z-cz, |p-c|^2} (16 B/pt, what the hot kernel streams through
+ * shared memory with 1-D TMA bulk copies), samples rows x k u32, counts rows u32.
+ */
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "context.h"
+#include "exact_math.cuh"
+
+namespace m3d {
+
+constexpr int kTile = 1024;  /* points per TMA stage (16 KB)                      */
+constexpr int kStages = 3;   /* ring depth                                        */
+constexpr int kSub = 128;    /* points between two "any ambiguous point?" checks  */
+constexpr uint32_t kInvalidBit = 0x80000000u;
+constexpr double kU32 = 5.9604644775390625e-08; /* 2^-24 */
+constexpr double kU64 = 1.1102230246251565e-16; /* 2^-53 */
+
+/* ------------------------------------------------------------------ mbarrier / TMA (1-D bulk) */
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+/* cp.async.bulk (TMA, SASS UBLKCP): global -> shared, completion on an mbarrier */
+__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    const uint32_t b = smem_u32(bar);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(dst)),
+        "l"(src), "r"(bytes), "r"(b)
+        : "memory");
+}
+
+/* ------------------------------------------------------------------------- cloud preparation */
+struct BBoxPart {
+    double mn[3], mx[3], mraw;
+    int nonfinite;
+    int pad;
+};
+
+__device__ __forceinline__ double warp_min(double v) {
+    for (int o = 16; o; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+    for (int o = 16; o; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__global__ void __launch_bounds__(256) bbox_kernel(const double *__restrict__ xyz, uint32_t n,
+                                                   BBoxPart *__restrict__ part) {
+    double mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+    double mraw = 0;
+    int bad = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const double v = xyz[3 * (size_t)i + c];
+            bad |= !isfinite(v);
+            mn[c] = fmin(mn[c], v);
+            mx[c] = fmax(mx[c], v);
+            mraw = fmax(mraw, fabs(v));
+        }
+    }
+    __shared__ BBoxPart sh[8];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        mn[c] = warp_min(mn[c]);
+        mx[c] = warp_max(mx[c]);
+    }
+    mraw = warp_max(mraw);
+    bad = __any_sync(0xffffffffu, bad);
+    if (lane == 0) {
+        for (int c = 0; c < 3; ++c) {
+            sh[w].mn[c] = mn[c];
+            sh[w].mx[c] = mx[c];
+        }
+        sh[w].mraw = mraw;
+        sh[w].nonfinite = bad;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        BBoxPart r = sh[0];
+        for (int k = 1; k < 8; ++k) {
+            for (int c = 0; c < 3; ++c) {
+                r.mn[c] = fmin(r.mn[c], sh[k].mn[c]);
+                r.mx[c] = fmax(r.mx[c], sh[k].mx[c]);
+            }
+            r.mraw = fmax(r.mraw, sh[k].mraw);
+            r.nonfinite |= sh[k].nonfinite;
+        }
+        part[blockIdx.x] = r;
+    }
+}
+
+__global__ void bbox_final_kernel(const BBoxPart *__restrict__ part, int nparts, CloudMeta *meta) {
+    if (threadIdx.x != 0) return;
+    BBoxPart r = part[0];
+    for (int k = 1; k < nparts; ++k) {
+        for (int c = 0; c < 3; ++c) {
+            r.mn[c] = fmin(r.mn[c], part[k].mn[c]);
+            r.mx[c] = fmax(r.mx[c], part[k].mx[c]);
+        }
+        r.mraw = fmax(r.mraw, part[k].mraw);
+        r.nonfinite |= part[k].nonfinite;
+    }
+    for (int c = 0; c < 3; ++c) {
+        const double ctr = 0.5 * (r.mn[c] + r.mx[c]);
+        meta->center[c] = isfinite(ctr) ? ctr : 0.0;
+    }
+    meta->mraw = r.mraw;
+    meta->nonfinite = r.nonfinite;
+    meta->mc = 0;
+}
+
+/* pts32[i] = {x-cx, y-cy, z-cz, |p-c|^2}; per-block max |centred coordinate| */
+__global__ void __launch_bounds__(256) convert_kernel(const double *__restrict__ xyz, uint32_t n,
+                                                      const CloudMeta *__restrict__ meta,
+                                                      float4 *__restrict__ pts32,
+                                                      double *__restrict__ part) {
+    const double cx = meta->center[0], cy = meta->center[1], cz = meta->center[2];
+    double mc = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const double x = xyz[3 * (size_t)i] - cx, y = xyz[3 * (size_t)i + 1] - cy,
+                     z = xyz[3 * (size_t)i + 2] - cz;
+        mc = fmax(mc, fmax(fabs(x), fmax(fabs(y), fabs(z))));
+        pts32[i] = make_float4((float)x, (float)y, (float)z, (float)(x * x + y * y + z * z));
+    }
+    __shared__ double sh[8];
+    mc = warp_max(mc);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = mc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 1; k < 8; ++k) mc = fmax(mc, sh[k]);
+        part[blockIdx.x] = mc;
+    }
+}
+__global__ void convert_final_kernel(const double *__restrict__ part, int nparts, CloudMeta *meta) {
+    if (threadIdx.x != 0) return;
+    double mc = 0;
+    for (int k = 0; k < nparts; ++k) mc = fmax(mc, part[k]);
+    meta->mc = mc;
+}
+
+/* --------------------------------------------------------------- sample gather + minimal fit */
+/* RandomSampler row (draw order) -> SelectByIndex order (ascending, ransac.h:578 / Open3D mask
+ * pass) -> MinimalFit.  Returns MinimalFit's bool. */
+template <int KIND>
+__device__ __forceinline__ bool fit_row(const double *__restrict__ xyz, const double *__restrict__ nrm,
+                                        const uint32_t *__restrict__ samples, uint32_t row, double *m) {
+    constexpr int K = sample_size(KIND);
+    uint32_t s[K];
+#pragma unroll
+    for (int i = 0; i < K; ++i) s[i] = samples[(size_t)row * K + i];
+#pragma unroll
+    for (int i = 1; i < K; ++i) /* K <= 4: sorting network by insertion */
+#pragma unroll
+        for (int j = i; j > 0; --j)
+            if (s[j - 1] > s[j]) {
+                const uint32_t t = s[j];
+                s[j] = s[j - 1];
+                s[j - 1] = t;
+            }
+    double pts[3 * K];
+    double nr[KIND == kCylinder ? 3 * K : 1];
+#pragma unroll
+    for (int i = 0; i < K; ++i)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            pts[3 * i + c] = xyz[3 * (size_t)s[i] + c];
+            if (KIND == kCylinder) nr[3 * i + c] = nrm[3 * (size_t)s[i] + c];
+        }
+    return ex::minimal_fit<KIND>(pts, nr, m);
+}
+
+template <int KIND>
+__global__ void minimal_fit_rows_kernel(const double *__restrict__ xyz, const double *__restrict__ nrm,
+                                        const uint32_t *__restrict__ samples, uint32_t rows,
+                                        double *__restrict__ models, uint8_t *__restrict__ valid) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    double m[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const bool ok = fit_row<KIND>(xyz, nrm, samples, r, m);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) models[(size_t)r * 8 + i] = ok ? m[i] : 0.0;
+    valid[r] = ok ? 1 : 0;
+}
+
+/* ------------------------------------------------------------------ fp32 guard-banded scoring */
+/* Fast<KIND>: for a centred fp32 point p = {x,y,z,|p|^2} the value t(p) satisfies
+ *      |t| <  lo  =>  the reference predicate `distance < threshold` is certainly true
+ *      |t| >= hi  =>  certainly false
+ * anything else (including NaN) is decided by the fp64 reference-order distance.
+ *   plane     t = w.p + w3'                      (|t| vs threshold*||w||)
+ *   sphere    t = |p - c|^2 - mid                (|t| vs half; [mid-half, mid+half] is the
+ *   cylinder  t = |p - c|^2 - ((p-c).n)^2 - mid   interval of squared distances (r-thr)^2..(r+thr)^2)
+ */
+template <int KIND>
+struct Fast {
+    float c[KIND == kCylinder ? 8 : 4];
+    float lo, hi;
+};
+
+template <int KIND>
+__device__ __forceinline__ float fast_eval(const Fast<KIND> &f, const float4 p) {
+    if (KIND == kPlane) {
+        return fmaf(f.c[0], p.x, fmaf(f.c[1], p.y, fmaf(f.c[2], p.z, f.c[3])));
+    } else if (KIND == kSphere) {
+        return fmaf(f.c[0], p.x, fmaf(f.c[1], p.y, fmaf(f.c[2], p.z, __fadd_rn(p.w, f.c[3]))));
+    } else {
+        const float a = fmaf(f.c[0], p.x, fmaf(f.c[1], p.y, fmaf(f.c[2], p.z, __fadd_rn(p.w, f.c[3]))));
+        const float b = fmaf(f.c[4], p.x, fmaf(f.c[5], p.y, fmaf(f.c[6], p.z, f.c[7])));
+        return fmaf(-b, b, a);
+    }
+}
+
+/* the two counter updates of the inner loop; kCountForm picks the instruction mix
+ *   1: FSETP + @P IADD for both            (fma pipe 3, alu pipe 4 per point-hypothesis pair)
+ *   3: FADD + LEA.HI (sign bit) for both   (fma 5, alu 2)
+ *   4: one of each                         (fma 4, alu 3)
+ * all forms leave NaN / exact ties uncounted, i.e. "ambiguous". */
+#ifndef M3D_COUNT_FORM
+#define M3D_COUNT_FORM 4
+#endif
+template <int FORM>
+__device__ __forceinline__ void count2(float at, float lo, float hi, uint32_t &clo, uint32_t &cout) {
+    if (FORM == 1 || FORM == 4) {
+        asm("{.reg .pred p; setp.lt.f32 p, %1, %2; @p add.u32 %0, %0, 1;}" : "+r"(clo) : "f"(at), "f"(lo));
+    } else {
+        clo += __float_as_uint(__fsub_rn(at, lo)) >> 31;
+    }
+    if (FORM == 1) {
+        asm("{.reg .pred p; setp.ge.f32 p, %1, %2; @p add.u32 %0, %0, 1;}" : "+r"(cout) : "f"(at), "f"(hi));
+    } else {
+        cout += __float_as_uint(__fsub_rn(hi, at)) >> 31; /* at > hi */
+    }
+}
+/* the same decision, as a predicate (resolve path) */
+template <int FORM>
+__device__ __forceinline__ bool is_ambiguous(float at, float lo, float hi) {
+    uint32_t a = 0, b = 0;
+    count2<FORM>(at, lo, hi, a, b);
+    return (a + b) == 0;
+}
+
+template <int KIND>
+__device__ inline void make_fast(const double *m, bool ok, const CloudMeta &M, double thr, Fast<KIND> &f) {
+    constexpr int NC = KIND == kCylinder ? 8 : 4;
+#pragma unroll
+    for (int i = 0; i < NC; ++i) f.c[i] = 0.f;
+    f.lo = -1.f; /* |t| <  -1 never : no certain inlier                                       */
+    f.hi = -1.f; /* |t| >= -1 always: every point a certain outlier (t is finite: p is finite) */
+    if (!ok || !(thr > 0)) return;
+    bool fin = true;
+#pragma unroll
+    for (int i = 0; i < param_count(KIND); ++i) fin = fin && isfinite(m[i]);
+    if (!fin) return; /* a NaN/inf model makes every reference distance NaN/inf: never an inlier */
+
+    double c[NC], lo, hi, smax = 0;
+    const double cx = M.center[0], cy = M.center[1], cz = M.center[2];
+    if (KIND == kPlane) {
+        const double nrm = ex::plane_norm(m);
+        const double thrn = thr * nrm;
+        const double w3c = m[3] + (m[0] * cx + m[1] * cy + m[2] * cz);
+        const double l1 = fabs(m[0]) + fabs(m[1]) + fabs(m[2]);
+        const double S = l1 * M.mc + fabs(w3c);
+        const double band = 16 * kU32 * S + 4 * kU32 * thrn + 16 * kU64 * (l1 * M.mraw + fabs(m[3]));
+        smax = S;
+        c[0] = m[0];
+        c[1] = m[1];
+        c[2] = m[2];
+        c[3] = w3c;
+        lo = thrn - band;
+        hi = thrn + band;
+    } else {
+        const double r = (KIND == kSphere) ? m[3] : m[6];
+        const double Hi = (r + thr) * (r + thr);
+        const double Lo = (r >= thr) ? (r - thr) * (r - thr) : -Hi;
+        const double mid = 0.5 * (Lo + Hi), half = 0.5 * (Hi - Lo);
+        const double rh = sqrt(Hi);
+        double ax = m[0] - cx, ay = m[1] - cy, az = m[2] - cz; /* centre / axis point, centred */
+        double band;
+        if (KIND == kSphere) {
+            const double c3 = (ax * ax + ay * ay + az * az) - mid;
+            const double l1 = fabs(ax) + fabs(ay) + fabs(az);
+            const double S = 3 * M.mc * M.mc + fabs(c3) + 2 * l1 * M.mc;
+            band = 24 * kU32 * S + 4 * kU32 * half +
+                   2 * rh * 16 * kU64 * (M.mraw + fabs(m[0]) + fabs(m[1]) + fabs(m[2]) + rh);
+            smax = S;
+            c[3] = c3;
+        } else {
+            /* the reference measures the distance to the line through `center` and
+             * `center + dir` (ransac.h:438-442): direction = (center + dir) - center */
+            const ex::V3 cen = {m[0], m[1], m[2]};
+            const ex::V3 ref = {ex::add(m[0], m[3]), ex::add(m[1], m[4]), ex::add(m[2], m[5])};
+            const ex::V3 ne = ex::sub3(ref, cen);
+            const double L2 = ne.x * ne.x + ne.y * ne.y + ne.z * ne.z;
+            if (!(L2 > 0) || !isfinite(L2)) return; /* 0/0 = NaN distance: never an inlier */
+            const double L = sqrt(L2);
+            const double nx = ne.x / L, ny = ne.y / L, nz = ne.z / L;
+            const double cnorm = sqrt(ax * ax + ay * ay + az * az);
+            /* re-anchor the axis point at the foot of the cloud centre (same line, no
+             * cancellation between |c|^2 and (c.n)^2) */
+            const double proj = ax * nx + ay * ny + az * nz;
+            ax -= proj * nx;
+            ay -= proj * ny;
+            az -= proj * nz;
+            const double c3 = (ax * ax + ay * ay + az * az) - mid;
+            const double l1 = fabs(ax) + fabs(ay) + fabs(az);
+            const double n3 = -(nx * ax + ny * ay + nz * az);
+            const double Sa = 3 * M.mc * M.mc + fabs(c3) + 2 * l1 * M.mc;
+            const double Sb = (fabs(nx) + fabs(ny) + fabs(nz)) * M.mc + fabs(n3);
+            const double A = 1.7320508075688772 * M.mraw + sqrt(m[0] * m[0] + m[1] * m[1] + m[2] * m[2]) + L;
+            band = 32 * kU32 * (Sa + Sb * Sb) + 4 * kU32 * half +
+                   2 * rh * 16 * kU64 * (A * A / L + cnorm + M.mc);
+            smax = Sa + Sb * Sb;
+            c[3] = c3;
+            c[4] = nx;
+            c[5] = ny;
+            c[6] = nz;
+            c[7] = n3;
+        }
+        c[0] = -2 * ax;
+        c[1] = -2 * ay;
+        c[2] = -2 * az;
+        lo = half - band;
+        hi = half + band;
+    }
+    /* smax bounds every intermediate of fast_eval: keep it far from fp32 overflow */
+    bool okf = isfinite(lo) && isfinite(hi) && (smax < 1e30);
+#pragma unroll
+    for (int i = 0; i < NC; ++i) {
+        f.c[i] = (float)c[i];
+        okf = okf && isfinite(f.c[i]);
+    }
+    f.lo = __double2float_rd(lo);
+    f.hi = __double2float_ru(hi);
+    okf = okf && isfinite(f.lo) && isfinite(f.hi);
+    if (!okf) { /* fp32 cannot represent this model: decide every point by the fp64 path */
+#pragma unroll
+        for (int i = 0; i < NC; ++i) f.c[i] = 0.f;
+        f.lo = -1.f;
+        f.hi = __int_as_float(0x7fc00000); /* |t| >= NaN is never true */
+    }
+}
+
+struct ScoreArgs {
+    const float4 *pts32;
+    const double *xyz;
+    const double *nrm;
+    const CloudMeta *meta;
+    const uint32_t *samples; /* rows x k of this wave (device)                          */
+    uint32_t *counts;        /* [rows]: inlier count (atomicAdd per chunk), bit31 = MinimalFit false */
+    unsigned long long *resolves;
+    double thr;
+    uint32_t n;
+    uint32_t row_begin; /* first row of the wave buffer this launch scores             */
+    uint32_t rows;      /* number of rows this launch scores                           */
+    uint32_t chunk_tiles;
+};
+
+/* the rare path: points of one sub-tile whose fp32 value fell inside the guard band are decided
+ * with the reference's own fp64 arithmetic on the original coordinates */
+template <int KIND>
+__device__ __noinline__ void resolve_subtile(const ScoreArgs &a, uint32_t row, const Fast<KIND> f,
+                                             const float4 *sp, uint32_t gbase, int cnt,
+                                             uint32_t &clo, uint32_t &cout, uint32_t &nres) {
+    double m[8];
+    const bool ok = fit_row<KIND>(a.xyz, a.nrm, a.samples, row, m);
+    ex::Dist<KIND> dist;
+    if (ok) dist.set(m);
+    for (int j = 0; j < cnt; ++j) {
+        const float at = fabsf(fast_eval<KIND>(f, sp[j]));
+        if (is_ambiguous<M3D_COUNT_FORM>(at, f.lo, f.hi)) {
+            bool in = false;
+            if (ok) in = dist(ex::ld3(a.xyz + 3 * (size_t)(gbase + j))) < a.thr;
+            if (in)
+                ++clo;
+            else
+                ++cout;
+            ++nres;
+        }
+    }
+}
+
+template <int KIND, int THREADS, int HPT>
+__global__ void __launch_bounds__(THREADS) score_kernel(const ScoreArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float4 *tiles = reinterpret_cast<float4 *>(smem_raw);
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)kStages * kTile * sizeof(float4));
+
+    const int tid = threadIdx.x;
+    const uint32_t ntiles = (a.n + kTile - 1) / kTile;
+    const uint32_t t0 = blockIdx.y * a.chunk_tiles;
+    const uint32_t t1 = min(t0 + a.chunk_tiles, ntiles);
+
+    auto issue = [&](uint32_t t) {
+        const uint32_t base = t * kTile;
+        const uint32_t npt = min((uint32_t)kTile, a.n - base);
+        const int st = (t - t0) % kStages;
+        tma_load_1d(tiles + (size_t)st * kTile, a.pts32 + base, npt * (uint32_t)sizeof(float4), &full[st]);
+    };
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < kStages; ++s) mbar_init(&full[s], 1);
+        mbar_fence_init();
+        for (uint32_t t = t0; t < t1 && t < t0 + kStages; ++t) issue(t);
+    }
+
+    /* prologue: this thread's hypotheses -- gather, solve (fp64 reference order), fp32 coefficients */
+    const CloudMeta M = *a.meta;
+    uint32_t row[HPT];
+    Fast<KIND> f[HPT];
+    uint32_t clo[HPT], cout[HPT];
+    bool invalid[HPT];
+#pragma unroll
+    for (int h = 0; h < HPT; ++h) {
+        row[h] = (blockIdx.x * HPT + h) * THREADS + tid;
+        double m[8];
+        bool ok = false;
+        if (row[h] < a.rows) ok = fit_row<KIND>(a.xyz, a.nrm, a.samples, a.row_begin + row[h], m);
+        invalid[h] = (row[h] < a.rows) && !ok;
+        make_fast<KIND>(m, ok, M, a.thr, f[h]);
+        clo[h] = 0;
+        cout[h] = 0;
+    }
+    __syncthreads(); /* barrier init visible to all waiters */
+
+    uint32_t seen = 0, nres = 0;
+    for (uint32_t t = t0; t < t1; ++t) {
+        const int st = (t - t0) % kStages;
+        mbar_wait(&full[st], ((t - t0) / kStages) & 1);
+        const float4 *sp = tiles + (size_t)st * kTile;
+        const uint32_t base = t * kTile;
+        const int npt = (int)min((uint32_t)kTile, a.n - base);
+        for (int s0 = 0; s0 < npt; s0 += kSub) {
+            const int cnt = min(kSub, npt - s0);
+            if (cnt == kSub) {
+#pragma unroll 8
+                for (int j = 0; j < kSub; ++j) {
+                    const float4 p = sp[s0 + j];
+#pragma unroll
+                    for (int h = 0; h < HPT; ++h) {
+                        const float at = fabsf(fast_eval<KIND>(f[h], p));
+                        count2<M3D_COUNT_FORM>(at, f[h].lo, f[h].hi, clo[h], cout[h]);
+                    }
+                }
+            } else {
+                for (int j = 0; j < cnt; ++j) {
+                    const float4 p = sp[s0 + j];
+#pragma unroll
+                    for (int h = 0; h < HPT; ++h) {
+                        const float at = fabsf(fast_eval<KIND>(f[h], p));
+                        count2<M3D_COUNT_FORM>(at, f[h].lo, f[h].hi, clo[h], cout[h]);
+                    }
+                }
+            }
+            seen += cnt;
+#pragma unroll
+            for (int h = 0; h < HPT; ++h) {
+                if (clo[h] + cout[h] != seen) {
+                    if (row[h] < a.rows)
+                        resolve_subtile<KIND>(a, a.row_begin + row[h], f[h], sp + s0, base + s0, cnt,
+                                              clo[h], cout[h], nres);
+                    else
+                        cout[h] = seen - clo[h];
+                }
+            }
+        }
+        __syncthreads(); /* every warp is done with stage st */
+        if (tid == 0 && t + kStages < t1) issue(t + kStages);
+    }
+
+#pragma unroll
+    for (int h = 0; h < HPT; ++h) {
+        if (row[h] < a.rows) {
+            if (clo[h]) atomicAdd(&a.counts[row[h]], clo[h]);
+            if (invalid[h] && blockIdx.y == 0) atomicOr(&a.counts[row[h]], kInvalidBit);
+        }
+    }
+    if (nres) atomicAdd(a.resolves, (unsigned long long)nres);
+}
+
+/* fp64 reference-order scoring of every point (no fp32 copy involved) */
+template <int KIND>
+__global__ void __launch_bounds__(128) score_exact_kernel(const ScoreArgs a) {
+    const uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t ntiles = (a.n + kTile - 1) / kTile;
+    const uint32_t p0 = min((uint64_t)a.n, (uint64_t)blockIdx.y * a.chunk_tiles * kTile);
+    const uint32_t p1 = min((uint64_t)a.n, ((uint64_t)blockIdx.y + 1) * a.chunk_tiles * kTile);
+    (void)ntiles;
+    if (row >= a.rows) return;
+    double m[8];
+    const bool ok = fit_row<KIND>(a.xyz, a.nrm, a.samples, a.row_begin + row, m);
+    if (!ok) {
+        if (blockIdx.y == 0) atomicOr(&a.counts[row], kInvalidBit);
+        return;
+    }
+    ex::Dist<KIND> dist;
+    dist.set(m);
+    uint32_t c = 0;
+    for (uint32_t i = p0; i < p1; ++i) c += (dist(ex::ld3(a.xyz + 3 * (size_t)i)) < a.thr) ? 1u : 0u;
+    if (c) atomicAdd(&a.counts[row], c);
+    atomicAdd(a.resolves, (unsigned long long)(p1 - p0));
+}
+
+/* ------------------------------------------------------------------------------- RefineModel */
+constexpr int kRB = 256;    /* threads per refine block                     */
+constexpr int kRItems = 8;  /* points per thread; block = 2048 consecutive points */
+constexpr int kRBlockPts = kRB * kRItems;
+
+struct RefineMid { /* written by refine_scan */
+    unsigned long long n_inl;
+    double err;     /* sum of inlier distances (parallel fp64 sum, fixed order) */
+    double mean[3]; /* inlier centroid */
+};
+struct RefineOut {
+    double model[8];
+    int ok;
+    int pad;
+};
+
+/* pass 1 (ransac.h:536-543 predicate): per-block inlier count and partial sums */
+template <int KIND>
+__global__ void __launch_bounds__(kRB) refine_count_kernel(const double *__restrict__ xyz, uint32_t n,
+                                                           const double *__restrict__ model, double thr,
+                                                           uint32_t *__restrict__ blk_cnt,
+                                                           double *__restrict__ blk_part /*[nblk][4]*/) {
+    ex::Dist<KIND> dist;
+    {
+        double m[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) m[i] = model[i];
+        dist.set(m);
+    }
+    uint32_t cnt = 0;
+    double s[4] = {0, 0, 0, 0};
+    const uint32_t base = blockIdx.x * kRBlockPts;
+#pragma unroll
+    for (int it = 0; it < kRItems; ++it) {
+        const uint32_t i = base + it * kRB + threadIdx.x;
+        if (i < n) {
+            const ex::V3 q = ex::ld3(xyz + 3 * (size_t)i);
+            const double d = dist(q);
+            if (d < thr) {
+                ++cnt;
+                s[0] += d;
+                s[1] += q.x;
+                s[2] += q.y;
+                s[3] += q.z;
+            }
+        }
+    }
+    __shared__ double sh[8][4];
+    __shared__ uint32_t shc[8];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) s[k] = warp_sum(s[k]);
+    if (lane == 0) {
+        shc[w] = cnt;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) sh[w][k] = s[k];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t c = 0;
+        double r[4] = {0, 0, 0, 0};
+        for (int k = 0; k < 8; ++k) {
+            c += shc[k];
+            for (int q = 0; q < 4; ++q) r[q] += sh[k][q];
+        }
+        blk_cnt[blockIdx.x] = c;
+        for (int q = 0; q < 4; ++q) blk_part[(size_t)blockIdx.x * 4 + q] = r[q];
+    }
+}
+
+/* pass 2: exclusive scan of the block counts + fixed-order reduction of the partial sums */
+__global__ void __launch_bounds__(1024) refine_scan_kernel(const uint32_t *__restrict__ blk_cnt,
+                                                           const double *__restrict__ blk_part,
+                                                           uint32_t nblk, uint32_t *__restrict__ blk_off,
+                                                           RefineMid *__restrict__ mid) {
+    __shared__ uint32_t wsum[32];
+    __shared__ uint32_t carry_s;
+    __shared__ double red[32][4];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    double s[4] = {0, 0, 0, 0};
+    for (uint32_t b0 = 0; b0 < nblk; b0 += 1024) {
+        const uint32_t b = b0 + threadIdx.x;
+        const uint32_t v = b < nblk ? blk_cnt[b] : 0;
+        if (b < nblk) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) s[k] += blk_part[(size_t)b * 4 + k];
+        }
+        uint32_t x = v;
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += y;
+        }
+        if (lane == 31) wsum[w] = x;
+        __syncthreads();
+        if (w == 0) {
+            uint32_t ws = wsum[lane];
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xffffffffu, ws, o);
+                if (lane >= o) ws += y;
+            }
+            wsum[lane] = ws; /* inclusive */
+        }
+        __syncthreads();
+        const uint32_t carry = carry_s;
+        const uint32_t woff = w ? wsum[w - 1] : 0;
+        if (b < nblk) blk_off[b] = carry + woff + x - v;
+        __syncthreads();
+        if (threadIdx.x == 0) carry_s = carry + wsum[31];
+        __syncthreads();
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) s[k] = warp_sum(s[k]);
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) red[w][k] = s[k];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double r[4] = {0, 0, 0, 0};
+        for (int k = 0; k < 32; ++k)
+            for (int q = 0; q < 4; ++q) r[q] += red[k][q];
+        const unsigned long long ni = carry_s;
+        mid->n_inl = ni;
+        mid->err = r[0];
+        const double inv = ni ? 1.0 / (double)ni : 0.0;
+        mid->mean[0] = r[1] * inv;
+        mid->mean[1] = r[2] * inv;
+        mid->mean[2] = r[3] * inv;
+    }
+}
+
+/* segmentation side outputs of pass 3 (all optional) */
+struct SegArgs {
+    const float4 *pts32_in;
+    const uint32_t *orig_in; /* original index of every current point */
+    double *xyz_out;
+    float4 *pts32_out;
+    uint32_t *orig_out;
+    unsigned long long *labels; /* [n_original] */
+    unsigned long long plane_id;
+};
+
+/* pass 3: ascending inlier indices (stable), centred moments for GeneralFit; with SEG also the
+ * stable compaction of the remaining points (SelectByIndex(inliers, invert=true),
+ * iterative_plane_segmentation.cpp:32-33) and the cluster labels */
+template <int KIND, bool SEG>
+__global__ void __launch_bounds__(kRB) refine_write_kernel(const double *__restrict__ xyz, uint32_t n,
+                                                           const double *__restrict__ model, double thr,
+                                                           const uint32_t *__restrict__ blk_off,
+                                                           const RefineMid *__restrict__ mid,
+                                                           unsigned long long *__restrict__ inl,
+                                                           double *__restrict__ blk_mom /*[nblk][10]*/,
+                                                           const SegArgs seg) {
+    ex::Dist<KIND> dist;
+    {
+        double m[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) m[i] = model[i];
+        dist.set(m);
+    }
+    const double mx = mid->mean[0], my = mid->mean[1], mz = mid->mean[2];
+    __shared__ uint32_t wcnt[8];
+    __shared__ double sh[8][10];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const uint32_t base = blockIdx.x * kRBlockPts;
+    uint32_t running = blk_off[blockIdx.x];
+    double mom[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll 1
+    for (int it = 0; it < kRItems; ++it) {
+        const uint32_t i = base + it * kRB + threadIdx.x;
+        bool in = false;
+        ex::V3 q = {0, 0, 0};
+        if (i < n) {
+            q = ex::ld3(xyz + 3 * (size_t)i);
+            in = dist(q) < thr;
+        }
+        const uint32_t bal = __ballot_sync(0xffffffffu, in);
+        if (lane == 0) wcnt[w] = __popc(bal);
+        __syncthreads();
+        uint32_t before = 0, total = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const uint32_t c = wcnt[k];
+            before += (k < w) ? c : 0;
+            total += c;
+        }
+        const uint32_t rank = running + before + __popc(bal & ((1u << lane) - 1));
+        if (in) {
+            inl[rank] = i;
+            const double ux = q.x - mx, uy = q.y - my, uz = q.z - mz;
+            mom[0] += ux * ux;
+            mom[1] += ux * uy;
+            mom[2] += ux * uz;
+            mom[3] += uy * uy;
+            mom[4] += uy * uz;
+            mom[5] += uz * uz;
+            if (KIND == kSphere) {
+                const double uu = ux * ux + uy * uy + uz * uz;
+                mom[6] += ux * uu;
+                mom[7] += uy * uu;
+                mom[8] += uz * uu;
+                mom[9] += uu;
+            }
+            if (SEG) seg.labels[seg.orig_in[i]] = seg.plane_id;
+        } else if (SEG && i < n) {
+            const uint32_t dst = i - rank; /* rank == number of inliers before i */
+            seg.xyz_out[3 * (size_t)dst] = q.x;
+            seg.xyz_out[3 * (size_t)dst + 1] = q.y;
+            seg.xyz_out[3 * (size_t)dst + 2] = q.z;
+            seg.pts32_out[dst] = seg.pts32_in[i];
+            seg.orig_out[dst] = seg.orig_in[i];
+        }
+        running += total;
+        __syncthreads();
+    }
+    constexpr int NM = (KIND == kSphere) ? 10 : 6;
+#pragma unroll
+    for (int k = 0; k < NM; ++k) mom[k] = warp_sum(mom[k]);
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < NM; ++k) sh[w][k] = mom[k];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int q = 0; q < NM; ++q) {
+            double r = 0;
+            for (int k = 0; k < 8; ++k) r += sh[k][q];
+            blk_mom[(size_t)blockIdx.x * 10 + q] = r;
+        }
+    }
+}
+
+/* pass 4: GeneralFit from the moments (PlaneEstimator::GeneralFit ransac.h:164-213;
+ * SphereEstimator::GeneralFit ransac.h:296-330 as centred normal equations instead of the
+ * reference's full-U BDCSVD; CylinderEstimator::GeneralFit ransac.h:427-433 is a no-op) */
+template <int KIND>
+__global__ void __launch_bounds__(256) refine_final_kernel(const double *__restrict__ blk_mom, uint32_t nblk,
+                                                           const RefineMid *__restrict__ mid,
+                                                           const double *__restrict__ model,
+                                                           RefineOut *__restrict__ out) {
+    __shared__ double sh[8][10];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    double mom[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (uint32_t b = threadIdx.x; b < nblk; b += blockDim.x)
+#pragma unroll
+        for (int k = 0; k < 10; ++k) mom[k] += blk_mom[(size_t)b * 10 + k];
+#pragma unroll
+    for (int k = 0; k < 10; ++k) mom[k] = warp_sum(mom[k]);
+    if (lane == 0)
+#pragma unroll
+        for (int k = 0; k < 10; ++k) sh[w][k] = mom[k];
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    for (int q = 0; q < 10; ++q) {
+        double r = 0;
+        for (int k = 0; k < 8; ++k) r += sh[k][q];
+        mom[q] = r;
+    }
+    double m[8];
+    for (int i = 0; i < 8; ++i) m[i] = model[i];
+    int ok = 1;
+    const unsigned long long ni = mid->n_inl;
+    const double mx = mid->mean[0], my = mid->mean[1], mz = mid->mean[2];
+    if (KIND == kPlane) {
+        if (ni < 3) {
+            ok = 0;
+        } else {
+            const double xx = mom[0], xy = mom[1], xz = mom[2], yy = mom[3], yz = mom[4], zz = mom[5];
+            const double det_x = yy * zz - yz * yz, det_y = xx * zz - xz * xz, det_z = xx * yy - xy * xy;
+            double a, b, c;
+            if (det_x > det_y && det_x > det_z) { /* ransac.h:195-201 */
+                a = det_x;
+                b = xz * yz - xy * zz;
+                c = xy * yz - xz * yy;
+            } else if (det_y > det_z) {
+                a = xz * yz - xy * zz;
+                b = det_y;
+                c = xy * xz - yz * xx;
+            } else {
+                a = xy * yz - xz * yy;
+                b = xy * xz - yz * xx;
+                c = det_z;
+            }
+            const double nrm = sqrt(a * a + b * b + c * c);
+            if (nrm < kEps) {
+                ok = 0;
+            } else {
+                a /= nrm;
+                b /= nrm;
+                c /= nrm;
+                m[0] = a;
+                m[1] = b;
+                m[2] = c;
+                m[3] = -(a * mx + b * my + c * mz);
+            }
+        }
+    } else if (KIND == kSphere) {
+        if (ni < 4) {
+            ok = 0;
+        } else {
+            /* min sum (2 c'.u + w - |u|^2)^2 with sum u = 0:  2 (sum u u^T) c' = sum u |u|^2 ;
+             * r^2 = |c'|^2 + mean |u|^2 */
+            const double A00 = mom[0], A01 = mom[1], A02 = mom[2], A11 = mom[3], A12 = mom[4], A22 = mom[5];
+            const double b0 = 0.5 * mom[6], b1 = 0.5 * mom[7], b2 = 0.5 * mom[8];
+            const double c00 = A11 * A22 - A12 * A12, c01 = A02 * A12 - A01 * A22, c02 = A01 * A12 - A02 * A11;
+            const double c11 = A00 * A22 - A02 * A02, c12 = A01 * A02 - A00 * A12, c22 = A00 * A11 - A01 * A01;
+            const double det = A00 * c00 + A01 * c01 + A02 * c02;
+            const double x = (c00 * b0 + c01 * b1 + c02 * b2) / det;
+            const double y = (c01 * b0 + c11 * b1 + c12 * b2) / det;
+            const double z = (c02 * b0 + c12 * b1 + c22 * b2) / det;
+            m[0] = x + mx;
+            m[1] = y + my;
+            m[2] = z + mz;
+            m[3] = sqrt(x * x + y * y + z * z + mom[9] / (double)ni);
+        }
+    }
+    for (int i = 0; i < 8; ++i) out->model[i] = m[i];
+    out->ok = ok;
+}
+
+/* EvaluateModel's error exactly as the reference sums it (ransac.h:632-640): index order, one
+ * accumulator.  Only used to break inlier-count ties whose parallel sums are too close to call. */
+template <int KIND>
+__global__ void seq_err_kernel(const double *__restrict__ xyz, const unsigned long long *__restrict__ inl,
+                               unsigned long long n_inl, const double *__restrict__ model,
+                               double *__restrict__ out) {
+    ex::Dist<KIND> dist;
+    {
+        double m[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) m[i] = model[i];
+        dist.set(m);
+    }
+    const int lane = threadIdx.x;
+    double acc = 0;
+    for (unsigned long long b = 0; b < n_inl; b += 32) {
+        const unsigned long long j = b + lane;
+        double d = 0;
+        if (j < n_inl) d = dist(ex::ld3(xyz + 3 * (size_t)inl[j]));
+        const int cnt = (int)min((unsigned long long)32, n_inl - b);
+        for (int k = 0; k < cnt; ++k) acc = ex::add(acc, __shfl_sync(0xffffffffu, d, k));
+    }
+    if (lane == 0) *out = acc;
+}
+
+}  // namespace m3d

@@ -1,0 +1,210 @@
+"""GPU parity tests of the RANSAC path: libm3d_b200.so (through the C-ABI) against the CPU oracle
+on the same seeded inputs -- bit-exact for models of the minimal fits, inlier counts, inlier
+index sets and loop statistics; tolerance (stated per test) for the least-squares refits."""
+import os
+
+import numpy as np
+import pytest
+
+from misc3d_b200 import synth
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+KINDS = [0, 1, 2]
+
+
+def _cloud(kind, n, seed):
+    xyz, nrm = synth.make_c2(n=n, seed=seed)
+    return xyz, (nrm if kind == 2 else None)
+
+
+def _oracle_rows(orc, kind, xyz, nrm, table, thr):
+    valid = np.zeros(len(table), np.uint8)
+    counts = np.zeros(len(table), np.uint64)
+    models = np.zeros((len(table), 8))
+    for i, row in enumerate(table):
+        idx = np.sort(row)
+        ok, m = orc.minimal_fit(kind, xyz[idx], None if nrm is None else nrm[idx])
+        if ok:
+            valid[i] = 1
+            models[i, :len(m)] = m
+            counts[i], _ = orc.evaluate(kind, xyz, m, thr)
+    return valid, counts, models
+
+
+@pytest.mark.parametrize("kind", KINDS)
+@pytest.mark.parametrize("n,rows", [(20000, 300), (1025, 64), (5000, 2500)])
+def test_score_samples_bit_exact(ctx, capi, orc, kind, n, rows):
+    xyz, nrm = _cloud(kind, n, seed=100 + kind)
+    table = capi.sample_table(7 + kind, n, capi.KSAMPLE[kind], rows)
+    cloud = ctx.upload(xyz, nrm)
+    counts, models, valid = ctx.score_samples(kind, cloud, table, 0.01)
+    ovalid, ocounts, omodels = _oracle_rows(orc, kind, xyz, nrm, table, 0.01)
+    np.testing.assert_array_equal(valid, ovalid)
+    np.testing.assert_array_equal(models.view(np.uint64), omodels.view(np.uint64))  # bit-exact, NaN included
+    np.testing.assert_array_equal(counts, ocounts)
+    # the fp64 reference-order kernel gives the same counts
+    counts2, _, _ = ctx.score_samples(kind, cloud, table, 0.01, flags=capi.FLAG_EXACT_ONLY, want_models=False)
+    np.testing.assert_array_equal(counts2, ocounts)
+    cloud.free()
+
+
+def _check_fit(ctx, capi, orc, kind, xyz, nrm, thr, max_it, prob, seed, rtol_refit=1e-9):
+    rc, model, inl, st = ctx.ransac_fit(kind, xyz, nrm, thr, max_it, prob, seed)
+    orc_rc, omodel, oinl, ost = orc.ransac_fit(kind, xyz, nrm, thr=thr, max_it=max_it, prob=prob, seed=seed)
+    assert rc == orc_rc
+    for key in ("best_index", "best_count", "iterations_run", "stop_index", "found", "refit_ok"):
+        assert st[key] == ost[key], (key, st, ost)
+    np.testing.assert_array_equal(inl, oinl)  # bit-exact inlier index set, ascending
+    if ost["found"]:
+        assert abs(st["best_rmse"] - ost["best_rmse"]) <= 1e-12 * max(1.0, abs(ost["best_rmse"]))
+    if kind == 2:  # GeneralFit is a no-op for the cylinder: the minimal model, bit-exact
+        np.testing.assert_array_equal(model, omodel)
+    else:          # least-squares refit: summation order differs (the reference's own OMP reduction
+        #            is order-nondeterministic) -> 1e-9 relative / 1e-12 absolute
+        np.testing.assert_allclose(model, omodel, rtol=rtol_refit, atol=1e-12)
+    return st, ost
+
+
+def test_c1_plane_golden(ctx, capi, orc):
+    """BASELINE config C1: fit_plane, 50k points, 100 iterations, seed 1 -- against the committed golden."""
+    g = np.load(os.path.join(GOLD, "c1_plane.npz"))
+    xyz = synth.make_c1()
+    rc, model, inl, st = ctx.ransac_fit(capi.PLANE, xyz, None, 0.01, 100, 0.9999, 1)
+    assert rc == int(g["rc"])
+    np.testing.assert_array_equal(inl, g["inl"])
+    np.testing.assert_allclose(model, g["model"], rtol=0, atol=1e-12)
+    for key in ("best_index", "best_count", "iterations_run", "stop_index"):
+        assert st[key] == int(g[key]), key
+    _check_fit(ctx, capi, orc, capi.PLANE, xyz, None, 0.01, 100, 0.9999, 1)
+
+
+@pytest.mark.parametrize("kind,name,seed", [(1, "small_sphere", 2), (2, "small_cylinder", 3)])
+def test_small_goldens(ctx, capi, orc, kind, name, seed):
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    xyz, nrm = synth.make_c2(n=20000, seed=11)
+    rc, model, inl, st = ctx.ransac_fit(kind, xyz, nrm if kind == 2 else None, 0.01, 300, 0.9999, seed)
+    np.testing.assert_array_equal(inl, g["inl"])
+    np.testing.assert_allclose(model, g["model"], rtol=1e-9, atol=1e-12)
+    for key in ("best_index", "best_count", "iterations_run", "stop_index"):
+        assert st[key] == int(g[key]), key
+
+
+@pytest.mark.parametrize("kind", KINDS)
+@pytest.mark.parametrize("prob", [0.9999, 1.0])
+def test_fit_parity_with_and_without_early_exit(ctx, capi, orc, kind, prob):
+    xyz, nrm = _cloud(kind, 60000, seed=31)
+    st, ost = _check_fit(ctx, capi, orc, kind, xyz, nrm, 0.01, 700, prob, seed=17 + kind)
+    if prob < 1 and kind == 0:
+        assert ost["stop_index"] < 700
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_fit_parity_offset_and_scaled_clouds(ctx, capi, orc, kind):
+    """coordinates far from the origin / millimetre scale: the fp32 copy is centred, the guard band scales"""
+    xyz, nrm = _cloud(kind, 30000, seed=5)
+    _check_fit(ctx, capi, orc, kind, xyz + np.array([1500.0, -2200.0, 870.0]), nrm, 0.01, 200, 1.0, seed=3)
+    _check_fit(ctx, capi, orc, kind, xyz * 1000.0, nrm, 10.0, 200, 1.0, seed=4, rtol_refit=1e-8)
+
+
+def test_fit_parity_nonfinite_points(ctx, capi, orc):
+    xyz = synth.make_c1(n=8000, seed=2)
+    xyz[17] = np.nan
+    xyz[4000, 1] = np.inf
+    _check_fit(ctx, capi, orc, capi.PLANE, xyz, None, 0.01, 150, 1.0, seed=9)
+
+
+def test_degenerate_inputs(ctx, capi, orc):
+    # all points identical: every MinimalFit fails -> no model, zero parameters, FitModel false
+    xyz = np.tile([[0.5, 0.25, -1.0]], (100, 1))
+    rc, model, inl, st = ctx.ransac_fit(capi.PLANE, xyz, None, 0.01, 50, 0.9999, 1)
+    orc_rc, omodel, oinl, ost = orc.ransac_fit(orc.PLANE, xyz, thr=0.01, max_it=50, prob=0.9999, seed=1)
+    assert (rc, st["found"], st["iterations_run"]) == (orc_rc, ost["found"], ost["iterations_run"]) == (0, 0, 0)
+    assert len(inl) == 0 and not model.any()
+    # exactly k points; a perfect plane (fitness 1 -> current_iteration = 0, ransac.h:607-609)
+    xyz = np.array([[0, 0, 0.0], [1, 0, 0], [0, 1, 0]])
+    _check_fit(ctx, capi, orc, capi.PLANE, xyz, None, 0.01, 10, 0.9999, seed=1)
+    plane = np.c_[np.random.default_rng(1).uniform(-1, 1, (500, 2)), np.zeros(500)]
+    _check_fit(ctx, capi, orc, capi.PLANE, plane, None, 0.01, 100, 0.9999, seed=2)
+
+
+def test_error_codes_mirror_the_reference_throws(ctx, capi):
+    xyz = synth.make_c1(n=100, seed=1)
+    with pytest.raises(capi.M3DError) as e:
+        ctx.ransac_fit(capi.PLANE, xyz[:2], None, 0.01, 10, 0.9999, 1)
+    assert e.value.code == capi.ERR_TOO_FEW_POINTS
+    for bad in (0.0, -1.0, 1.5):
+        with pytest.raises(capi.M3DError) as e:
+            ctx.ransac_fit(capi.PLANE, xyz, None, 0.01, 10, bad, 1)
+        assert e.value.code == capi.ERR_PROBABILITY
+    with pytest.raises(capi.M3DError) as e:
+        ctx.ransac_fit(capi.CYLINDER, xyz, None, 0.01, 10, 0.9999, 1)
+    assert e.value.code == capi.ERR_NO_NORMALS
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_evaluate_model_sequential_error_is_bit_exact(ctx, capi, orc, kind):
+    xyz, nrm = _cloud(kind, 30000, seed=77)
+    table = capi.sample_table(5, len(xyz), capi.KSAMPLE[kind], 400)
+    cloud = ctx.upload(xyz, nrm)
+    counts, models, valid = ctx.score_samples(kind, cloud, table, 0.01)
+    best = int(np.argmax(counts * valid))
+    m = models[best, :capi.NPARAM[kind]]
+    ocnt, oerr = orc.evaluate(kind, xyz, m, 0.01)
+    cnt, err = ctx.evaluate_model(kind, cloud, m, 0.01, sequential=True)
+    assert cnt == ocnt and err == oerr  # the reference's index-order sum, bit for bit
+    cnt, err = ctx.evaluate_model(kind, cloud, m, 0.01, sequential=False)
+    assert cnt == ocnt and abs(err - oerr) <= 1e-12 * oerr
+    cloud.free()
+
+
+def test_count_ties_resolved_like_the_sequential_loop(ctx, capi, orc):
+    """few points, coarse threshold: many hypotheses share an inlier count, so the strict
+    rmse tie-break (ransac.h:595-596) decides -- the GPU path must pick the same hypothesis"""
+    rng = np.random.default_rng(4)
+    for trial in range(6):
+        xyz = np.round(rng.uniform(-1, 1, (40, 3)), 1)  # lattice points -> exact ties and duplicates
+        _check_fit(ctx, capi, orc, capi.PLANE, xyz, None, 0.15, 400, 1.0, seed=trial)
+
+
+def test_segmentation_parity(ctx, capi, orc):
+    g = np.load(os.path.join(GOLD, "seg_small.npz"))
+    xyz = synth.make_c3(n=30000, seed=4)
+    rc, planes, labels, ms = ctx.segment_plane_iterative(xyz, 0.01, 100, 0.05, seed=7)
+    assert rc == int(g["rc"]) == 0
+    np.testing.assert_array_equal(labels, g["labels"])  # bit-exact cluster membership
+    np.testing.assert_allclose(planes, g["planes"], rtol=0, atol=1e-12)
+    # a second scene with different parameters against the live oracle
+    xyz = synth.make_c3(n=50000, seed=12)
+    rc, planes, labels, ms = ctx.segment_plane_iterative(xyz, 0.008, 60, 0.1, seed=3)
+    orc_rc, oplanes, olabels = orc.segment_plane_iterative(xyz, 0.008, 60, 0.1, seed=3)
+    assert rc == orc_rc
+    np.testing.assert_array_equal(labels, olabels)
+    np.testing.assert_allclose(planes, oplanes, rtol=0, atol=1e-12)
+    # fewer than 3 points: warning + empty result in the reference (:14-17)
+    rc, planes, labels, ms = ctx.segment_plane_iterative(xyz[:2], 0.01)
+    assert rc == 0 and len(planes) == 0
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_full_size_properties_c2(ctx, capi, kind):
+    """BASELINE config C2 size (1M points): size-independent properties instead of the oracle --
+    fast counts == fp64 reference-order counts, inliers ascending and exactly {d < thr}."""
+    xyz, nrm = synth.make_c2()
+    cloud = ctx.upload(xyz, nrm if kind == 2 else None)
+    table = capi.sample_table(3, len(xyz), capi.KSAMPLE[kind], 4096)
+    counts, models, valid = ctx.score_samples(kind, cloud, table, 0.01)
+    sub = np.r_[np.argsort(counts)[-8:], np.arange(8)]
+    exact, _, _ = ctx.score_samples(kind, cloud, table[sub], 0.01, flags=capi.FLAG_EXACT_ONLY, want_models=False)
+    np.testing.assert_array_equal(counts[sub], exact)
+    rc, model, inl, st = ctx.ransac_fit_cloud(kind, cloud, 0.01, 4096, 1.0, seed=3)
+    assert st["best_count"] == counts.max() == len(inl)
+    assert st["best_index"] == int(np.argmax(np.where(valid > 0, counts, 0)))  # first max, no ties expected
+    assert np.all(np.diff(inl.astype(np.int64)) > 0)
+    cnt, err = ctx.evaluate_model(kind, cloud, models[st["best_index"]], 0.01)
+    assert cnt == len(inl)
+    if kind == 0:  # independent numpy check of the inlier definition on the minimal model
+        m = models[st["best_index"]]
+        d = np.abs((m[0] * xyz[:, 0] + m[2] * xyz[:, 2]) + (m[1] * xyz[:, 1] + m[3])) / np.sqrt(m[0] ** 2 + m[1] ** 2 + m[2] ** 2)
+        np.testing.assert_array_equal(np.nonzero(d < 0.01)[0], inl)
+    cloud.free()

@@ -1,0 +1,148 @@
+"""CPU tests of the product's host side: the C-ABI library loads and exports every symbol the
+header declares, the host-only helpers agree with the oracle, and (world_size 2, gloo) the
+hypothesis-sharded path reproduces the sequential result.  No compute entry point is called:
+those need a GPU and refuse to run without one."""
+import os
+import re
+import socket
+
+import numpy as np
+import pytest
+
+from misc3d_b200 import synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol(capi):
+    hdr = open(os.path.join(ROOT, "include", "m3d_capi.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = sorted(set(re.findall(r"\b(m3d_[a-z0-9_]+)\s*\(", hdr)) - {"m3d_allgather_fn"})
+    assert len(declared) >= 20
+    L = capi.lib()
+    missing = [s for s in declared if not hasattr(L, s)]
+    assert not missing, missing
+    assert sorted(capi.EXPORTS) == declared
+    assert L.m3d_abi_version() == 1
+
+
+def test_no_cpu_fallback(capi):
+    if capi.device_count() > 0:
+        pytest.skip("GPU present")
+    with pytest.raises(capi.M3DError) as e:
+        capi.Context(0)
+    assert e.value.code == capi.ERR_CUDA
+
+
+def test_product_does_not_touch_the_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "misc3d_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp", "Makefile")):
+                txt = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert "oracle" not in txt.replace("the oracle", "").lower() or f == "synth.py", (dirpath, f)
+    for d in ("include", "python"):
+        for dirpath, _, files in os.walk(os.path.join(ROOT, d)):
+            for f in files:
+                txt = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert "m3d_oracle" not in txt and "import orc" not in txt, (dirpath, f)
+
+
+@pytest.mark.parametrize("k,n", [(3, 50000), (4, 1000), (2, 7), (3, 3)])
+def test_sample_table_equals_oracle(capi, orc, k, n):
+    a = capi.sample_table(99, n, k, 500)
+    b = orc.sample_table(99, n, k, 500)
+    np.testing.assert_array_equal(a, b)
+    assert all(len(set(r)) == k for r in a.tolist())
+
+
+def _oracle_counts(orc, kind, xyz, nrm, table, thr):
+    """per-hypothesis (valid, count, err) with the oracle's building blocks"""
+    H = len(table)
+    valid = np.zeros(H, np.uint8)
+    counts = np.zeros(H, np.uint64)
+    err = np.zeros(H)
+    for i, row in enumerate(table):
+        idx = np.sort(row)
+        ok, m = orc.minimal_fit(kind, xyz[idx], None if nrm is None else nrm[idx])
+        if ok:
+            valid[i] = 1
+            counts[i], err[i] = orc.evaluate(kind, xyz, m, thr)
+    return valid, counts, err
+
+
+@pytest.mark.parametrize("prob", [0.9999, 0.99, 1.0])
+def test_ordered_scan_replays_the_sequential_loop(capi, orc, prob):
+    xyz = synth.make_c1(n=3000, seed=21)
+    H, thr, seed = 300, 0.01, 5
+    table = orc.sample_table(seed, len(xyz), 3, H)
+    valid, counts, err = _oracle_counts(orc, orc.PLANE, xyz, None, table, thr)
+    st = capi.ordered_scan(counts, valid, err, len(xyz), 3, prob, H)
+    rc, model, inl, ost = orc.ransac_fit(orc.PLANE, xyz, thr=thr, max_it=H, prob=prob, seed=seed)
+    for key in ("best_index", "best_count", "iterations_run", "stop_index", "found"):
+        assert st[key] == ost[key], key
+    if prob < 1.0:
+        assert ost["stop_index"] < H  # the adaptive exit really fired in this case
+
+
+def test_ordered_scan_tie_break_uses_rmse(capi):
+    counts = np.array([10, 10, 10, 7], np.uint64)
+    valid = np.ones(4, np.uint8)
+    err = np.array([3.0, 2.0, 2.0, 0.1])
+    st = capi.ordered_scan(counts, valid, err, 100, 3, 1.0, 4)
+    assert st["best_index"] == 1  # strictly smaller rmse wins, an equal one does not (ransac.h:595-596)
+    st = capi.ordered_scan(np.array([0, 0], np.uint64), np.ones(2, np.uint8), None, 100, 3, 1.0, 2)
+    assert st["found"] == 0 and st["iterations_run"] == 2
+    st = capi.ordered_scan(np.array([5, 9], np.uint64), np.array([0, 1], np.uint8), None, 100, 3, 1.0, 2)
+    assert st["best_index"] == 1 and st["iterations_run"] == 1  # failed MinimalFit is not counted
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _shard_worker(rank, world, port, q):
+    import sys
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import torch
+    import torch.distributed as dist
+    import orc
+    from misc3d_b200 import capi, synth as sy
+    from misc3d_b200.sharding import shard_rows, gather_counts
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    xyz = sy.make_c1(n=2000, seed=8)
+    H, thr, seed = 101, 0.01, 3
+    table = capi.sample_table(seed, len(xyz), 3, H)  # every rank draws the same global table
+    lo, hi, S = shard_rows(H, rank, world)
+    valid, counts, _ = _oracle_counts(orc, orc.PLANE, xyz, None, table[lo:hi], thr)
+    packed = np.zeros(S, np.uint32)
+    packed[: hi - lo] = counts.astype(np.uint32) | ((1 - valid).astype(np.uint32) << 31)
+    allc = gather_counts(packed, world, lambda t, outs: dist.all_gather(outs, t))[:H]
+    st = capi.ordered_scan(allc & 0x7FFFFFFF, ((allc >> 31) == 0).astype(np.uint8), None, len(xyz), 3, 0.9999, H)
+    q.put((rank, st["best_index"], st["best_count"], st["iterations_run"], st["stop_index"]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_counts_over_gloo_match_single_process(capi, orc):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_shard_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    xyz = synth.make_c1(n=2000, seed=8)
+    rc, model, inl, ost = orc.ransac_fit(orc.PLANE, xyz, thr=0.01, max_it=101, prob=0.9999, seed=3)
+    for r in res:
+        assert r[1:] == (ost["best_index"], ost["best_count"], ost["iterations_run"], ost["stop_index"])
