@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libm3d_b200.so")
+LIB_PATH = os.environ.get("M3D_LIB") or os.path.join(_HERE, "libm3d_b200.so")  # M3D_LIB: tuning builds only
 
 PLANE, SPHERE, CYLINDER = 0, 1, 2
 KSAMPLE = {PLANE: 3, SPHERE: 4, CYLINDER: 2}

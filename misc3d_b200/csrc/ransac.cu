@@ -92,7 +92,12 @@ int launch_score_t(m3d_ctx *ctx, const ScoreArgs &a, uint32_t ntiles) {
     /* point chunks: enough CTAs for >= ~8 balanced waves over the SMs, each chunk a whole number
      * of tiles.  Grid = hypothesis blocks x point chunks, chunks a multiple of the SM count. */
     const uint32_t resident = (uint32_t)ctx->sm_count * (THREADS >= 256 ? 2u : 4u);
-    uint32_t chunks = std::max<uint32_t>(1, (8 * resident + hb - 1) / hb);
+    static int waves = 0;
+    if (!waves) {
+        const char *e = getenv("M3D_CHUNK_WAVES");
+        waves = (e && atoi(e) > 0) ? atoi(e) : 8;
+    }
+    uint32_t chunks = std::max<uint32_t>(1, (waves * resident + hb - 1) / hb);
     chunks = ((chunks + ctx->sm_count - 1) / ctx->sm_count) * ctx->sm_count;
     chunks = std::min(chunks, ntiles);
     ScoreArgs b = a;
@@ -104,9 +109,30 @@ int launch_score_t(m3d_ctx *ctx, const ScoreArgs &a, uint32_t ntiles) {
     return M3D_OK;
 }
 
+/* tuning knob for experiments: M3D_SCORE_VARIANT=<threads>x<hypotheses per thread> */
+int score_variant_override() {
+    static int v = -1;
+    if (v < 0) {
+        v = 0;
+        if (const char *e = getenv("M3D_SCORE_VARIANT")) {
+            int t = 0, h = 0;
+            if (sscanf(e, "%dx%d", &t, &h) == 2) v = t * 16 + h;
+        }
+    }
+    return v;
+}
+
 template <int KIND>
 int launch_score(m3d_ctx *ctx, const m3d_cloud *c, ScoreArgs a, bool exact_only) {
     const uint32_t ntiles = std::max<uint32_t>(1, (a.n + kTile - 1) / kTile);
+    /* per-launch scratch: the minimal models and the queue of guard-band (hypothesis, point) pairs */
+    constexpr uint32_t kQueueCap = 1u << 22;
+    M3D_CUDA(ctx, ctx->d_models.reserve(sizeof(double) * 8 * (size_t)a.rows));
+    M3D_CUDA(ctx, ctx->d_queue.reserve(sizeof(uint2) * (size_t)kQueueCap + 16));
+    a.models = ctx->d_models.as<double>();
+    a.queue_count = ctx->d_queue.as<uint32_t>();
+    a.queue = reinterpret_cast<uint2 *>(ctx->d_queue.as<char>() + 16);
+    a.queue_cap = kQueueCap;
     if (exact_only || c->h_meta.nonfinite) {
         const uint32_t hb = (a.rows + 127) / 128;
         uint32_t chunks = std::min<uint32_t>(ntiles, std::max<uint32_t>(1, (4u * ctx->sm_count * 4u) / hb));
@@ -116,8 +142,23 @@ int launch_score(m3d_ctx *ctx, const m3d_cloud *c, ScoreArgs a, bool exact_only)
         M3D_LAUNCHED(ctx);
         return M3D_OK;
     }
-    if (a.rows >= 2048) return launch_score_t<KIND, 256, 2>(ctx, a, ntiles);
-    return launch_score_t<KIND, 128, 1>(ctx, a, ntiles);
+    M3D_CUDA(ctx, cudaMemsetAsync(a.queue_count, 0, sizeof(uint32_t), ctx->stream));
+    int rc;
+    switch (score_variant_override()) {
+        case 128 * 16 + 1: rc = launch_score_t<KIND, 128, 1>(ctx, a, ntiles); break;
+        case 128 * 16 + 2: rc = launch_score_t<KIND, 128, 2>(ctx, a, ntiles); break;
+        case 128 * 16 + 4: rc = launch_score_t<KIND, 128, 4>(ctx, a, ntiles); break;
+        case 256 * 16 + 1: rc = launch_score_t<KIND, 256, 1>(ctx, a, ntiles); break;
+        case 256 * 16 + 2: rc = launch_score_t<KIND, 256, 2>(ctx, a, ntiles); break;
+        case 256 * 16 + 4: rc = launch_score_t<KIND, 256, 4>(ctx, a, ntiles); break;
+        default:
+            rc = (a.rows >= 2048) ? launch_score_t<KIND, 256, 2>(ctx, a, ntiles)
+                                  : launch_score_t<KIND, 128, 1>(ctx, a, ntiles);
+    }
+    if (rc) return rc;
+    resolve_queue_kernel<KIND><<<ctx->sm_count * 2, 256, 0, ctx->stream>>>(a);
+    M3D_LAUNCHED(ctx);
+    return M3D_OK;
 }
 
 int launch_score_kind(m3d_ctx *ctx, int kind, const m3d_cloud *c, const ScoreArgs &a, bool exact_only) {

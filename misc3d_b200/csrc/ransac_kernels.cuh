@@ -24,7 +24,10 @@ namespace m3d {
 
 constexpr int kTile = 1024;  /* points per TMA stage (16 KB)                      */
 constexpr int kStages = 3;   /* ring depth                                        */
-constexpr int kSub = 128;    /* points between two "any ambiguous point?" checks  */
+#ifndef M3D_SUB
+#define M3D_SUB 32
+#endif
+constexpr int kSub = M3D_SUB; /* points between two "any ambiguous point?" checks */
 constexpr uint32_t kInvalidBit = 0x80000000u;
 constexpr double kU32 = 5.9604644775390625e-08; /* 2^-24 */
 constexpr double kU64 = 1.1102230246251565e-16; /* 2^-53 */
@@ -389,6 +392,10 @@ struct ScoreArgs {
     const uint32_t *samples; /* rows x k of this wave (device)                          */
     uint32_t *counts;        /* [rows]: inlier count (atomicAdd per chunk), bit31 = MinimalFit false */
     unsigned long long *resolves;
+    double *models;        /* [rows][8] minimal models (written by the point-chunk-0 CTAs)  */
+    uint2 *queue;          /* (local row, point) pairs inside the guard band                */
+    uint32_t *queue_count; /* atomic cursor of `queue`                                      */
+    uint32_t queue_cap;
     double thr;
     uint32_t n;
     uint32_t row_begin; /* first row of the wave buffer this launch scores             */
@@ -402,21 +409,51 @@ template <int KIND>
 __device__ __noinline__ void resolve_subtile(const ScoreArgs &a, uint32_t row, const Fast<KIND> f,
                                              const float4 *sp, uint32_t gbase, int cnt,
                                              uint32_t &clo, uint32_t &cout, uint32_t &nres) {
-    double m[8];
-    const bool ok = fit_row<KIND>(a.xyz, a.nrm, a.samples, row, m);
+    bool have_model = false, ok = false;
     ex::Dist<KIND> dist;
-    if (ok) dist.set(m);
     for (int j = 0; j < cnt; ++j) {
         const float at = fabsf(fast_eval<KIND>(f, sp[j]));
         if (is_ambiguous<M3D_COUNT_FORM>(at, f.lo, f.hi)) {
+            ++nres;
+            /* normal case: queue (hypothesis, point) for resolve_queue_kernel and count the point
+             * as an outlier for now */
+            const uint32_t pos = atomicAdd(a.queue_count, 1u);
+            if (pos < a.queue_cap) {
+                a.queue[pos] = make_uint2(row - a.row_begin, gbase + j);
+                ++cout;
+                continue;
+            }
+            /* queue full: decide here */
+            if (!have_model) {
+                double m[8];
+                ok = fit_row<KIND>(a.xyz, a.nrm, a.samples, row, m);
+                if (ok) dist.set(m);
+                have_model = true;
+            }
             bool in = false;
             if (ok) in = dist(ex::ld3(a.xyz + 3 * (size_t)(gbase + j))) < a.thr;
             if (in)
                 ++clo;
             else
                 ++cout;
-            ++nres;
         }
+    }
+}
+
+/* second half of the rare path: one thread per queued (hypothesis, point) pair evaluates the
+ * reference's fp64 predicate with the model the scoring kernel stored */
+template <int KIND>
+__global__ void __launch_bounds__(256) resolve_queue_kernel(const ScoreArgs a) {
+    const uint32_t total = min(*a.queue_count, a.queue_cap);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const uint2 e = a.queue[i];
+        if (a.counts[e.x] & kInvalidBit) continue; /* MinimalFit failed: no inliers */
+        double m[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) m[k] = a.models[(size_t)e.x * 8 + k];
+        ex::Dist<KIND> dist;
+        dist.set(m);
+        if (dist(ex::ld3(a.xyz + 3 * (size_t)e.y)) < a.thr) atomicAdd(&a.counts[e.x], 1u);
     }
 }
 
@@ -457,6 +494,11 @@ __global__ void __launch_bounds__(THREADS) score_kernel(const ScoreArgs a) {
         bool ok = false;
         if (row[h] < a.rows) ok = fit_row<KIND>(a.xyz, a.nrm, a.samples, a.row_begin + row[h], m);
         invalid[h] = (row[h] < a.rows) && !ok;
+        if (blockIdx.y == 0 && row[h] < a.rows) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                a.models[(size_t)row[h] * 8 + i] = (ok && i < param_count(KIND)) ? m[i] : 0.0;
+        }
         make_fast<KIND>(m, ok, M, a.thr, f[h]);
         clo[h] = 0;
         cout[h] = 0;
@@ -529,6 +571,10 @@ __global__ void __launch_bounds__(128) score_exact_kernel(const ScoreArgs a) {
     if (row >= a.rows) return;
     double m[8];
     const bool ok = fit_row<KIND>(a.xyz, a.nrm, a.samples, a.row_begin + row, m);
+    if (blockIdx.y == 0) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) a.models[(size_t)row * 8 + i] = (ok && i < param_count(KIND)) ? m[i] : 0.0;
+    }
     if (!ok) {
         if (blockIdx.y == 0) atomicOr(&a.counts[row], kInvalidBit);
         return;

@@ -1,0 +1,73 @@
+"""Tuning sweep of the scoring kernel on the C2 cloud (run on the GPU box).
+
+  python tools/score_sweep.py build      # compile the library variants (CPU box, nvcc)
+  python tools/score_sweep.py run        # time every (library variant x launch variant x primitive)
+  python tools/score_sweep.py one        # (internal) one configuration, JSON line on stdout
+"""
+import itertools
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+LIBS = {  # name -> extra nvcc flags
+    "f4s32": "-DM3D_COUNT_FORM=4 -DM3D_SUB=32",
+    "f1s32": "-DM3D_COUNT_FORM=1 -DM3D_SUB=32",
+    "f3s32": "-DM3D_COUNT_FORM=3 -DM3D_SUB=32",
+    "f4s64": "-DM3D_COUNT_FORM=4 -DM3D_SUB=64",
+    "f4s128": "-DM3D_COUNT_FORM=4 -DM3D_SUB=128",
+}
+LAUNCH = ["256x2", "128x2", "256x1", "128x4", "256x4", "128x1"]
+
+
+def build():
+    for name, extra in LIBS.items():
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "misc3d_b200", "csrc"), "-s", "-j4",
+                               f"VARIANT={name}", f"EXTRA={extra}"])
+
+
+def one():
+    import numpy as np
+    from misc3d_b200 import capi, synth
+    xyz, nrm = synth.make_c2()
+    ctx = capi.Context(0)
+    cloud = ctx.upload(xyz, nrm)
+    out = {}
+    for kind, name in ((0, "plane"), (1, "sphere"), (2, "cylinder")):
+        ms = []
+        for rep in range(4):
+            rc, model, inl, st = ctx.ransac_fit_cloud(kind, cloud, 0.01, 10000, 1.0, seed=rep, want_inliers=False)
+            ms.append(st["score_ms"])
+        out[name] = {"score_ms": float(np.min(ms[1:])), "resolves": st["exact_resolves"],
+                     "Gpairs_per_s": 1e10 / (float(np.min(ms[1:])) * 1e-3) / 1e9}
+    print(json.dumps(out))
+
+
+def run():
+    rows = []
+    for lib, launch in itertools.chain(((l, "256x2") for l in LIBS), (("f4s32", v) for v in LAUNCH[1:]),
+                                       (("f1s32", v) for v in LAUNCH[1:4])):
+        env = dict(os.environ, M3D_LIB=os.path.join(ROOT, "misc3d_b200", "variants", f"libm3d_{lib}.so"),
+                   M3D_SCORE_VARIANT=launch)
+        r = subprocess.run([sys.executable, __file__, "one"], env=env, capture_output=True, text=True)
+        try:
+            d = json.loads(r.stdout.strip().splitlines()[-1])
+        except Exception:
+            d = {"error": (r.stderr or r.stdout)[-400:]}
+        rows.append({"lib": lib, "launch": launch, **d})
+        print(json.dumps(rows[-1]), flush=True)
+    for waves in (4, 16, 32):
+        env = dict(os.environ, M3D_LIB=os.path.join(ROOT, "misc3d_b200", "variants", "libm3d_f4s32.so"),
+                   M3D_SCORE_VARIANT="256x2", M3D_CHUNK_WAVES=str(waves))
+        r = subprocess.run([sys.executable, __file__, "one"], env=env, capture_output=True, text=True)
+        try:
+            d = json.loads(r.stdout.strip().splitlines()[-1])
+        except Exception:
+            d = {"error": (r.stderr or r.stdout)[-400:]}
+        print(json.dumps({"lib": "f4s32", "launch": "256x2", "waves": waves, **d}), flush=True)
+
+
+if __name__ == "__main__":
+    {"build": build, "run": run, "one": one}[sys.argv[1]]()
