@@ -1,11 +1,510 @@
-/* matching.cu -- placeholder until the brute-force L2 kernel lands (same session). */
+/*
+ * matching.cu -- descriptor correspondence matching on sm_100a.
+ *
+ * Replaces misc3d::registration::ANNMatcher::Match / NearestSearch
+ * (src/correspondence_matching.cpp:13-84): bidirectional 1-NN in descriptor space followed by the
+ * mutual cross-check (:67-78).  The reference searches with FLANN (exact kd-tree) or Annoy
+ * (approximate); here both enum values run one exact brute-force search:
+ *
+ *   nn_top2_kernel   fp32 |a|^2 + |b|^2 - 2 a.b over 128 x 128 tiles (descriptors staged k-major
+ *                    in shared memory by 1-D TMA bulk copies, 8 x 8 register micro-tiles), keeping
+ *                    the best and second-best distance of every query row;
+ *   nn_exact_kernel  rows whose best/second-best gap is inside the fp32 error bound are searched
+ *                    again in fp64 with the reference metric's accumulation order (nanoflann
+ *                    L2_Adaptor: groups of four) and the lowest-index tie rule;
+ *   mutual_*         nn10[nn01[i]] == i, stable compaction in ascending source index.
+ */
+#include <algorithm>
+#include <vector>
+
 #include "context.h"
+#include "exact_math.cuh"
+
+namespace m3d {
+
+constexpr int kMT = 128;      /* descriptors per tile */
+constexpr int kMaxKP = 128;   /* largest (padded) dimension the fp32 tile kernel handles */
+constexpr float kPadNorm = 1e38f;
+
+__device__ __forceinline__ uint32_t m_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void m_mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(m_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void m_mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}\n" ::"r"(m_smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void m_tma_load_1d(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    const uint32_t b = m_smem_u32(bar);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            m_smem_u32(dst)),
+        "l"(src), "r"(bytes), "r"(b)
+        : "memory");
+}
+
+/* order-preserving map double -> uint64 (for atomicMin/atomicMax) */
+__device__ __forceinline__ unsigned long long enc_f64(double x) {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(x);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double dec_f64(unsigned long long e) {
+    const unsigned long long b = (e >> 63) ? (e & 0x7fffffffffffffffull) : ~e;
+    return __longlong_as_double((long long)b);
+}
+
+/* per-dimension min / max over a descriptor set (F: dim x count column-major) */
+__global__ void __launch_bounds__(256) feat_minmax_kernel(const double *__restrict__ F, size_t total, int dim,
+                                                          unsigned long long *__restrict__ mn,
+                                                          unsigned long long *__restrict__ mx) {
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+        const double v = F[e];
+        if (v != v) continue;
+        const int k = (int)(e % (size_t)dim);
+        const unsigned long long c = enc_f64(v);
+        if (c < mn[k]) atomicMin(&mn[k], c);
+        if (c > mx[k]) atomicMax(&mx[k], c);
+    }
+}
+__global__ void feat_center_kernel(const unsigned long long *mn, const unsigned long long *mx, int dim,
+                                   double *center) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= dim) return;
+    const double c = 0.5 * (dec_f64(mn[k]) + dec_f64(mx[k]));
+    center[k] = isfinite(c) ? c : 0.0;
+}
+
+/* fp64 column-major descriptors -> centred fp32 tiles [(KP+1)][128] (k-major; row KP = |.|^2) */
+__global__ void __launch_bounds__(128) feat_convert_kernel(const double *__restrict__ F, uint32_t count, int dim,
+                                                           int KP, const double *__restrict__ center,
+                                                           float *__restrict__ tiles,
+                                                           uint32_t *__restrict__ maxnorm_bits) {
+    const uint32_t tile = blockIdx.x, lane = threadIdx.x;
+    const uint32_t j = tile * kMT + lane;
+    float *t = tiles + (size_t)tile * (KP + 1) * kMT;
+    double n2 = 0;
+    if (j < count) {
+        for (int k = 0; k < dim; ++k) {
+            const double v = F[(size_t)j * dim + k] - center[k];
+            n2 += v * v;
+            t[(size_t)k * kMT + lane] = (float)v;
+        }
+        for (int k = dim; k < KP; ++k) t[(size_t)k * kMT + lane] = 0.f;
+        const float nf = (float)n2;
+        t[(size_t)KP * kMT + lane] = nf;
+        if (nf == nf && nf < 3e38f) atomicMax(maxnorm_bits, __float_as_uint(nf));
+    } else {
+        for (int k = 0; k < KP; ++k) t[(size_t)k * kMT + lane] = 0.f;
+        t[(size_t)KP * kMT + lane] = kPadNorm;
+    }
+}
+
+/* best / second-best neighbour of every row of A among the columns B */
+__global__ void __launch_bounds__(256, 2) nn_top2_kernel(const float *__restrict__ At, const float *__restrict__ Bt,
+                                                         uint32_t na, uint32_t nb, int KP,
+                                                         const uint32_t *__restrict__ maxnorm_bits,
+                                                         uint32_t *__restrict__ nn, uint32_t *__restrict__ amb_list,
+                                                         uint32_t *__restrict__ amb_count) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int tile_f = (KP + 1) * kMT;
+    float *As = reinterpret_cast<float *>(smem_raw);
+    float *Bs = As + tile_f;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(Bs + 2 * tile_f);
+    const uint32_t tile_bytes = (uint32_t)tile_f * 4u;
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const uint32_t ntb = (nb + kMT - 1) / kMT;
+
+    if (tid == 0) {
+        m_mbar_init(&bars[0], 1);
+        m_mbar_init(&bars[1], 1);
+        m_mbar_init(&bars[2], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        m_tma_load_1d(As, At + (size_t)blockIdx.x * tile_f, tile_bytes, &bars[2]);
+        m_tma_load_1d(Bs, Bt, tile_bytes, &bars[0]);
+        if (ntb > 1) m_tma_load_1d(Bs + tile_f, Bt + (size_t)tile_f, tile_bytes, &bars[1]);
+    }
+    __syncthreads();
+    m_mbar_wait(&bars[2], 0);
+
+    float an[8], m1[8], m2[8];
+    uint32_t i1[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        an[r] = As[KP * kMT + ty * 8 + r];
+        m1[r] = INFINITY;
+        m2[r] = INFINITY;
+        i1[r] = 0;
+    }
+    const int c_lo = tx * 4, c_hi = 64 + tx * 4; /* this thread's columns: c_lo..+3 and c_hi..+3 */
+
+    for (uint32_t t = 0; t < ntb; ++t) {
+        const float *B = Bs + (size_t)(t & 1) * tile_f;
+        m_mbar_wait(&bars[t & 1], (t >> 1) & 1);
+        float acc[8][8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+#pragma unroll
+            for (int c = 0; c < 8; ++c) acc[r][c] = 0.f;
+#pragma unroll 4
+        for (int k = 0; k < KP; ++k) {
+            const float4 a0 = *reinterpret_cast<const float4 *>(As + k * kMT + ty * 8);
+            const float4 a1 = *reinterpret_cast<const float4 *>(As + k * kMT + ty * 8 + 4);
+            const float4 b0 = *reinterpret_cast<const float4 *>(B + k * kMT + c_lo);
+            const float4 b1 = *reinterpret_cast<const float4 *>(B + k * kMT + c_hi);
+            const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+            for (int r = 0; r < 8; ++r)
+#pragma unroll
+                for (int c = 0; c < 8; ++c) acc[r][c] = fmaf(a[r], b[c], acc[r][c]);
+        }
+        const float4 n0 = *reinterpret_cast<const float4 *>(B + KP * kMT + c_lo);
+        const float4 n1 = *reinterpret_cast<const float4 *>(B + KP * kMT + c_hi);
+        const float bn[8] = {n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, n1.z, n1.w};
+        const uint32_t jbase = t * kMT;
+        const bool last = (t == ntb - 1);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const uint32_t j = jbase + (c < 4 ? c_lo + c : c_hi + c - 4);
+            if (last && j >= nb) continue;
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                const float d = fmaf(-2.f, acc[r][c], an[r] + bn[c]);
+                if (d < m2[r]) {
+                    if (d < m1[r]) {
+                        m2[r] = m1[r];
+                        m1[r] = d;
+                        i1[r] = j;
+                    } else {
+                        m2[r] = d;
+                    }
+                }
+            }
+        }
+        __syncthreads(); /* everyone is done with this stage */
+        if (tid == 0 && t + 2 < ntb)
+            m_tma_load_1d(Bs + (size_t)(t & 1) * tile_f, Bt + (size_t)(t + 2) * tile_f, tile_bytes, &bars[t & 1]);
+    }
+
+    /* merge the 16 threads (tx) that share a row; columns of a thread ascend with tx within each
+     * half, so ties are resolved on the index explicitly */
+    const float bnmax = __uint_as_float(*maxnorm_bits);
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        float a1 = m1[r], a2 = m2[r];
+        uint32_t ai = i1[r];
+#pragma unroll
+        for (int o = 1; o < 16; o <<= 1) {
+            const float b1 = __shfl_xor_sync(0xffffffffu, a1, o);
+            const float b2 = __shfl_xor_sync(0xffffffffu, a2, o);
+            const uint32_t bi = __shfl_xor_sync(0xffffffffu, ai, o);
+            if (b1 < a1 || (b1 == a1 && bi < ai)) {
+                a2 = fminf(a1, b2);
+                a1 = b1;
+                ai = bi;
+            } else {
+                a2 = fminf(a2, b1);
+            }
+        }
+        const uint32_t row = blockIdx.x * kMT + ty * 8 + r;
+        if (tx == 0 && row < na) {
+            nn[row] = ai;
+            /* |d32 - exact| <= (KP + 10) * 2^-24 * (|a|^2 + max|b|^2) */
+            const float E = (float)(KP + 10) * 5.9604645e-08f * (an[r] + bnmax);
+            if (!(a2 - a1 > 2.5f * E)) amb_list[atomicAdd(amb_count, 1u)] = row;
+        }
+    }
+}
+
+/* nanoflann L2_Adaptor::evalMetric order: groups of four, then the tail */
+__device__ __forceinline__ double l2_groups4(const double *a, const double *b, int dim) {
+    double result = 0;
+    int d = 0;
+    for (; d + 3 < dim; d += 4) {
+        const double d0 = ex::sub(a[d], b[d]), d1 = ex::sub(a[d + 1], b[d + 1]), d2 = ex::sub(a[d + 2], b[d + 2]),
+                     d3 = ex::sub(a[d + 3], b[d + 3]);
+        result = ex::add(result, ex::add(ex::add(ex::add(ex::mul(d0, d0), ex::mul(d1, d1)), ex::mul(d2, d2)),
+                                         ex::mul(d3, d3)));
+    }
+    for (; d < dim; ++d) {
+        const double d0 = ex::sub(a[d], b[d]);
+        result = ex::add(result, ex::mul(d0, d0));
+    }
+    return result;
+}
+
+/* exact 1-NN (strict <, lowest index on ties) for the listed rows; one CTA per row.
+ * list == nullptr: all rows 0..na-1 */
+__global__ void __launch_bounds__(256) nn_exact_kernel(const double *__restrict__ A, const double *__restrict__ B,
+                                                       uint32_t na, uint32_t nb, int dim,
+                                                       const uint32_t *__restrict__ list,
+                                                       const uint32_t *__restrict__ list_count,
+                                                       uint32_t *__restrict__ nn) {
+    extern __shared__ double qa[]; /* dim doubles */
+    __shared__ double sd[8];
+    __shared__ uint32_t sj[8];
+    const uint32_t total = list ? *list_count : na;
+    for (uint32_t it = blockIdx.x; it < total; it += gridDim.x) {
+        const uint32_t row = list ? list[it] : it;
+        __syncthreads();
+        for (int k = threadIdx.x; k < dim; k += blockDim.x) qa[k] = A[(size_t)row * dim + k];
+        __syncthreads();
+        double best = INFINITY;
+        uint32_t bj = 0xffffffffu;
+        for (uint32_t j = threadIdx.x; j < nb; j += blockDim.x) {
+            const double d = l2_groups4(qa, B + (size_t)j * dim, dim);
+            if (d < best) {
+                best = d;
+                bj = j;
+            }
+        }
+        for (int o = 16; o; o >>= 1) {
+            const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+            const uint32_t oj = __shfl_xor_sync(0xffffffffu, bj, o);
+            if (ob < best || (ob == best && oj < bj)) {
+                best = ob;
+                bj = oj;
+            }
+        }
+        if ((threadIdx.x & 31) == 0) {
+            sd[threadIdx.x >> 5] = best;
+            sj[threadIdx.x >> 5] = bj;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int w = 1; w < 8; ++w)
+                if (sd[w] < best || (sd[w] == best && sj[w] < bj)) {
+                    best = sd[w];
+                    bj = sj[w];
+                }
+            nn[row] = (bj == 0xffffffffu) ? 0u : bj; /* nothing compared below +inf: the reference keeps 0 */
+        }
+    }
+}
+
+/* ---- mutual check (correspondence_matching.cpp:67-78) + stable compaction */
+constexpr int kMB = 256, kMItems = 8;
+__device__ __forceinline__ bool mutual(const uint32_t *nn01, const uint32_t *nn10, uint32_t i, uint32_t nd) {
+    const uint32_t j = nn01[i];
+    return j < nd && nn10[j] == i;
+}
+__global__ void __launch_bounds__(kMB) mutual_count_kernel(const uint32_t *__restrict__ nn01,
+                                                           const uint32_t *__restrict__ nn10, uint32_t ns,
+                                                           uint32_t nd, uint32_t *__restrict__ blk_cnt) {
+    uint32_t c = 0;
+    const uint32_t base = blockIdx.x * kMB * kMItems;
+    for (int it = 0; it < kMItems; ++it) {
+        const uint32_t i = base + it * kMB + threadIdx.x;
+        if (i < ns && mutual(nn01, nn10, i, nd)) ++c;
+    }
+    __shared__ uint32_t sh[8];
+    for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t s = 0;
+        for (int k = 0; k < 8; ++k) s += sh[k];
+        blk_cnt[blockIdx.x] = s;
+    }
+}
+__global__ void mutual_scan_kernel(const uint32_t *__restrict__ blk_cnt, uint32_t nblk,
+                                   uint32_t *__restrict__ blk_off, uint32_t *__restrict__ total) {
+    if (threadIdx.x != 0) return; /* nblk <= ~1000: a serial scan is a few microseconds */
+    uint32_t run = 0;
+    for (uint32_t b = 0; b < nblk; ++b) {
+        blk_off[b] = run;
+        run += blk_cnt[b];
+    }
+    *total = run;
+}
+__global__ void __launch_bounds__(kMB) mutual_write_kernel(const uint32_t *__restrict__ nn01,
+                                                           const uint32_t *__restrict__ nn10, uint32_t ns,
+                                                           uint32_t nd, const uint32_t *__restrict__ blk_off,
+                                                           unsigned long long *__restrict__ idx0,
+                                                           unsigned long long *__restrict__ idx1) {
+    __shared__ uint32_t wcnt[8];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    uint32_t running = blk_off[blockIdx.x];
+    const uint32_t base = blockIdx.x * kMB * kMItems;
+    for (int it = 0; it < kMItems; ++it) {
+        const uint32_t i = base + it * kMB + threadIdx.x;
+        const bool f = i < ns && mutual(nn01, nn10, i, nd);
+        const uint32_t bal = __ballot_sync(0xffffffffu, f);
+        if (lane == 0) wcnt[w] = __popc(bal);
+        __syncthreads();
+        uint32_t before = 0, tot = 0;
+        for (int k = 0; k < 8; ++k) {
+            before += (k < w) ? wcnt[k] : 0;
+            tot += wcnt[k];
+        }
+        if (f) {
+            const uint32_t pos = running + before + __popc(bal & ((1u << lane) - 1));
+            idx0[pos] = i;
+            idx1[pos] = nn01[i];
+        }
+        running += tot;
+        __syncthreads();
+    }
+}
+
+/* ------------------------------------------------------------------------------ host side */
+struct FeatDev {
+    double *f64 = nullptr; /* dim x count, column-major */
+    float *tiles = nullptr;
+    uint32_t count = 0, ntiles = 0;
+};
+
+struct MatchScratch { /* layout of the small device block */
+    unsigned long long mn[kMaxKP], mx[kMaxKP];
+    double center[kMaxKP];
+    uint32_t maxnorm[2]; /* per set */
+    uint32_t amb_count[2];
+    uint32_t total;
+};
+
+static int nn_direction(m3d_ctx *ctx, const FeatDev &A, const FeatDev &B, int dim, int KP, bool fast,
+                        const uint32_t *d_maxnorm_B, uint32_t *d_nn, uint32_t *d_amb, uint32_t *d_amb_count) {
+    if (fast) {
+        const size_t smem = (size_t)3 * (KP + 1) * kMT * sizeof(float) + 3 * sizeof(uint64_t);
+        M3D_CUDA(ctx, cudaFuncSetAttribute(nn_top2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        nn_top2_kernel<<<A.ntiles, 256, smem, ctx->stream>>>(A.tiles, B.tiles, A.count, B.count, KP, d_maxnorm_B,
+                                                            d_nn, d_amb, d_amb_count);
+        M3D_LAUNCHED(ctx);
+        nn_exact_kernel<<<ctx->sm_count * 4, 256, sizeof(double) * dim, ctx->stream>>>(
+            A.f64, B.f64, A.count, B.count, dim, d_amb, d_amb_count, d_nn);
+        M3D_LAUNCHED(ctx);
+    } else {
+        nn_exact_kernel<<<ctx->sm_count * 4, 256, sizeof(double) * dim, ctx->stream>>>(
+            A.f64, B.f64, A.count, B.count, dim, nullptr, nullptr, d_nn);
+        M3D_LAUNCHED(ctx);
+    }
+    return M3D_OK;
+}
+
+/* uploads both descriptor sets, builds the fp32 tiles; returns device handles in A, B */
+static int match_impl(m3d_ctx *ctx, const double *src, size_t ns, const double *dst, size_t nd, int dim,
+                      bool both_directions, size_t *nn_out, size_t *idx0, size_t *idx1, size_t *n_out,
+                      float *device_ms) {
+    if (!ctx || dim <= 0 || (ns && !src) || (nd && !dst)) return M3D_ERR_INVALID_ARG;
+    if (ns >= (1ull << 31) || nd >= (1ull << 31)) return ctx->fail(M3D_ERR_INVALID_ARG, "more than 2^31 descriptors");
+    M3D_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (n_out) *n_out = 0;
+    if (device_ms) *device_ms = 0;
+    if (ns == 0 || nd == 0) return M3D_OK;
+    const int KP = (dim + 3) & ~3;
+    const bool fast = KP <= kMaxKP;
+    FeatDev A, B;
+    A.count = (uint32_t)ns;
+    B.count = (uint32_t)nd;
+    A.ntiles = (A.count + kMT - 1) / kMT;
+    B.ntiles = (B.count + kMT - 1) / kMT;
+    const size_t fa = sizeof(double) * (size_t)dim * ns, fb = sizeof(double) * (size_t)dim * nd;
+    const size_t ta = fast ? sizeof(float) * (size_t)A.ntiles * (KP + 1) * kMT : 16;
+    const size_t tb = fast ? sizeof(float) * (size_t)B.ntiles * (KP + 1) * kMT : 16;
+    M3D_CUDA(ctx, ctx->d_tmp0.reserve(fa));
+    M3D_CUDA(ctx, ctx->d_tmp1.reserve(fb));
+    M3D_CUDA(ctx, ctx->d_tmp2.reserve(ta));
+    M3D_CUDA(ctx, ctx->d_tmp3.reserve(tb));
+    M3D_CUDA(ctx, ctx->d_tmp4.reserve(sizeof(uint32_t) * 2 * (ns + nd) + 64));
+    M3D_CUDA(ctx, ctx->d_small.reserve(sizeof(MatchScratch) + 4096));
+    M3D_CUDA(ctx, ctx->h_small.reserve(sizeof(MatchScratch) + 4096));
+    A.f64 = ctx->d_tmp0.as<double>();
+    B.f64 = ctx->d_tmp1.as<double>();
+    A.tiles = ctx->d_tmp2.as<float>();
+    B.tiles = ctx->d_tmp3.as<float>();
+    uint32_t *d_nn01 = ctx->d_tmp4.as<uint32_t>();
+    uint32_t *d_nn10 = d_nn01 + ns;
+    uint32_t *d_amb01 = d_nn10 + nd;
+    uint32_t *d_amb10 = d_amb01 + ns;
+    MatchScratch *sc = ctx->d_small.as<MatchScratch>();
+
+    M3D_CUDA(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
+    M3D_CUDA(ctx, cudaMemcpyAsync(A.f64, src, fa, cudaMemcpyHostToDevice, ctx->stream));
+    M3D_CUDA(ctx, cudaMemcpyAsync(B.f64, dst, fb, cudaMemcpyHostToDevice, ctx->stream));
+    M3D_CUDA(ctx, cudaMemsetAsync(sc, 0, sizeof(MatchScratch), ctx->stream));
+    if (fast) {
+        M3D_CUDA(ctx, cudaMemsetAsync(sc->mn, 0xff, sizeof(sc->mn), ctx->stream));
+        const int gb = ctx->sm_count * 8;
+        feat_minmax_kernel<<<gb, 256, 0, ctx->stream>>>(A.f64, (size_t)dim * ns, dim, sc->mn, sc->mx);
+        M3D_LAUNCHED(ctx);
+        feat_minmax_kernel<<<gb, 256, 0, ctx->stream>>>(B.f64, (size_t)dim * nd, dim, sc->mn, sc->mx);
+        M3D_LAUNCHED(ctx);
+        feat_center_kernel<<<1, 128, 0, ctx->stream>>>(sc->mn, sc->mx, dim, sc->center);
+        M3D_LAUNCHED(ctx);
+        feat_convert_kernel<<<A.ntiles, kMT, 0, ctx->stream>>>(A.f64, A.count, dim, KP, sc->center, A.tiles,
+                                                              &sc->maxnorm[0]);
+        M3D_LAUNCHED(ctx);
+        feat_convert_kernel<<<B.ntiles, kMT, 0, ctx->stream>>>(B.f64, B.count, dim, KP, sc->center, B.tiles,
+                                                              &sc->maxnorm[1]);
+        M3D_LAUNCHED(ctx);
+    }
+    if (int rc = nn_direction(ctx, A, B, dim, KP, fast, &sc->maxnorm[1], d_nn01, d_amb01, &sc->amb_count[0])) return rc;
+    if (both_directions) {
+        if (int rc = nn_direction(ctx, B, A, dim, KP, fast, &sc->maxnorm[0], d_nn10, d_amb10, &sc->amb_count[1]))
+            return rc;
+        /* mutual check + stable compaction */
+        const uint32_t nblk = ((uint32_t)ns + kMB * kMItems - 1) / (kMB * kMItems);
+        M3D_CUDA(ctx, ctx->d_blk.reserve(sizeof(uint32_t) * 2 * nblk + 64));
+        M3D_CUDA(ctx, ctx->d_inl.reserve(sizeof(unsigned long long) * 2 * ns));
+        uint32_t *blk_cnt = ctx->d_blk.as<uint32_t>(), *blk_off = blk_cnt + nblk;
+        unsigned long long *d_i0 = ctx->d_inl.as<unsigned long long>(), *d_i1 = d_i0 + ns;
+        mutual_count_kernel<<<nblk, kMB, 0, ctx->stream>>>(d_nn01, d_nn10, (uint32_t)ns, (uint32_t)nd, blk_cnt);
+        M3D_LAUNCHED(ctx);
+        mutual_scan_kernel<<<1, 32, 0, ctx->stream>>>(blk_cnt, nblk, blk_off, &sc->total);
+        M3D_LAUNCHED(ctx);
+        mutual_write_kernel<<<nblk, kMB, 0, ctx->stream>>>(d_nn01, d_nn10, (uint32_t)ns, (uint32_t)nd, blk_off, d_i0,
+                                                          d_i1);
+        M3D_LAUNCHED(ctx);
+        MatchScratch *hs = ctx->h_small.as<MatchScratch>();
+        M3D_CUDA(ctx, cudaMemcpyAsync(hs, sc, sizeof(MatchScratch), cudaMemcpyDeviceToHost, ctx->stream));
+        M3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        const size_t m = hs->total;
+        static_assert(sizeof(size_t) == sizeof(unsigned long long), "size_t must be 64-bit");
+        if (m) {
+            M3D_CUDA(ctx, cudaMemcpyAsync(idx0, d_i0, sizeof(size_t) * m, cudaMemcpyDeviceToHost, ctx->stream));
+            M3D_CUDA(ctx, cudaMemcpyAsync(idx1, d_i1, sizeof(size_t) * m, cudaMemcpyDeviceToHost, ctx->stream));
+        }
+        M3D_CUDA(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
+        M3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        *n_out = m;
+    } else {
+        std::vector<uint32_t> h(ns);
+        M3D_CUDA(ctx, cudaMemcpyAsync(h.data(), d_nn01, sizeof(uint32_t) * ns, cudaMemcpyDeviceToHost, ctx->stream));
+        M3D_CUDA(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
+        M3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        for (size_t i = 0; i < ns; ++i) nn_out[i] = h[i];
+    }
+    if (device_ms) cudaEventElapsedTime(device_ms, ctx->ev[0], ctx->ev[1]);
+    return M3D_OK;
+}
+
+}  // namespace m3d
+
 extern "C" {
-int m3d_match_correspondence(m3d_ctx *ctx, const double *, size_t, const double *, size_t, int, int, int, size_t *,
-                             size_t *, size_t *, float *) {
-    return ctx ? ctx->fail(M3D_ERR_INTERNAL, "m3d_match_correspondence: not built yet") : M3D_ERR_INVALID_ARG;
+
+int m3d_match_correspondence(m3d_ctx *ctx, const double *src, size_t ns, const double *dst, size_t nd, int dim,
+                             int method, int n_trees, size_t *idx0, size_t *idx1, size_t *n_out, float *device_ms) {
+    (void)n_trees; /* Annoy forest size: the exact search has no such parameter */
+    if (!ctx || !n_out || (ns && (!idx0 || !idx1))) return M3D_ERR_INVALID_ARG;
+    if (method != M3D_MATCH_FLANN && method != M3D_MATCH_ANNOY)
+        return ctx->fail(M3D_ERR_INVALID_ARG, "unknown match method %d", method);
+    return m3d::match_impl(ctx, src, ns, dst, nd, dim, true, nullptr, idx0, idx1, n_out, device_ms);
 }
-int m3d_nearest(m3d_ctx *ctx, const double *, size_t, const double *, size_t, int, size_t *, float *) {
-    return ctx ? ctx->fail(M3D_ERR_INTERNAL, "m3d_nearest: not built yet") : M3D_ERR_INVALID_ARG;
+
+int m3d_nearest(m3d_ctx *ctx, const double *src, size_t ns, const double *dst, size_t nd, int dim, size_t *nn,
+                float *device_ms) {
+    if (!ctx || (ns && !nn)) return M3D_ERR_INVALID_ARG;
+    return m3d::match_impl(ctx, src, ns, dst, nd, dim, false, nn, nullptr, nullptr, nullptr, device_ms);
 }
-}
+
+} /* extern "C" */

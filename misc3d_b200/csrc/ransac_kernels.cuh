@@ -227,19 +227,25 @@ __global__ void minimal_fit_rows_kernel(const double *__restrict__ xyz, const do
 }
 
 /* ------------------------------------------------------------------ fp32 guard-banded scoring */
-/* Fast<KIND>: for a centred fp32 point p = {x,y,z,|p|^2} the value t(p) satisfies
- *      |t| <  lo  =>  the reference predicate `distance < threshold` is certainly true
- *      |t| >= hi  =>  certainly false
- * anything else (including NaN) is decided by the fp64 reference-order distance.
- *   plane     t = w.p + w3'                      (|t| vs threshold*||w||)
- *   sphere    t = |p - c|^2 - mid                (|t| vs half; [mid-half, mid+half] is the
+/* Fast<KIND>: for a centred fp32 point p = {x,y,z,|p|^2} let v = |t(p)| - T.  Then
+ *      v <= -band  =>  the reference predicate `distance < threshold` is certainly true
+ *      v >=  band  =>  certainly false
+ * and a point with |v| < band is decided by the fp64 reference-order distance.  The inner loop
+ * counts sign(v) (provisional decision) and tracks min |v|; only when min |v| < band is a
+ * sub-tile looked at again.
+ *   plane     t = w.p + w3'                      (T = threshold*||w||)
+ *   sphere    t = |p - c|^2 - mid                (T = half; [mid-half, mid+half] is the
  *   cylinder  t = |p - c|^2 - ((p-c).n)^2 - mid   interval of squared distances (r-thr)^2..(r+thr)^2)
+ * Per point-hypothesis pair: 3 / 4 / 8 FFMA-pipe ops + FADD + LEA.HI + FMNMX.
  */
 template <int KIND>
 struct Fast {
     float c[KIND == kCylinder ? 8 : 4];
-    float lo, hi;
+    float T, band;
 };
+/* v = |t| - T (one FADD with the |.| operand modifier) */
+template <int KIND>
+__device__ __forceinline__ float fast_v(const Fast<KIND> &f, const float4 p);
 
 template <int KIND>
 __device__ __forceinline__ float fast_eval(const Fast<KIND> &f, const float4 p) {
@@ -254,33 +260,9 @@ __device__ __forceinline__ float fast_eval(const Fast<KIND> &f, const float4 p) 
     }
 }
 
-/* the two counter updates of the inner loop; kCountForm picks the instruction mix
- *   1: FSETP + @P IADD for both            (fma pipe 3, alu pipe 4 per point-hypothesis pair)
- *   3: FADD + LEA.HI (sign bit) for both   (fma 5, alu 2)
- *   4: one of each                         (fma 4, alu 3)
- * all forms leave NaN / exact ties uncounted, i.e. "ambiguous". */
-#ifndef M3D_COUNT_FORM
-#define M3D_COUNT_FORM 4
-#endif
-template <int FORM>
-__device__ __forceinline__ void count2(float at, float lo, float hi, uint32_t &clo, uint32_t &cout) {
-    if (FORM == 1 || FORM == 4) {
-        asm("{.reg .pred p; setp.lt.f32 p, %1, %2; @p add.u32 %0, %0, 1;}" : "+r"(clo) : "f"(at), "f"(lo));
-    } else {
-        clo += __float_as_uint(__fsub_rn(at, lo)) >> 31;
-    }
-    if (FORM == 1) {
-        asm("{.reg .pred p; setp.ge.f32 p, %1, %2; @p add.u32 %0, %0, 1;}" : "+r"(cout) : "f"(at), "f"(hi));
-    } else {
-        cout += __float_as_uint(__fsub_rn(hi, at)) >> 31; /* at > hi */
-    }
-}
-/* the same decision, as a predicate (resolve path) */
-template <int FORM>
-__device__ __forceinline__ bool is_ambiguous(float at, float lo, float hi) {
-    uint32_t a = 0, b = 0;
-    count2<FORM>(at, lo, hi, a, b);
-    return (a + b) == 0;
+template <int KIND>
+__device__ __forceinline__ float fast_v(const Fast<KIND> &f, const float4 p) {
+    return __fsub_rn(fabsf(fast_eval<KIND>(f, p)), f.T);
 }
 
 template <int KIND>
@@ -288,15 +270,15 @@ __device__ inline void make_fast(const double *m, bool ok, const CloudMeta &M, d
     constexpr int NC = KIND == kCylinder ? 8 : 4;
 #pragma unroll
     for (int i = 0; i < NC; ++i) f.c[i] = 0.f;
-    f.lo = -1.f; /* |t| <  -1 never : no certain inlier                                       */
-    f.hi = -1.f; /* |t| >= -1 always: every point a certain outlier (t is finite: p is finite) */
+    f.T = -1.f;   /* v = |t| + 1 >= 1: never an inlier ...                                      */
+    f.band = 0.f; /* ... and never inside the band (t is finite: p and the coefficients are)    */
     if (!ok || !(thr > 0)) return;
     bool fin = true;
 #pragma unroll
     for (int i = 0; i < param_count(KIND); ++i) fin = fin && isfinite(m[i]);
     if (!fin) return; /* a NaN/inf model makes every reference distance NaN/inf: never an inlier */
 
-    double c[NC], lo, hi, smax = 0;
+    double c[NC], Tc, bd, smax = 0;
     const double cx = M.center[0], cy = M.center[1], cz = M.center[2];
     if (KIND == kPlane) {
         const double nrm = ex::plane_norm(m);
@@ -310,8 +292,8 @@ __device__ inline void make_fast(const double *m, bool ok, const CloudMeta &M, d
         c[1] = m[1];
         c[2] = m[2];
         c[3] = w3c;
-        lo = thrn - band;
-        hi = thrn + band;
+        Tc = thrn;
+        bd = band;
     } else {
         const double r = (KIND == kSphere) ? m[3] : m[6];
         const double Hi = (r + thr) * (r + thr);
@@ -363,24 +345,25 @@ __device__ inline void make_fast(const double *m, bool ok, const CloudMeta &M, d
         c[0] = -2 * ax;
         c[1] = -2 * ay;
         c[2] = -2 * az;
-        lo = half - band;
-        hi = half + band;
+        Tc = half;
+        bd = band;
     }
     /* smax bounds every intermediate of fast_eval: keep it far from fp32 overflow */
-    bool okf = isfinite(lo) && isfinite(hi) && (smax < 1e30);
+    bool okf = isfinite(Tc) && isfinite(bd) && (smax < 1e30);
 #pragma unroll
     for (int i = 0; i < NC; ++i) {
         f.c[i] = (float)c[i];
         okf = okf && isfinite(f.c[i]);
     }
-    f.lo = __double2float_rd(lo);
-    f.hi = __double2float_ru(hi);
-    okf = okf && isfinite(f.lo) && isfinite(f.hi);
+    f.T = (float)Tc;
+    /* + the rounding of T itself and of the subtraction |t| - T */
+    f.band = __double2float_ru(bd * (1.0 + 8 * kU32) + 2 * kU32 * fabs(Tc));
+    okf = okf && isfinite(f.T) && isfinite(f.band);
     if (!okf) { /* fp32 cannot represent this model: decide every point by the fp64 path */
 #pragma unroll
         for (int i = 0; i < NC; ++i) f.c[i] = 0.f;
-        f.lo = -1.f;
-        f.hi = __int_as_float(0x7fc00000); /* |t| >= NaN is never true */
+        f.T = 0.f;
+        f.band = INFINITY; /* |v| < inf for every (finite) point */
     }
 }
 
@@ -403,27 +386,25 @@ struct ScoreArgs {
     uint32_t chunk_tiles;
 };
 
-/* the rare path: points of one sub-tile whose fp32 value fell inside the guard band are decided
- * with the reference's own fp64 arithmetic on the original coordinates */
+/* the rare path, first half: a sub-tile contained a point inside the guard band.  Find the
+ * points again and queue (hypothesis, point, provisional decision) for resolve_queue_kernel.
+ * If the queue is full the point is decided right here. */
 template <int KIND>
-__device__ __noinline__ void resolve_subtile(const ScoreArgs &a, uint32_t row, const Fast<KIND> f,
-                                             const float4 *sp, uint32_t gbase, int cnt,
-                                             uint32_t &clo, uint32_t &cout, uint32_t &nres) {
+__device__ __noinline__ void rescan_subtile(const ScoreArgs &a, uint32_t row, const Fast<KIND> f,
+                                            const float4 *sp, uint32_t gbase, int cnt, uint32_t &clo,
+                                            uint32_t &nres) {
     bool have_model = false, ok = false;
     ex::Dist<KIND> dist;
     for (int j = 0; j < cnt; ++j) {
-        const float at = fabsf(fast_eval<KIND>(f, sp[j]));
-        if (is_ambiguous<M3D_COUNT_FORM>(at, f.lo, f.hi)) {
+        const float v = fast_v<KIND>(f, sp[j]);
+        if (fabsf(v) < f.band) {
             ++nres;
-            /* normal case: queue (hypothesis, point) for resolve_queue_kernel and count the point
-             * as an outlier for now */
+            const uint32_t prov = __float_as_uint(v) >> 31; /* what the inner loop counted */
             const uint32_t pos = atomicAdd(a.queue_count, 1u);
             if (pos < a.queue_cap) {
-                a.queue[pos] = make_uint2(row - a.row_begin, gbase + j);
-                ++cout;
+                a.queue[pos] = make_uint2(row - a.row_begin, (gbase + j) | (prov << 31));
                 continue;
             }
-            /* queue full: decide here */
             if (!have_model) {
                 double m[8];
                 ok = fit_row<KIND>(a.xyz, a.nrm, a.samples, row, m);
@@ -432,28 +413,26 @@ __device__ __noinline__ void resolve_subtile(const ScoreArgs &a, uint32_t row, c
             }
             bool in = false;
             if (ok) in = dist(ex::ld3(a.xyz + 3 * (size_t)(gbase + j))) < a.thr;
-            if (in)
-                ++clo;
-            else
-                ++cout;
+            clo += (in ? 1u : 0u) - prov;
         }
     }
 }
 
-/* second half of the rare path: one thread per queued (hypothesis, point) pair evaluates the
- * reference's fp64 predicate with the model the scoring kernel stored */
+/* second half: one thread per queued pair evaluates the reference's fp64 predicate with the
+ * model the scoring kernel stored and corrects the provisional count */
 template <int KIND>
 __global__ void __launch_bounds__(256) resolve_queue_kernel(const ScoreArgs a) {
     const uint32_t total = min(*a.queue_count, a.queue_cap);
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         const uint2 e = a.queue[i];
-        if (a.counts[e.x] & kInvalidBit) continue; /* MinimalFit failed: no inliers */
+        const uint32_t prov = e.y >> 31, pt = e.y & 0x7fffffffu;
         double m[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) m[k] = a.models[(size_t)e.x * 8 + k];
         ex::Dist<KIND> dist;
         dist.set(m);
-        if (dist(ex::ld3(a.xyz + 3 * (size_t)e.y)) < a.thr) atomicAdd(&a.counts[e.x], 1u);
+        const uint32_t in = (dist(ex::ld3(a.xyz + 3 * (size_t)pt)) < a.thr) ? 1u : 0u;
+        if (in != prov) atomicAdd(&a.counts[e.x], in - prov); /* +1 or -1 (mod 2^32) */
     }
 }
 
@@ -485,7 +464,8 @@ __global__ void __launch_bounds__(THREADS) score_kernel(const ScoreArgs a) {
     const CloudMeta M = *a.meta;
     uint32_t row[HPT];
     Fast<KIND> f[HPT];
-    uint32_t clo[HPT], cout[HPT];
+    uint32_t clo[HPT];
+    float mn[HPT];
     bool invalid[HPT];
 #pragma unroll
     for (int h = 0; h < HPT; ++h) {
@@ -501,11 +481,11 @@ __global__ void __launch_bounds__(THREADS) score_kernel(const ScoreArgs a) {
         }
         make_fast<KIND>(m, ok, M, a.thr, f[h]);
         clo[h] = 0;
-        cout[h] = 0;
+        mn[h] = INFINITY;
     }
     __syncthreads(); /* barrier init visible to all waiters */
 
-    uint32_t seen = 0, nres = 0;
+    uint32_t nres = 0;
     for (uint32_t t = t0; t < t1; ++t) {
         const int st = (t - t0) % kStages;
         mbar_wait(&full[st], ((t - t0) / kStages) & 1);
@@ -520,8 +500,9 @@ __global__ void __launch_bounds__(THREADS) score_kernel(const ScoreArgs a) {
                     const float4 p = sp[s0 + j];
 #pragma unroll
                     for (int h = 0; h < HPT; ++h) {
-                        const float at = fabsf(fast_eval<KIND>(f[h], p));
-                        count2<M3D_COUNT_FORM>(at, f[h].lo, f[h].hi, clo[h], cout[h]);
+                        const float v = fast_v<KIND>(f[h], p);
+                        clo[h] += __float_as_uint(v) >> 31;
+                        mn[h] = fminf(mn[h], fabsf(v));
                     }
                 }
             } else {
@@ -529,22 +510,21 @@ __global__ void __launch_bounds__(THREADS) score_kernel(const ScoreArgs a) {
                     const float4 p = sp[s0 + j];
 #pragma unroll
                     for (int h = 0; h < HPT; ++h) {
-                        const float at = fabsf(fast_eval<KIND>(f[h], p));
-                        count2<M3D_COUNT_FORM>(at, f[h].lo, f[h].hi, clo[h], cout[h]);
+                        const float v = fast_v<KIND>(f[h], p);
+                        clo[h] += __float_as_uint(v) >> 31;
+                        mn[h] = fminf(mn[h], fabsf(v));
                     }
                 }
             }
-            seen += cnt;
 #pragma unroll
             for (int h = 0; h < HPT; ++h) {
-                if (clo[h] + cout[h] != seen) {
+                if (mn[h] < f[h].band) {
                     if (row[h] < a.rows)
-                        resolve_subtile<KIND>(a, a.row_begin + row[h], f[h], sp + s0, base + s0, cnt,
-                                              clo[h], cout[h], nres);
-                    else
-                        cout[h] = seen - clo[h];
+                        rescan_subtile<KIND>(a, a.row_begin + row[h], f[h], sp + s0, base + s0, cnt, clo[h], nres);
+                    mn[h] = INFINITY;
                 }
             }
+            __syncwarp(); /* lanes that took the rare path rejoin here, not at the end of the tile */
         }
         __syncthreads(); /* every warp is done with stage st */
         if (tid == 0 && t + kStages < t1) issue(t + kStages);

@@ -1,0 +1,84 @@
+"""GPU parity tests of match_correspondence (brute-force L2 + mutual check) against the oracle:
+index lists must be identical (integer work: bit-exact)."""
+import os
+
+import numpy as np
+import pytest
+
+from misc3d_b200 import synth
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def test_golden_reg_small_matches(ctx, capi):
+    g = np.load(os.path.join(GOLD, "reg_small.npz"))
+    d = synth.make_c4(n=3000, seed=5)
+    i0, i1, ms = ctx.match_correspondence(d["src_feat"], d["dst_feat"])
+    np.testing.assert_array_equal(i0, g["i0"])
+    np.testing.assert_array_equal(i1, g["i1"])
+
+
+@pytest.mark.parametrize("ns,nd,dim", [(1000, 1300, 33), (257, 129, 33), (500, 500, 8), (300, 200, 352), (1, 5, 33),
+                                       (130, 1, 3)])
+def test_nearest_and_match_equal_oracle(ctx, capi, orc, ns, nd, dim):
+    rng = np.random.default_rng(ns + nd + dim)
+    a = np.asfortranarray(rng.uniform(0, 100, size=(dim, ns)))
+    b = np.asfortranarray(rng.uniform(0, 100, size=(dim, nd)))
+    nn, ms = ctx.nearest(a, b)
+    np.testing.assert_array_equal(nn, orc.nearest(a, b))
+    for method in (capi.MATCH_FLANN, capi.MATCH_ANNOY):
+        i0, i1, ms = ctx.match_correspondence(a, b, method=method)
+        o0, o1 = orc.match_correspondence(a, b)
+        np.testing.assert_array_equal(i0, o0)
+        np.testing.assert_array_equal(i1, o1)
+        assert np.all(np.diff(i0.astype(np.int64)) > 0)
+
+
+def test_exact_ties_pick_the_lowest_index(ctx, capi, orc):
+    """FPFH histograms repeat on real data: duplicated descriptors must resolve to the lowest index"""
+    rng = np.random.default_rng(3)
+    base = np.round(rng.uniform(0, 10, size=(33, 40)))  # small integer lattice -> many equal distances
+    a = np.asfortranarray(base[:, rng.integers(0, 40, 700)])
+    b = np.asfortranarray(base[:, rng.integers(0, 40, 900)])
+    nn, ms = ctx.nearest(a, b)
+    np.testing.assert_array_equal(nn, orc.nearest(a, b))
+    i0, i1, ms = ctx.match_correspondence(a, b)
+    o0, o1 = orc.match_correspondence(a, b)
+    np.testing.assert_array_equal(i0, o0)
+    np.testing.assert_array_equal(i1, o1)
+
+
+def test_offset_descriptors_and_empty_sets(ctx, capi, orc):
+    rng = np.random.default_rng(8)
+    a = np.asfortranarray(rng.normal(0, 1, size=(33, 600)) + 1.0e4)  # large common offset: centring matters
+    b = np.asfortranarray(a[:, rng.permutation(600)] + rng.normal(0, 0.05, size=(33, 600)))
+    i0, i1, ms = ctx.match_correspondence(a, b)
+    o0, o1 = orc.match_correspondence(a, b)
+    np.testing.assert_array_equal(i0, o0)
+    np.testing.assert_array_equal(i1, o1)
+    e = np.zeros((33, 0), order="F")
+    i0, i1, ms = ctx.match_correspondence(e, b)
+    assert len(i0) == 0 and len(i1) == 0
+    i0, i1, ms = ctx.match_correspondence(a, e)
+    assert len(i0) == 0 and len(i1) == 0
+
+
+def test_c4_sized_properties(ctx, capi):
+    """BASELINE config C4 size (200k x 200k x 33): mutual pairs are consistent and recover the
+    planted correspondences (30 % of the descriptors are noisy copies)."""
+    d = synth.make_c4()
+    i0, i1, ms = ctx.match_correspondence(d["src_feat"], d["dst_feat"])
+    assert np.all(np.diff(i0.astype(np.int64)) > 0) and len(np.unique(i1)) == len(i1)
+    perm, mask = d["perm"], d["true_mask"]          # dst[j] <- src[perm[j]] where mask[j]
+    truth = {int(perm[j]): int(j) for j in np.nonzero(mask)[0]}
+    got = dict(zip(i0.tolist(), i1.tolist()))
+    hit = sum(1 for s, t in truth.items() if got.get(s) == t)
+    assert hit >= 0.999 * len(truth)
+    # spot-check 64 rows against a numpy brute force
+    rng = np.random.default_rng(0)
+    rows = rng.choice(len(i0), 64, replace=False)
+    A, B = d["src_feat"], d["dst_feat"]
+    for r in rows:
+        dist = ((B - A[:, [int(i0[r])]]) ** 2).sum(0)
+        assert int(np.argmin(dist)) == int(i1[r])

@@ -13,11 +13,10 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 LIBS = {  # name -> extra nvcc flags
-    "f4s32": "-DM3D_COUNT_FORM=4 -DM3D_SUB=32",
-    "f1s32": "-DM3D_COUNT_FORM=1 -DM3D_SUB=32",
-    "f3s32": "-DM3D_COUNT_FORM=3 -DM3D_SUB=32",
-    "f4s64": "-DM3D_COUNT_FORM=4 -DM3D_SUB=64",
-    "f4s128": "-DM3D_COUNT_FORM=4 -DM3D_SUB=128",
+    "s32": "-DM3D_SUB=32",
+    "s64": "-DM3D_SUB=64",
+    "s128": "-DM3D_SUB=128",
+    "s256": "-DM3D_SUB=256",
 }
 LAUNCH = ["256x2", "128x2", "256x1", "128x4", "256x4", "128x1"]
 
@@ -47,8 +46,7 @@ def one():
 
 def run():
     rows = []
-    for lib, launch in itertools.chain(((l, "256x2") for l in LIBS), (("f4s32", v) for v in LAUNCH[1:]),
-                                       (("f1s32", v) for v in LAUNCH[1:4])):
+    for lib, launch in itertools.chain(((l, "256x2") for l in LIBS), (("s64", v) for v in LAUNCH[1:])):
         env = dict(os.environ, M3D_LIB=os.path.join(ROOT, "misc3d_b200", "variants", f"libm3d_{lib}.so"),
                    M3D_SCORE_VARIANT=launch)
         r = subprocess.run([sys.executable, __file__, "one"], env=env, capture_output=True, text=True)
@@ -59,14 +57,14 @@ def run():
         rows.append({"lib": lib, "launch": launch, **d})
         print(json.dumps(rows[-1]), flush=True)
     for waves in (4, 16, 32):
-        env = dict(os.environ, M3D_LIB=os.path.join(ROOT, "misc3d_b200", "variants", "libm3d_f4s32.so"),
+        env = dict(os.environ, M3D_LIB=os.path.join(ROOT, "misc3d_b200", "variants", "libm3d_s64.so"),
                    M3D_SCORE_VARIANT="256x2", M3D_CHUNK_WAVES=str(waves))
         r = subprocess.run([sys.executable, __file__, "one"], env=env, capture_output=True, text=True)
         try:
             d = json.loads(r.stdout.strip().splitlines()[-1])
         except Exception:
             d = {"error": (r.stderr or r.stdout)[-400:]}
-        print(json.dumps({"lib": "f4s32", "launch": "256x2", "waves": waves, **d}), flush=True)
+        print(json.dumps({"lib": "s64", "launch": "256x2", "waves": waves, **d}), flush=True)
 
 
 if __name__ == "__main__":
