@@ -24,10 +24,7 @@ namespace m3d {
 
 constexpr int kTile = 1024;  /* points per TMA stage (16 KB)                      */
 constexpr int kStages = 3;   /* ring depth                                        */
-#ifndef M3D_SUB
-#define M3D_SUB 32
-#endif
-constexpr int kSub = M3D_SUB; /* points between two "any ambiguous point?" checks */
+constexpr int kSub = 32; /* points between two "any point inside the band?" checks = one warp-wide rescan */
 constexpr uint32_t kInvalidBit = 0x80000000u;
 constexpr double kU32 = 5.9604644775390625e-08; /* 2^-24 */
 constexpr double kU64 = 1.1102230246251565e-16; /* 2^-53 */
@@ -386,34 +383,53 @@ struct ScoreArgs {
     uint32_t chunk_tiles;
 };
 
-/* the rare path, first half: a sub-tile contained a point inside the guard band.  Find the
- * points again and queue (hypothesis, point, provisional decision) for resolve_queue_kernel.
- * If the queue is full the point is decided right here. */
+/* the rare path, first half: some lane's hypothesis saw a point of this 32-point sub-tile inside
+ * its guard band.  The whole warp re-examines the sub-tile for that hypothesis -- lane L takes
+ * point L with the owner's coefficients (shuffled) -- and queues the (hypothesis, point,
+ * provisional decision) triples for resolve_queue_kernel.  All lanes stay converged. */
 template <int KIND>
-__device__ __noinline__ void rescan_subtile(const ScoreArgs &a, uint32_t row, const Fast<KIND> f,
-                                            const float4 *sp, uint32_t gbase, int cnt, uint32_t &clo,
+__device__ __forceinline__ void rescan_warp(const ScoreArgs &a, unsigned need, uint32_t row_local,
+                                            const Fast<KIND> &f, const float4 *sp, uint32_t gbase, int cnt,
                                             uint32_t &nres) {
-    bool have_model = false, ok = false;
-    ex::Dist<KIND> dist;
-    for (int j = 0; j < cnt; ++j) {
-        const float v = fast_v<KIND>(f, sp[j]);
-        if (fabsf(v) < f.band) {
-            ++nres;
+    constexpr int NC = KIND == kCylinder ? 8 : 4;
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const float4 p = sp[lane < cnt ? lane : 0];
+    while (need) {
+        const int src = __ffs(need) - 1;
+        need &= need - 1;
+        Fast<KIND> g;
+#pragma unroll
+        for (int i = 0; i < NC; ++i) g.c[i] = __shfl_sync(full, f.c[i], src);
+        g.T = __shfl_sync(full, f.T, src);
+        g.band = __shfl_sync(full, f.band, src);
+        const uint32_t r = __shfl_sync(full, row_local, src);
+        const float v = fast_v<KIND>(g, p);
+        const bool amb = lane < cnt && fabsf(v) < g.band;
+        const unsigned am = __ballot_sync(full, amb);
+        if (am == 0) continue;
+        uint32_t pos0 = 0;
+        if (lane == 0) {
+            pos0 = atomicAdd(a.queue_count, (uint32_t)__popc(am));
+            nres += __popc(am);
+        }
+        pos0 = __shfl_sync(full, pos0, 0);
+        if (amb) {
             const uint32_t prov = __float_as_uint(v) >> 31; /* what the inner loop counted */
-            const uint32_t pos = atomicAdd(a.queue_count, 1u);
+            const uint32_t pos = pos0 + __popc(am & ((1u << lane) - 1));
             if (pos < a.queue_cap) {
-                a.queue[pos] = make_uint2(row - a.row_begin, (gbase + j) | (prov << 31));
-                continue;
-            }
-            if (!have_model) {
+                a.queue[pos] = make_uint2(r, (gbase + lane) | (prov << 31));
+            } else { /* queue full: decide here with the reference arithmetic */
                 double m[8];
-                ok = fit_row<KIND>(a.xyz, a.nrm, a.samples, row, m);
-                if (ok) dist.set(m);
-                have_model = true;
+                const bool ok = fit_row<KIND>(a.xyz, a.nrm, a.samples, a.row_begin + r, m);
+                uint32_t in = 0;
+                if (ok) {
+                    ex::Dist<KIND> dist;
+                    dist.set(m);
+                    in = dist(ex::ld3(a.xyz + 3 * (size_t)(gbase + lane))) < a.thr ? 1u : 0u;
+                }
+                if (in != prov) atomicAdd(&a.counts[r], in - prov);
             }
-            bool in = false;
-            if (ok) in = dist(ex::ld3(a.xyz + 3 * (size_t)(gbase + j))) < a.thr;
-            clo += (in ? 1u : 0u) - prov;
         }
     }
 }
@@ -518,13 +534,11 @@ __global__ void __launch_bounds__(THREADS) score_kernel(const ScoreArgs a) {
             }
 #pragma unroll
             for (int h = 0; h < HPT; ++h) {
-                if (mn[h] < f[h].band) {
-                    if (row[h] < a.rows)
-                        rescan_subtile<KIND>(a, a.row_begin + row[h], f[h], sp + s0, base + s0, cnt, clo[h], nres);
-                    mn[h] = INFINITY;
-                }
+                const bool flag = mn[h] < f[h].band;
+                const unsigned need = __ballot_sync(0xffffffffu, flag && row[h] < a.rows);
+                if (need) rescan_warp<KIND>(a, need, row[h], f[h], sp + s0, base + s0, cnt, nres);
+                if (flag) mn[h] = INFINITY;
             }
-            __syncwarp(); /* lanes that took the rare path rejoin here, not at the end of the tile */
         }
         __syncthreads(); /* every warp is done with stage st */
         if (tid == 0 && t + kStages < t1) issue(t + kStages);

@@ -45,26 +45,14 @@ def one():
 
 
 def run():
-    rows = []
-    for lib, launch in itertools.chain(((l, "256x2") for l in LIBS), (("s64", v) for v in LAUNCH[1:])):
-        env = dict(os.environ, M3D_LIB=os.path.join(ROOT, "misc3d_b200", "variants", f"libm3d_{lib}.so"),
-                   M3D_SCORE_VARIANT=launch)
+    for launch in LAUNCH:
+        env = dict(os.environ, M3D_SCORE_VARIANT=launch)
         r = subprocess.run([sys.executable, __file__, "one"], env=env, capture_output=True, text=True)
         try:
             d = json.loads(r.stdout.strip().splitlines()[-1])
         except Exception:
             d = {"error": (r.stderr or r.stdout)[-400:]}
-        rows.append({"lib": lib, "launch": launch, **d})
-        print(json.dumps(rows[-1]), flush=True)
-    for waves in (4, 16, 32):
-        env = dict(os.environ, M3D_LIB=os.path.join(ROOT, "misc3d_b200", "variants", "libm3d_s64.so"),
-                   M3D_SCORE_VARIANT="256x2", M3D_CHUNK_WAVES=str(waves))
-        r = subprocess.run([sys.executable, __file__, "one"], env=env, capture_output=True, text=True)
-        try:
-            d = json.loads(r.stdout.strip().splitlines()[-1])
-        except Exception:
-            d = {"error": (r.stderr or r.stdout)[-400:]}
-        print(json.dumps({"lib": "s64", "launch": "256x2", "waves": waves, **d}), flush=True)
+        print(json.dumps({"launch": launch, **d}), flush=True)
 
 
 if __name__ == "__main__":
