@@ -1,0 +1,316 @@
+/*
+ * b200_facade.hpp -- C++ facade over libm3d_b200.so that keeps the reference's class names and call
+ * shapes for the RANSAC / segmentation / matching / registration path, so existing callers
+ * (python/py_*.cpp, examples/cpp/{ransac_and_boundary,segment_plane_iterative,
+ * transform_estimation}.cpp, src/pipeline.cpp:800-812) keep compiling against
+ *   <misc3d/common/ransac.h>                                 (reference: include/misc3d/common/ransac.h)
+ *   <misc3d/segmentation/iterative_plane_segmentation.h>     (.../iterative_plane_segmentation.h)
+ *   <misc3d/registration/correspondence_matching.h>          (.../correspondence_matching.h)
+ *   <misc3d/registration/transform_estimation.h>             (.../transform_estimation.h)
+ *   <misc3d/logging.h>                                       (.../logging.h)
+ *
+ * Open3D and Eigen are not available in this build environment, so the geometry types are plain
+ * standard-library stand-ins with the same memory layout (std::vector<std::array<double,3>> ==
+ * std::vector<Eigen::Vector3d>).  Define M3D_WITH_OPEN3D before including to alias the real
+ * open3d::geometry::PointCloud instead.
+ *
+ * Every compute call goes through the C-ABI of include/m3d_capi.h; C-ABI error codes are mapped
+ * back to what the reference does (LogError -> throws std::runtime_error; FitModel -> bool).
+ */
+#pragma once
+#include <array>
+#include <cstdint>
+#include <cstdio>
+#include <functional>
+#include <memory>
+#include <random>
+#include <stdexcept>
+#include <string>
+#include <tuple>
+#include <utility>
+#include <vector>
+
+#include "../m3d_capi.h"
+
+namespace misc3d {
+
+/* ------------------------------------------------------------------ logging (logging.h) */
+enum class VerbosityLevel { Error = 0, Warning = 1, Info = 2, Debug = 3 };
+namespace detail {
+inline VerbosityLevel &verbosity() {
+    static VerbosityLevel v = VerbosityLevel::Info; /* reference default, logging.cpp:56 */
+    return v;
+}
+}  // namespace detail
+inline void SetVerbosityLevel(VerbosityLevel level) { detail::verbosity() = level; }
+inline VerbosityLevel GetVerbosityLevel() { return detail::verbosity(); }
+[[noreturn]] inline void LogError(const std::string &msg) { /* logging.cpp:64-74: throws */
+    throw std::runtime_error("[Misc3D Error] " + msg);
+}
+inline void LogWarning(const std::string &msg) {
+    if (detail::verbosity() >= VerbosityLevel::Warning) std::fprintf(stderr, "[Misc3D Warning] %s\n", msg.c_str());
+}
+inline void LogInfo(const std::string &msg) {
+    if (detail::verbosity() >= VerbosityLevel::Info) std::fprintf(stdout, "[Misc3D Info] %s\n", msg.c_str());
+}
+
+/* ------------------------------------------------------------------ geometry stand-ins */
+using Vector3d = std::array<double, 3>;
+using Vector4d = std::array<double, 4>;
+using Matrix4d = std::array<double, 16>; /* row-major */
+
+struct PointCloud { /* the part of open3d::geometry::PointCloud this path touches */
+    std::vector<Vector3d> points_;
+    std::vector<Vector3d> normals_;
+    PointCloud() = default;
+    explicit PointCloud(std::vector<Vector3d> pts) : points_(std::move(pts)) {}
+    bool HasPoints() const { return !points_.empty(); }
+    bool HasNormals() const { return !points_.empty() && normals_.size() == points_.size(); }
+    void Clear() {
+        points_.clear();
+        normals_.clear();
+    }
+    /* ascending order, duplicates collapse (Open3D mask pass) */
+    std::shared_ptr<PointCloud> SelectByIndex(const std::vector<size_t> &indices, bool invert = false) const {
+        std::vector<bool> mask(points_.size(), invert);
+        for (size_t i : indices) mask[i] = !invert;
+        auto out = std::make_shared<PointCloud>();
+        const bool nrm = HasNormals();
+        for (size_t i = 0; i < points_.size(); ++i)
+            if (mask[i]) {
+                out->points_.push_back(points_[i]);
+                if (nrm) out->normals_.push_back(normals_[i]);
+            }
+        return out;
+    }
+};
+using PointCloudPtr = std::shared_ptr<PointCloud>;
+
+/* dim x count column-major descriptors (open3d Feature::data_ / Eigen::MatrixXd) */
+struct FeatureMatrix {
+    int dim = 0;
+    size_t count = 0;
+    const double *data = nullptr; /* borrowed */
+};
+
+/* ------------------------------------------------------------------ the CUDA context */
+namespace b200 {
+inline m3d_ctx *DefaultContext() {
+    struct Holder {
+        m3d_ctx *ctx = nullptr;
+        Holder() {
+            const char *dev = std::getenv("M3D_DEVICE");
+            if (m3d_ctx_create(dev ? std::atoi(dev) : 0, &ctx) != M3D_OK)
+                throw std::runtime_error("misc3d (B200 build): no usable CUDA device; there is no CPU fallback");
+        }
+        ~Holder() { m3d_ctx_destroy(ctx); }
+    };
+    thread_local Holder h; /* one m3d_ctx per host thread */
+    return h.ctx;
+}
+inline uint32_t RandomSeed() { /* the reference seeds every sampler from std::random_device */
+    return std::random_device{}();
+}
+[[noreturn]] inline void Raise(m3d_ctx *ctx) { LogError(m3d_last_error(ctx)); }
+}  // namespace b200
+
+/* ------------------------------------------------------------------ common/ransac.h */
+namespace common {
+
+class Model { /* ransac.h:24-47 */
+public:
+    std::vector<double> parameters_; /* plane [a,b,c,d], sphere [x,y,z,r], cylinder [x,y,z,nx,ny,nz,r] */
+protected:
+    explicit Model(size_t n) : parameters_(n, 0.0) {}
+};
+class Plane : public Model {
+public:
+    Plane() : Model(4) {}
+};
+class Sphere : public Model {
+public:
+    Sphere() : Model(4) {}
+};
+class Cylinder : public Model {
+public:
+    Cylinder() : Model(7) {}
+};
+
+/* RANSAC<ModelEstimator, Model, Sampler> (ransac.h:455-664).  The estimator / sampler template
+ * arguments of the reference collapse into the primitive id: sampling, minimal solves, scoring and
+ * the refit all run inside m3d_ransac_fit. */
+template <int KIND, class ModelT>
+class RANSAC {
+public:
+    RANSAC() = default;
+    void SetPointCloud(const PointCloud &pc) { pc_ = pc; }       /* deep copy, ransac.h:469-475 */
+    void SetProbability(double probability) {                     /* ransac.h:482-487 */
+        if (probability <= 0 || probability > 1) LogError("Probability must be > 0 or <= 1.0");
+        probability_ = probability;
+    }
+    void SetMaxIteration(size_t num) { max_iteration_ = num; }    /* ransac.h:495 */
+    /* not in the reference: fixes the sample stream (default: std::random_device, utils.h:74-77) */
+    void SetSeed(uint32_t seed) {
+        seed_ = seed;
+        has_seed_ = true;
+    }
+    const m3d_ransac_stats &LastStats() const { return stats_; }
+
+    /* ransac.h:506-516 */
+    bool FitModel(double threshold, ModelT &model, std::vector<size_t> &inlier_indices) {
+        m3d_ctx *ctx = b200::DefaultContext();
+        const size_t n = pc_.points_.size();
+        m3d_ransac_params p{};
+        p.threshold = threshold;
+        p.max_iteration = max_iteration_;
+        p.probability = probability_;
+        p.seed = has_seed_ ? seed_ : b200::RandomSeed();
+        double out[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        inlier_indices.assign(n, 0);
+        size_t n_inl = 0;
+        const double *nrm = pc_.HasNormals() ? pc_.normals_[0].data() : nullptr;
+        const int rc = m3d_ransac_fit(ctx, KIND, n ? pc_.points_[0].data() : nullptr, nrm, n, &p, out,
+                                      inlier_indices.data(), &n_inl, &stats_);
+        inlier_indices.resize(n_inl);
+        if (rc < 0) b200::Raise(ctx); /* lack of points / no normals: the reference throws */
+        char line[160];
+        std::snprintf(line, sizeof line, "Find best model with %g%% inliers and run %llu iterations",
+                      n ? 100.0 * (double)stats_.best_count / (double)n : 0.0,
+                      (unsigned long long)stats_.iterations_run); /* ransac.h:616-619 */
+        LogInfo(line);
+        if (stats_.found) model.parameters_.assign(out, out + model.parameters_.size());
+        return rc == 1;
+    }
+
+private:
+    PointCloud pc_;
+    double probability_ = 0.9999;  /* ransac.h:462 */
+    size_t max_iteration_ = 1000;  /* ransac.h:461 */
+    uint32_t seed_ = 0;
+    bool has_seed_ = false;
+    m3d_ransac_stats stats_{};
+};
+using RANSACPlane = RANSAC<M3D_PLANE, Plane>;
+using RANSACShpere = RANSAC<M3D_SPHERE, Sphere>; /* (sic) ransac.h:667 */
+using RANSACCylinder = RANSAC<M3D_CYLINDER, Cylinder>;
+
+}  // namespace common
+
+/* ------------------------------------------------------------------ segmentation */
+namespace segmentation {
+/* iterative_plane_segmentation.h:25-28 / .cpp:7-39 */
+inline std::vector<std::pair<Vector4d, PointCloud>> SegmentPlaneIterative(const PointCloud &pcd,
+                                                                          const double threshold,
+                                                                          const int max_iteration = 100,
+                                                                          const double min_ratio = 0.05,
+                                                                          const uint32_t *seed = nullptr) {
+    std::vector<std::pair<Vector4d, PointCloud>> result;
+    const size_t n = pcd.points_.size();
+    if (n < 3) {
+        LogWarning("No enough points to segment plane."); /* :14-17 */
+        return result;
+    }
+    m3d_ctx *ctx = b200::DefaultContext();
+    const size_t cap = 1024;
+    std::vector<double> planes(4 * cap);
+    std::vector<uint64_t> labels(n);
+    size_t n_planes = 0;
+    const int rc = m3d_segment_plane_iterative(ctx, pcd.points_[0].data(), n, threshold, max_iteration, min_ratio,
+                                               seed ? *seed : b200::RandomSeed(), planes.data(), cap, labels.data(),
+                                               &n_planes, nullptr);
+    if (rc != M3D_OK) b200::Raise(ctx);
+    result.resize(n_planes);
+    for (size_t k = 0; k < n_planes; ++k)
+        for (int i = 0; i < 4; ++i) result[k].first[i] = planes[4 * k + i];
+    for (size_t i = 0; i < n; ++i) /* clusters keep ascending original order (stable compaction) */
+        if (labels[i] != UINT64_MAX) result[labels[i]].second.points_.push_back(pcd.points_[i]);
+    return result;
+}
+}  // namespace segmentation
+
+/* ------------------------------------------------------------------ registration */
+namespace registration {
+
+enum class MatchMethod { FLANN = 0, ANNOY = 1 }; /* correspondence_matching.h:14-17 */
+
+class ANNMatcher { /* correspondence_matching.h:67-91 */
+public:
+    ANNMatcher() : method_(MatchMethod::FLANN), n_trees_(4) {}
+    explicit ANNMatcher(const MatchMethod &method) : method_(method), n_trees_(4) {}
+    ANNMatcher(const MatchMethod &method, int n_trees) : method_(method), n_trees_(n_trees) {}
+
+    std::pair<std::vector<size_t>, std::vector<size_t>> Match(const FeatureMatrix &src,
+                                                             const FeatureMatrix &dst) const {
+        if (src.dim != dst.dim) LogError("Descriptor dimensions differ");
+        m3d_ctx *ctx = b200::DefaultContext();
+        std::pair<std::vector<size_t>, std::vector<size_t>> out;
+        out.first.resize(src.count);
+        out.second.resize(src.count);
+        size_t n_out = 0;
+        const int rc = m3d_match_correspondence(ctx, src.data, src.count, dst.data, dst.count, src.dim,
+                                                (int)method_, n_trees_, out.first.data(), out.second.data(), &n_out,
+                                                nullptr);
+        if (rc != M3D_OK) b200::Raise(ctx);
+        out.first.resize(n_out);
+        out.second.resize(n_out);
+        return out;
+    }
+
+private:
+    MatchMethod method_;
+    int n_trees_;
+};
+
+class RANSACSolver { /* transform_estimation.h:114-146 */
+public:
+    explicit RANSACSolver(double threshold, int max_iter = 100000, double edge_length_threshold = 0.9)
+        : threshold_(threshold), max_iter_(max_iter), edge_length_threshold_(edge_length_threshold) {}
+    /* the reference's member is self-initialised (transform_estimation.h:126): the argument is
+     * honoured here -- documented deviation */
+    void SetSeed(uint32_t seed) {
+        seed_ = seed;
+        has_seed_ = true;
+    }
+    Matrix4d Solve(const PointCloud &src, const PointCloud &dst,
+                   const std::pair<std::vector<size_t>, std::vector<size_t>> &corres) const {
+        if (corres.first.size() != corres.second.size()) LogError("Correspondence lists differ in length");
+        m3d_ctx *ctx = b200::DefaultContext();
+        Matrix4d T{};
+        const int rc = m3d_ransac_registration(
+            ctx, src.points_.empty() ? nullptr : src.points_[0].data(), src.points_.size(),
+            dst.points_.empty() ? nullptr : dst.points_[0].data(), dst.points_.size(), corres.first.data(),
+            corres.second.data(), corres.first.size(), threshold_, max_iter_, edge_length_threshold_, 0.999,
+            has_seed_ ? seed_ : b200::RandomSeed(), T.data(), nullptr);
+        if (rc < 0) b200::Raise(ctx); /* < 3 points: transform_estimation.cpp:130-133 throws */
+        return T;
+    }
+
+private:
+    double threshold_;
+    int max_iter_;
+    double edge_length_threshold_;
+    uint32_t seed_ = 0;
+    bool has_seed_ = false;
+};
+
+class LeastSquareSolver { /* transform_estimation.cpp:49-66 */
+public:
+    explicit LeastSquareSolver(bool scaling = false) : scaling_(scaling) {}
+    /* src, dst: n corresponding points each */
+    Matrix4d Solve(const std::vector<Vector3d> &src, const std::vector<Vector3d> &dst) const {
+        if (src.size() != dst.size()) LogError("Point lists differ in length");
+        m3d_ctx *ctx = b200::DefaultContext();
+        Matrix4d T{};
+        const int rc = m3d_least_squares_transform(ctx, src.empty() ? nullptr : src[0].data(),
+                                                   dst.empty() ? nullptr : dst[0].data(), src.size(), scaling_ ? 1 : 0,
+                                                   T.data());
+        if (rc != M3D_OK) b200::Raise(ctx);
+        return T;
+    }
+
+private:
+    bool scaling_;
+};
+
+}  // namespace registration
+}  // namespace misc3d

@@ -1,0 +1,237 @@
+/*
+ * py_misc3d.cpp -- pybind11 shim of the B200 build: module `misc3d` with the submodules, function
+ * names, argument names, defaults and return types of the reference's python binding for the
+ * RANSAC / segmentation / registration path:
+ *   common.fit_plane / fit_sphere / fit_cylinder            (reference python/py_common.cpp:11-78)
+ *   segmentation.segment_plane_iterative                     (python/py_segmentation.cpp:87-96)
+ *   registration.match_correspondence (2 overloads), compute_transformation_ransac,
+ *   compute_transformation_least_square, MatchMethod        (python/py_registration.cpp:12-106)
+ *   VerbosityLevel, set_verbosity_level, get_verbosity_level (python/py_misc3d.cpp:52-62)
+ *
+ * Point clouds: the reference takes open3d.geometry.PointCloud.  Here any object with a `.points`
+ * (and optional `.normals`) attribute convertible by numpy.asarray is accepted -- a real Open3D
+ * cloud where Open3D is installed -- as well as a plain (N,3) float64 ndarray or a (points,
+ * normals) tuple.  Features: any object with a `.data` attribute of shape (dim, n), or such an
+ * ndarray.  Extra keyword-only argument `seed` (default None = std::random_device, as the
+ * reference) fixes the sample stream.
+ */
+#include <pybind11/numpy.h>
+#include <pybind11/pybind11.h>
+#include <pybind11/stl.h>
+
+#include <cstring>
+
+#include <misc3d/common/ransac.h>
+#include <misc3d/logging.h>
+#include <misc3d/registration/correspondence_matching.h>
+#include <misc3d/registration/transform_estimation.h>
+#include <misc3d/segmentation/iterative_plane_segmentation.h>
+
+namespace py = pybind11;
+using namespace misc3d;
+using DArray = py::array_t<double, py::array::c_style | py::array::forcecast>;
+using FArray = py::array_t<double, py::array::f_style | py::array::forcecast>;
+
+namespace {
+
+std::vector<Vector3d> rows3(const py::handle &h, const char *what) {
+    DArray a = DArray::ensure(h);
+    if (!a || !((a.ndim() == 2 && a.shape(1) == 3) || a.size() == 0))
+        throw py::type_error(std::string(what) + " must be convertible to an (N, 3) float64 array");
+    std::vector<Vector3d> out((size_t)(a.size() / 3));
+    if (!out.empty()) std::memcpy(out[0].data(), a.data(), sizeof(double) * 3 * out.size());
+    return out;
+}
+
+/* returns the cloud and whether the caller passed an Open3D-like object (has .points) */
+PointCloud cloud_from_py(const py::object &o, bool *is_o3d = nullptr) {
+    PointCloud pc;
+    if (is_o3d) *is_o3d = false;
+    if (py::hasattr(o, "points")) {
+        if (is_o3d) *is_o3d = true;
+        pc.points_ = rows3(py::module_::import("numpy").attr("asarray")(o.attr("points")), "pc.points");
+        if (py::hasattr(o, "normals")) {
+            auto nr = rows3(py::module_::import("numpy").attr("asarray")(o.attr("normals")), "pc.normals");
+            if (nr.size() == pc.points_.size()) pc.normals_ = std::move(nr);
+        }
+    } else if (py::isinstance<py::tuple>(o) && py::len(o) == 2) {
+        py::tuple t = o.cast<py::tuple>();
+        pc.points_ = rows3(t[0], "points");
+        if (!t[1].is_none()) pc.normals_ = rows3(t[1], "normals");
+    } else {
+        pc.points_ = rows3(o, "pc");
+    }
+    return pc;
+}
+
+py::array_t<double> to_numpy(const std::vector<double> &v) {
+    py::array_t<double> a((py::ssize_t)v.size());
+    std::memcpy(a.mutable_data(), v.data(), sizeof(double) * v.size());
+    return a;
+}
+
+template <class Fit, class ModelT>
+std::tuple<py::array_t<double>, std::vector<size_t>> fit_primitive(const py::object &pc_obj, double threshold,
+                                                                   size_t max_iteration, double probability,
+                                                                   const py::object &seed, bool need_normals) {
+    PointCloud pc = cloud_from_py(pc_obj);
+    if (need_normals && !pc.HasNormals()) LogError("Fit cylinder requires normals."); /* py_common.cpp:50-52 */
+    Fit fit;
+    fit.SetMaxIteration(max_iteration);
+    fit.SetProbability(probability);
+    if (!seed.is_none()) fit.SetSeed(seed.cast<uint32_t>());
+    ModelT model;
+    std::vector<size_t> inliers;
+    fit.SetPointCloud(pc);
+    bool ret;
+    {
+        py::gil_scoped_release nogil;
+        ret = fit.FitModel(threshold, model, inliers);
+    }
+    if (!ret) model.parameters_.assign(4, 0.0); /* setZero(4), also for the cylinder (py_common.cpp:62) */
+    return std::make_tuple(to_numpy(model.parameters_), inliers);
+}
+
+FArray feature_from_py(const py::object &o) {
+    py::object src = py::hasattr(o, "data") && !py::isinstance<py::array>(o) ? py::object(o.attr("data")) : o;
+    FArray a = FArray::ensure(src);
+    if (!a || a.ndim() != 2) throw py::type_error("descriptors must be a (dim, n) float64 array");
+    return a;
+}
+
+std::pair<std::vector<size_t>, std::vector<size_t>> match(const py::object &src, const py::object &dst,
+                                                         const registration::MatchMethod &method, int n_trees) {
+    FArray a = feature_from_py(src), b = feature_from_py(dst);
+    registration::ANNMatcher matcher(method, n_trees);
+    FeatureMatrix fa{(int)a.shape(0), (size_t)a.shape(1), a.data()};
+    FeatureMatrix fb{(int)b.shape(0), (size_t)b.shape(1), b.data()};
+    py::gil_scoped_release nogil;
+    return matcher.Match(fa, fb);
+}
+
+py::array_t<double> mat4(const Matrix4d &T) {
+    py::array_t<double> a({4, 4});
+    std::memcpy(a.mutable_data(), T.data(), sizeof(double) * 16);
+    return a;
+}
+
+}  // namespace
+
+PYBIND11_MODULE(py_misc3d, m) {
+    m.doc() = "Misc3D RANSAC / segmentation / registration path, B200 (sm_100a) build";
+
+    py::module_ common = m.def_submodule("common");
+    common.def(
+        "fit_plane",
+        [](const py::object &pc, double threshold, size_t max_iteration, double probability, const py::object &seed) {
+            return fit_primitive<misc3d::common::RANSACPlane, misc3d::common::Plane>(pc, threshold, max_iteration,
+                                                                                    probability, seed, false);
+        },
+        "Fit a plane from point clouds", py::arg("pc"), py::arg("threshold") = 0.01, py::arg("max_iteration") = 1000,
+        py::arg("probability") = 0.9999, py::kw_only(), py::arg("seed") = py::none());
+    common.def(
+        "fit_sphere",
+        [](const py::object &pc, double threshold, size_t max_iteration, double probability, const py::object &seed) {
+            return fit_primitive<misc3d::common::RANSACShpere, misc3d::common::Sphere>(pc, threshold, max_iteration,
+                                                                                      probability, seed, false);
+        },
+        "Fit a sphere from point clouds", py::arg("pc"), py::arg("threshold") = 0.01, py::arg("max_iteration") = 1000,
+        py::arg("probability") = 0.9999, py::kw_only(), py::arg("seed") = py::none());
+    common.def(
+        "fit_cylinder",
+        [](const py::object &pc, double threshold, size_t max_iteration, double probability, const py::object &seed) {
+            return fit_primitive<misc3d::common::RANSACCylinder, misc3d::common::Cylinder>(
+                pc, threshold, max_iteration, probability, seed, true);
+        },
+        "Fit a cylinder from point clouds", py::arg("pc"), py::arg("threshold") = 0.01,
+        py::arg("max_iteration") = 1000, py::arg("probability") = 0.9999, py::kw_only(),
+        py::arg("seed") = py::none());
+
+    py::module_ seg = m.def_submodule("segmentation");
+    seg.def(
+        "segment_plane_iterative",
+        [](const py::object &pcd, const double threshold, const int max_iteration, const double min_ratio,
+           const py::object &seed) {
+            bool is_o3d = false;
+            PointCloud pc = cloud_from_py(pcd, &is_o3d);
+            uint32_t s = 0;
+            if (!seed.is_none()) s = seed.cast<uint32_t>();
+            std::vector<std::pair<Vector4d, PointCloud>> res;
+            {
+                py::gil_scoped_release nogil;
+                res = segmentation::SegmentPlaneIterative(pc, threshold, max_iteration, min_ratio,
+                                                          seed.is_none() ? nullptr : &s);
+            }
+            py::list out;
+            py::object o3d_cloud = py::none(), o3d_vec = py::none();
+            if (is_o3d) { /* hand clusters back as open3d.geometry.PointCloud when Open3D is there */
+                try {
+                    py::module_ o3d = py::module_::import("open3d");
+                    o3d_cloud = o3d.attr("geometry").attr("PointCloud");
+                    o3d_vec = o3d.attr("utility").attr("Vector3dVector");
+                } catch (py::error_already_set &) {
+                    o3d_cloud = py::none();
+                }
+            }
+            for (auto &pr : res) {
+                py::array_t<double> plane(4);
+                std::memcpy(plane.mutable_data(), pr.first.data(), sizeof(double) * 4);
+                const size_t k = pr.second.points_.size();
+                py::array_t<double> pts({(py::ssize_t)k, (py::ssize_t)3});
+                if (k) std::memcpy(pts.mutable_data(), pr.second.points_[0].data(), sizeof(double) * 3 * k);
+                py::object cluster = pts;
+                if (!o3d_cloud.is_none()) cluster = o3d_cloud(o3d_vec(pts));
+                out.append(py::make_tuple(plane, cluster));
+            }
+            return out;
+        },
+        "Segment plane iteratively using RANSAC plane fitting", py::arg("pcd"), py::arg("threshold"),
+        py::arg("max_iteration") = 100, py::arg("min_ratio") = 0.05, py::kw_only(), py::arg("seed") = py::none());
+
+    py::module_ reg = m.def_submodule("registration");
+    py::enum_<registration::MatchMethod>(reg, "MatchMethod")
+        .value("FLANN", registration::MatchMethod::FLANN)
+        .value("ANNOY", registration::MatchMethod::ANNOY)
+        .export_values();
+    reg.def("match_correspondence", &match, "Match corresponding point clouds (exact brute-force search on the GPU)",
+            py::arg("src"), py::arg("dst"), py::arg("method") = registration::MatchMethod::ANNOY,
+            py::arg("n_trees") = 4);
+    reg.def(
+        "compute_transformation_ransac",
+        [](const py::object &src, const py::object &dst,
+           const std::pair<std::vector<size_t>, std::vector<size_t>> &corres, double threshold, int max_iter,
+           double edge_length_threshold, const py::object &seed) {
+            PointCloud s = cloud_from_py(src), d = cloud_from_py(dst);
+            registration::RANSACSolver solver(threshold, max_iter, edge_length_threshold);
+            if (!seed.is_none()) solver.SetSeed(seed.cast<uint32_t>());
+            Matrix4d T;
+            {
+                py::gil_scoped_release nogil;
+                T = solver.Solve(s, d, corres);
+            }
+            return mat4(T);
+        },
+        "Compute 3D rigid transformation from corresponding point clouds using RANSAC", py::arg("src"),
+        py::arg("dst"), py::arg("corres"), py::arg("threshold") = 0.01, py::arg("max_iter") = 100000,
+        py::arg("edge_length_threshold") = 0.9, py::kw_only(), py::arg("seed") = py::none());
+    reg.def(
+        "compute_transformation_least_square",
+        [](const py::object &src, const py::object &dst) {
+            registration::LeastSquareSolver solver;
+            const auto s = rows3(py::hasattr(src, "points") ? py::object(src.attr("points")) : src, "src");
+            const auto d = rows3(py::hasattr(dst, "points") ? py::object(dst.attr("points")) : dst, "dst");
+            return mat4(solver.Solve(s, d));
+        },
+        "Compute 3D rigid transformation from corresponding point clouds using least square", py::arg("src"),
+        py::arg("dst"));
+
+    py::enum_<VerbosityLevel>(m, "VerbosityLevel", py::arithmetic(), "VerbosityLevel")
+        .value("Error", VerbosityLevel::Error)
+        .value("Warning", VerbosityLevel::Warning)
+        .value("Info", VerbosityLevel::Info)
+        .value("Debug", VerbosityLevel::Debug)
+        .export_values();
+    m.def("set_verbosity_level", &SetVerbosityLevel, "Set global verbosity level of Misc3D",
+          py::arg("verbosity_level"));
+    m.def("get_verbosity_level", &GetVerbosityLevel, "Get global verbosity level of Misc3D");
+}
