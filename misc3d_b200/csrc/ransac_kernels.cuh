@@ -24,6 +24,10 @@ namespace m3d {
 
 constexpr int kTile = 1024;  /* points per TMA stage (16 KB)                      */
 constexpr int kStages = 3;   /* ring depth                                        */
+#ifndef M3D_UNROLL
+#define M3D_UNROLL 16
+#endif
+constexpr int kUnroll = M3D_UNROLL;
 constexpr int kSub = 32; /* points between two "any point inside the band?" checks = one warp-wide rescan */
 constexpr uint32_t kInvalidBit = 0x80000000u;
 constexpr double kU32 = 5.9604644775390625e-08; /* 2^-24 */
@@ -511,7 +515,7 @@ __global__ void __launch_bounds__(THREADS) score_kernel(const ScoreArgs a) {
         for (int s0 = 0; s0 < npt; s0 += kSub) {
             const int cnt = min(kSub, npt - s0);
             if (cnt == kSub) {
-#pragma unroll 8
+#pragma unroll kUnroll
                 for (int j = 0; j < kSub; ++j) {
                     const float4 p = sp[s0 + j];
 #pragma unroll
@@ -532,12 +536,17 @@ __global__ void __launch_bounds__(THREADS) score_kernel(const ScoreArgs a) {
                     }
                 }
             }
+            bool any_flag = false;
 #pragma unroll
-            for (int h = 0; h < HPT; ++h) {
-                const bool flag = mn[h] < f[h].band;
-                const unsigned need = __ballot_sync(0xffffffffu, flag && row[h] < a.rows);
-                if (need) rescan_warp<KIND>(a, need, row[h], f[h], sp + s0, base + s0, cnt, nres);
-                if (flag) mn[h] = INFINITY;
+            for (int h = 0; h < HPT; ++h) any_flag = any_flag || (mn[h] < f[h].band);
+            if (__any_sync(0xffffffffu, any_flag)) { /* rare: some lane saw a point inside its band */
+#pragma unroll
+                for (int h = 0; h < HPT; ++h) {
+                    const bool flag = mn[h] < f[h].band;
+                    const unsigned need = __ballot_sync(0xffffffffu, flag && row[h] < a.rows);
+                    if (need) rescan_warp<KIND>(a, need, row[h], f[h], sp + s0, base + s0, cnt, nres);
+                    if (flag) mn[h] = INFINITY;
+                }
             }
         }
         __syncthreads(); /* every warp is done with stage st */
