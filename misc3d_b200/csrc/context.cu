@@ -194,6 +194,7 @@ void m3d_ctx_destroy(m3d_ctx *c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     if (c->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->nccl_comm);
+    if (c->scratch_cloud) m3d_cloud_free(c->scratch_cloud);
     DevBuf *db[] = {&c->d_samples, &c->d_counts, &c->d_counts_all, &c->d_blk, &c->d_part, &c->d_small,
                     &c->d_inl,     &c->d_models, &c->d_valid,      &c->d_tmp0, &c->d_tmp1, &c->d_tmp2,
                     &c->d_tmp3,    &c->d_tmp4,   &c->d_tmp5,      &c->d_queue};

@@ -54,30 +54,32 @@ int prepare_cloud(m3d_ctx *ctx, m3d_cloud *c) {
     return M3D_OK;
 }
 
+/* (re)fills a cloud object: buffers are grow-only, so a cached object costs no cudaMalloc */
+int cloud_fill(m3d_ctx *ctx, m3d_cloud *c, const double *xyz, const double *nrm, size_t n, cudaMemcpyKind kind) {
+    c->ctx = ctx;
+    c->n = n;
+    c->has_normals = nrm != nullptr;
+    const size_t bytes = sizeof(double) * 3 * std::max<size_t>(n, 1);
+    M3D_CUDA(ctx, c->xyz.reserve(bytes));
+    if (nrm) M3D_CUDA(ctx, c->nrm.reserve(bytes));
+    if (n) {
+        M3D_CUDA(ctx, cudaMemcpyAsync(c->xyz.p, xyz, sizeof(double) * 3 * n, kind, ctx->stream));
+        if (nrm) M3D_CUDA(ctx, cudaMemcpyAsync(c->nrm.p, nrm, sizeof(double) * 3 * n, kind, ctx->stream));
+    }
+    return prepare_cloud(ctx, c);
+}
+
 int cloud_create(m3d_ctx *ctx, const double *xyz, const double *nrm, size_t n, cudaMemcpyKind kind,
                  m3d_cloud **out) {
     if (!ctx || !out || (n && !xyz)) return M3D_ERR_INVALID_ARG;
     if (n >= (size_t)kInvalidBit) return ctx->fail(M3D_ERR_INVALID_ARG, "clouds of >= 2^31 points are not supported");
     M3D_CUDA(ctx, cudaSetDevice(ctx->device));
     m3d_cloud *c = new m3d_cloud();
-    c->ctx = ctx;
-    c->n = n;
-    c->has_normals = nrm != nullptr;
-    auto fail = [&](int rc) {
+    const int rc = cloud_fill(ctx, c, xyz, nrm, n, kind);
+    if (rc != M3D_OK) {
         m3d_cloud_free(c);
         return rc;
-    };
-    const size_t bytes = sizeof(double) * 3 * std::max<size_t>(n, 1);
-    if (c->xyz.reserve(bytes) != cudaSuccess) return fail(ctx->fail(M3D_ERR_CUDA, "cudaMalloc(%zu) failed", bytes));
-    if (nrm && c->nrm.reserve(bytes) != cudaSuccess) return fail(ctx->fail(M3D_ERR_CUDA, "cudaMalloc(%zu) failed", bytes));
-    if (n) {
-        if (cudaMemcpyAsync(c->xyz.p, xyz, sizeof(double) * 3 * n, kind, ctx->stream) != cudaSuccess)
-            return fail(ctx->fail(M3D_ERR_CUDA, "copy of the cloud failed"));
-        if (nrm && cudaMemcpyAsync(c->nrm.p, nrm, sizeof(double) * 3 * n, kind, ctx->stream) != cudaSuccess)
-            return fail(ctx->fail(M3D_ERR_CUDA, "copy of the normals failed"));
     }
-    const int rc = prepare_cloud(ctx, c);
-    if (rc != M3D_OK) return fail(rc);
     *out = c;
     return M3D_OK;
 }
@@ -85,7 +87,7 @@ int cloud_create(m3d_ctx *ctx, const double *xyz, const double *nrm, size_t n, c
 /* ---- launch of the hot kernel for one (wave, kind) */
 template <int KIND, int THREADS, int HPT>
 int launch_score_t(m3d_ctx *ctx, const ScoreArgs &a, uint32_t ntiles) {
-    const size_t smem = (size_t)kStages * kTile * sizeof(float4) + kStages * sizeof(uint64_t);
+    const size_t smem = (size_t)kStages * kTile * sizeof(float4) + 2 * kStages * sizeof(uint64_t);
     M3D_CUDA(ctx, cudaFuncSetAttribute(score_kernel<KIND, THREADS, HPT>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const uint32_t hb = (a.rows + THREADS * HPT - 1) / (THREADS * HPT);
@@ -104,7 +106,7 @@ int launch_score_t(m3d_ctx *ctx, const ScoreArgs &a, uint32_t ntiles) {
     b.chunk_tiles = (ntiles + chunks - 1) / chunks;
     chunks = (ntiles + b.chunk_tiles - 1) / b.chunk_tiles;
     dim3 grid(hb, chunks);
-    score_kernel<KIND, THREADS, HPT><<<grid, THREADS, smem, ctx->stream>>>(b);
+    score_kernel<KIND, THREADS, HPT><<<grid, THREADS + 32, smem, ctx->stream>>>(b); /* + producer warp */
     M3D_LAUNCHED(ctx);
     return M3D_OK;
 }
@@ -534,11 +536,12 @@ int m3d_ransac_fit(m3d_ctx *ctx, int kind, const double *xyz, const double *nrm,
     *n_inl = 0;
     if (stats) memset(stats, 0, sizeof *stats);
     if (int rc = check_params(ctx, kind, n, nrm != nullptr, p)) return rc;
-    m3d_cloud *c = nullptr;
-    if (int rc = m3d_cloud_upload(ctx, xyz, nrm, n, &c)) return rc;
-    const int rc = m3d_ransac_fit_cloud(ctx, kind, c, p, model_out, inl_out, n_inl, stats);
-    m3d_cloud_free(c);
-    return rc;
+    if (n >= (size_t)kInvalidBit) return ctx->fail(M3D_ERR_INVALID_ARG, "clouds of >= 2^31 points are not supported");
+    M3D_CUDA(ctx, cudaSetDevice(ctx->device));
+    /* the staging cloud lives in the context: repeated calls re-use its device buffers */
+    if (!ctx->scratch_cloud) ctx->scratch_cloud = new m3d_cloud();
+    if (int rc = cloud_fill(ctx, ctx->scratch_cloud, xyz, nrm, n, cudaMemcpyHostToDevice)) return rc;
+    return m3d_ransac_fit_cloud(ctx, kind, ctx->scratch_cloud, p, model_out, inl_out, n_inl, stats);
 }
 
 int m3d_score_samples(m3d_ctx *ctx, int kind, const m3d_cloud *cloud, const uint32_t *samples, size_t rows,

@@ -25,7 +25,7 @@ namespace m3d {
 constexpr int kTile = 1024;  /* points per TMA stage (16 KB)                      */
 constexpr int kStages = 3;   /* ring depth                                        */
 #ifndef M3D_UNROLL
-#define M3D_UNROLL 16
+#define M3D_UNROLL 32
 #endif
 constexpr int kUnroll = M3D_UNROLL;
 constexpr int kSub = 32; /* points between two "any point inside the band?" checks = one warp-wide rescan */
@@ -42,6 +42,9 @@ __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_fence_init() {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     asm volatile(
@@ -456,31 +459,47 @@ __global__ void __launch_bounds__(256) resolve_queue_kernel(const ScoreArgs a) {
     }
 }
 
+/* THREADS consumer threads (HPT hypotheses each) + one producer warp that only feeds the TMA ring:
+ * consumers never meet at a CTA-wide barrier inside the main loop, a warp delayed by the rare path
+ * only holds back its own ring slot (full[] / empty[] mbarriers, kStages deep). */
 template <int KIND, int THREADS, int HPT>
-__global__ void __launch_bounds__(THREADS) score_kernel(const ScoreArgs a) {
+__global__ void __launch_bounds__(THREADS + 32) score_kernel(const ScoreArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float4 *tiles = reinterpret_cast<float4 *>(smem_raw);
     uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)kStages * kTile * sizeof(float4));
+    uint64_t *empty = full + kStages;
 
     const int tid = threadIdx.x;
     const uint32_t ntiles = (a.n + kTile - 1) / kTile;
     const uint32_t t0 = blockIdx.y * a.chunk_tiles;
     const uint32_t t1 = min(t0 + a.chunk_tiles, ntiles);
 
-    auto issue = [&](uint32_t t) {
-        const uint32_t base = t * kTile;
-        const uint32_t npt = min((uint32_t)kTile, a.n - base);
-        const int st = (t - t0) % kStages;
-        tma_load_1d(tiles + (size_t)st * kTile, a.pts32 + base, npt * (uint32_t)sizeof(float4), &full[st]);
-    };
-    if (tid == 0) {
+    if (tid == THREADS) {
 #pragma unroll
-        for (int s = 0; s < kStages; ++s) mbar_init(&full[s], 1);
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], THREADS / 32);
+        }
         mbar_fence_init();
-        for (uint32_t t = t0; t < t1 && t < t0 + kStages; ++t) issue(t);
+    }
+    __syncthreads(); /* the only CTA-wide barrier: ring barriers are initialised */
+
+    if (tid >= THREADS) { /* ---------------- producer warp: one elected lane issues the bulk copies */
+        if (tid == THREADS) {
+            for (uint32_t t = t0; t < t1; ++t) {
+                const uint32_t k = t - t0;
+                const int st = k % kStages;
+                if (k >= kStages) mbar_wait(&empty[st], ((k / kStages) - 1) & 1); /* slot released by all warps */
+                const uint32_t base = t * kTile;
+                const uint32_t npt = min((uint32_t)kTile, a.n - base);
+                tma_load_1d(tiles + (size_t)st * kTile, a.pts32 + base, npt * (uint32_t)sizeof(float4), &full[st]);
+            }
+        }
+        return;
     }
 
-    /* prologue: this thread's hypotheses -- gather, solve (fp64 reference order), fp32 coefficients */
+    /* ---------------- consumers.  Prologue: this thread's hypotheses -- gather, solve (fp64
+     * reference order), fp32 coefficients */
     const CloudMeta M = *a.meta;
     uint32_t row[HPT];
     Fast<KIND> f[HPT];
@@ -503,12 +522,12 @@ __global__ void __launch_bounds__(THREADS) score_kernel(const ScoreArgs a) {
         clo[h] = 0;
         mn[h] = INFINITY;
     }
-    __syncthreads(); /* barrier init visible to all waiters */
 
     uint32_t nres = 0;
     for (uint32_t t = t0; t < t1; ++t) {
-        const int st = (t - t0) % kStages;
-        mbar_wait(&full[st], ((t - t0) / kStages) & 1);
+        const uint32_t k = t - t0;
+        const int st = k % kStages;
+        mbar_wait(&full[st], (k / kStages) & 1);
         const float4 *sp = tiles + (size_t)st * kTile;
         const uint32_t base = t * kTile;
         const int npt = (int)min((uint32_t)kTile, a.n - base);
@@ -549,8 +568,8 @@ __global__ void __launch_bounds__(THREADS) score_kernel(const ScoreArgs a) {
                 }
             }
         }
-        __syncthreads(); /* every warp is done with stage st */
-        if (tid == 0 && t + kStages < t1) issue(t + kStages);
+        __syncwarp();
+        if ((tid & 31) == 0) mbar_arrive(&empty[st]); /* this warp is done with the slot */
     }
 
 #pragma unroll
