@@ -633,16 +633,16 @@ int m3d_segment_plane_iterative(m3d_ctx *ctx, const double *xyz, size_t n, doubl
     if (!ctx || !n_planes || (n && (!xyz || !labels)) || (cap_planes && !planes)) return M3D_ERR_INVALID_ARG;
     *n_planes = 0;
     if (device_ms) *device_ms = 0;
-    for (size_t i = 0; i < n; ++i) labels[i] = UINT64_MAX;
-    if (n < 3) return M3D_OK; /* :14-17 warning + empty result */
+    if (n < 3) { /* :14-17 warning + empty result */
+        for (size_t i = 0; i < n; ++i) labels[i] = UINT64_MAX;
+        return M3D_OK;
+    }
+    if (n >= (size_t)kInvalidBit) return ctx->fail(M3D_ERR_INVALID_ARG, "clouds of >= 2^31 points are not supported");
     if (max_iteration < 0) max_iteration = 0;
     M3D_CUDA(ctx, cudaSetDevice(ctx->device));
-    m3d_cloud *c = nullptr;
-    if (int rc = m3d_cloud_upload(ctx, xyz, nullptr, n, &c)) return rc;
-    struct Guard {
-        m3d_cloud *c;
-        ~Guard() { m3d_cloud_free(c); }
-    } guard{c};
+    if (!ctx->scratch_cloud) ctx->scratch_cloud = new m3d_cloud();
+    m3d_cloud *c = ctx->scratch_cloud; /* staging cloud, buffers re-used across calls */
+    if (int rc = cloud_fill(ctx, c, xyz, nullptr, n, cudaMemcpyHostToDevice)) return rc;
 
     /* ping-pong buffers for the shrinking cloud + original indices + labels */
     const size_t n3 = sizeof(double) * 3 * n;
@@ -652,12 +652,8 @@ int m3d_segment_plane_iterative(m3d_ctx *ctx, const double *xyz, size_t n, doubl
     M3D_CUDA(ctx, ctx->d_tmp3.reserve(sizeof(uint32_t) * n));                /* orig B     */
     M3D_CUDA(ctx, ctx->d_tmp4.reserve(sizeof(unsigned long long) * n));      /* labels     */
     M3D_CUDA(ctx, cudaMemsetAsync(ctx->d_tmp4.p, 0xff, sizeof(unsigned long long) * n, ctx->stream));
-    {
-        std::vector<uint32_t> iota(n);
-        for (size_t i = 0; i < n; ++i) iota[i] = (uint32_t)i;
-        M3D_CUDA(ctx, cudaMemcpyAsync(ctx->d_tmp2.p, iota.data(), sizeof(uint32_t) * n, cudaMemcpyHostToDevice, ctx->stream));
-        M3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    }
+    iota_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(ctx->d_tmp2.as<uint32_t>(), (uint32_t)n);
+    M3D_LAUNCHED(ctx);
     double *xyz_cur = c->xyz.as<double>(), *xyz_nxt = ctx->d_tmp0.as<double>();
     float4 *p32_cur = c->pts32.as<float4>(), *p32_nxt = ctx->d_tmp1.as<float4>();
     uint32_t *org_cur = ctx->d_tmp2.as<uint32_t>(), *org_nxt = ctx->d_tmp3.as<uint32_t>();

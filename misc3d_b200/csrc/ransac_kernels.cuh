@@ -186,6 +186,10 @@ __global__ void convert_final_kernel(const double *__restrict__ part, int nparts
     meta->mc = mc;
 }
 
+__global__ void iota_kernel(uint32_t *out, uint32_t n) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = i;
+}
+
 /* --------------------------------------------------------------- sample gather + minimal fit */
 /* RandomSampler row (draw order) -> SelectByIndex order (ascending, ransac.h:578 / Open3D mask
  * pass) -> MinimalFit.  Returns MinimalFit's bool. */

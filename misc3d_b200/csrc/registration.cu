@@ -243,6 +243,7 @@ struct RegArgs {
     uint32_t *list;            /* surviving rows (any order) */
     uint32_t *list_count;
     uint32_t *counts;          /* [rows] */
+    double *err2;              /* [rows] approximate sum of inlier d^2 (fp32 per sub-tile, fp64 across) */
     uint2 *queue;
     uint32_t *queue_count;
     uint32_t queue_cap;
@@ -366,6 +367,7 @@ __global__ void __launch_bounds__(128) reg_solve_kernel(RegArgs a) {
     for (int i = 0; i < 16; ++i) a.T[(size_t)r * 16 + i] = T[i];
     a.pass[r] = pass ? 1 : 0;
     a.counts[r] = 0;
+    a.err2[r] = 0.0;
     if (pass) a.list[atomicAdd(a.list_count, 1u)] = r;
 }
 
@@ -490,6 +492,7 @@ __global__ void __launch_bounds__(kRegThreads) reg_score_kernel(const RegArgs a)
     }
     uint32_t clo = 0;
     float mn = INFINITY;
+    double esum = 0; /* sum over provisional inliers of d^2 (only used to rank count ties) */
     __syncthreads();
     for (uint32_t t = t0; t < t1; ++t) {
         const int st = (t - t0) % kRegStages;
@@ -499,12 +502,16 @@ __global__ void __launch_bounds__(kRegThreads) reg_score_kernel(const RegArgs a)
         const int npt = (int)min((uint32_t)kRegTile, a.m - base);
         for (int s0 = 0; s0 < npt; s0 += kRegSub) {
             const int cnt = min(kRegSub, npt - s0);
+            const uint32_t c0 = clo;
+            float es = 0.f; /* sum of min(v, 0) = sum over inliers of (d^2 - thr^2) */
 #pragma unroll 4
             for (int j = 0; j < cnt; ++j) {
                 const float v = reg_v(f, sp[2 * (s0 + j)], sp[2 * (s0 + j) + 1], thr2f);
                 clo += __float_as_uint(v) >> 31;
                 mn = fminf(mn, fabsf(v));
+                es += fminf(v, 0.f);
             }
+            esum += (double)es + (double)(clo - c0) * (double)thr2f;
             if (mn < f.band) {
                 reg_rescan(a, row, f, thr2f, sp + 2 * s0, base + s0, cnt);
                 mn = INFINITY;
@@ -514,7 +521,10 @@ __global__ void __launch_bounds__(kRegThreads) reg_score_kernel(const RegArgs a)
         __syncthreads();
         if (tid == 0 && t + kRegStages < t1) issue(t + kRegStages);
     }
-    if (active && clo) atomicAdd(&a.counts[row], clo);
+    if (active && clo) {
+        atomicAdd(&a.counts[row], clo);
+        atomicAdd(&a.err2[row], esum);
+    }
 }
 
 __global__ void __launch_bounds__(256) reg_resolve_kernel(const RegArgs a) {
@@ -733,13 +743,13 @@ int m3d_ransac_registration(m3d_ctx *ctx, const double *src_xyz, size_t ns, cons
     M3D_CUDA(ctx, ctx->d_tmp1.reserve(sizeof(double) * 3 * nd));
     M3D_CUDA(ctx, ctx->d_tmp2.reserve(sizeof(uint32_t) * 2 * m));
     M3D_CUDA(ctx, ctx->d_tmp3.reserve(sizeof(float4) * 2 * m));
-    M3D_CUDA(ctx, ctx->d_tmp4.reserve((sizeof(double) * 16 + 1 + 4 + 4) * (size_t)kWaveMax + 64));
+    M3D_CUDA(ctx, ctx->d_tmp4.reserve((sizeof(double) * 17 + 1 + 4 + 4) * (size_t)kWaveMax + 64));
     M3D_CUDA(ctx, ctx->d_samples.reserve(sizeof(uint32_t) * 3 * (size_t)kWaveMax));
     M3D_CUDA(ctx, ctx->h_samples.reserve(sizeof(uint32_t) * 3 * (size_t)kWaveMax));
     M3D_CUDA(ctx, ctx->d_queue.reserve(sizeof(uint2) * (size_t)kQueueCap + 16));
     M3D_CUDA(ctx, ctx->d_small.reserve(sizeof(RegSmall) + 4096));
     M3D_CUDA(ctx, ctx->h_small.reserve(sizeof(RegSmall) + 4096));
-    M3D_CUDA(ctx, ctx->h_counts.reserve((4 + 1) * (size_t)kWaveMax));
+    M3D_CUDA(ctx, ctx->h_counts.reserve((8 + 4 + 1) * (size_t)kWaveMax));
     M3D_CUDA(ctx, ctx->d_part.reserve(sizeof(double) * 2 * 1024));
     RegSmall *ds = ctx->d_small.as<RegSmall>();
     RegSmall *hs = ctx->h_small.as<RegSmall>();
@@ -770,7 +780,8 @@ int m3d_ransac_registration(m3d_ctx *ctx, const double *src_xyz, size_t ns, cons
     a.edge_thr = edge_thr;
     char *w = ctx->d_tmp4.as<char>();
     a.T = reinterpret_cast<double *>(w);
-    a.counts = reinterpret_cast<uint32_t *>(w + sizeof(double) * 16 * (size_t)kWaveMax);
+    a.err2 = reinterpret_cast<double *>(w + sizeof(double) * 16 * (size_t)kWaveMax);
+    a.counts = reinterpret_cast<uint32_t *>(w + sizeof(double) * 17 * (size_t)kWaveMax);
     a.list = a.counts + kWaveMax;
     a.pass = reinterpret_cast<uint8_t *>(a.list + kWaveMax);
     a.list_count = &ds->list_count;
@@ -815,7 +826,7 @@ int m3d_ransac_registration(m3d_ctx *ctx, const double *src_xyz, size_t ns, cons
     std::mt19937 rng(seed);
     std::uniform_int_distribution<int> dist(0, (int)m - 1);
     double best_fit = 0, best_rmse = 0;
-    bool best_rmse_known = true, best_rmse_exact = true, found = false;
+    bool best_rmse_known = true, best_rmse_accurate = true, best_rmse_exact = true, found = false;
     int est_k = max_iter;
     bool stopped = false;
     uint32_t wave = (confidence >= 1.0) ? kWaveMax : 1024;
@@ -842,8 +853,10 @@ int m3d_ransac_registration(m3d_ctx *ctx, const double *src_xyz, size_t ns, cons
         reg_resolve_kernel<<<ctx->sm_count * 2, 256, 0, ctx->stream>>>(a);
         M3D_LAUNCHED(ctx);
         M3D_CUDA(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));
-        uint32_t *hcnt = ctx->h_counts.as<uint32_t>();
+        double *herr = ctx->h_counts.as<double>();
+        uint32_t *hcnt = reinterpret_cast<uint32_t *>(herr + kWaveMax);
         uint8_t *hpass = reinterpret_cast<uint8_t *>(hcnt + kWaveMax);
+        M3D_CUDA(ctx, cudaMemcpyAsync(herr, a.err2, sizeof(double) * rows, cudaMemcpyDeviceToHost, ctx->stream));
         M3D_CUDA(ctx, cudaMemcpyAsync(hcnt, a.counts, sizeof(uint32_t) * rows, cudaMemcpyDeviceToHost, ctx->stream));
         M3D_CUDA(ctx, cudaMemcpyAsync(hpass, a.pass, rows, cudaMemcpyDeviceToHost, ctx->stream));
         M3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -870,28 +883,37 @@ int m3d_ransac_registration(m3d_ctx *ctx, const double *src_xyz, size_t ns, cons
             const double fitness = (double)good / (double)m;
             bool better = false;
             double mine = 0;
-            bool mine_known = false, mine_exact = false;
+            bool mine_known = false, mine_exact = false, mine_accurate = false;
             if (fitness > best_fit) {
                 better = true;
-            } else if (fitness == best_fit) {
-                double hT[16];
-                if (int rc = fetch_T(r, hT)) return rc;
-                double theirs = best_rmse;
-                if (!best_rmse_known) {
-                    if (int rc = eval_T(bestT.data(), false, &theirs, st.best_count)) return rc;
-                    best_rmse_exact = false;
-                }
-                if (int rc = eval_T(hT, false, &mine, good)) return rc;
-                if (std::fabs(mine - theirs) <= 1e-9 * std::max(mine, theirs)) {
-                    if (!best_rmse_exact)
-                        if (int rc = eval_T(bestT.data(), true, &theirs, st.best_count)) return rc;
-                    if (int rc = eval_T(hT, true, &mine, good)) return rc;
-                    best_rmse_exact = true;
-                    mine_exact = true;
-                }
-                best_rmse = theirs;
-                best_rmse_known = true;
+                mine = std::sqrt(std::max(herr[r], 0.0) / (double)good); /* kernel estimate, see below */
                 mine_known = true;
+            } else if (fitness == best_fit) {
+                /* inlier-count tie (frequent here): rank by rmse.  The scoring kernel's sum of d^2 is
+                 * good to ~2e-6 relative; only closer calls are re-evaluated in fp64 (parallel sum,
+                 * then the reference's index-order sum if still too close to call) */
+                mine = std::sqrt(std::max(herr[r], 0.0) / (double)good);
+                mine_known = true;
+                double theirs = best_rmse;
+                if (std::fabs(mine - theirs) <= 1e-5 * std::max(mine, theirs) || !best_rmse_known) {
+                    double hT[16];
+                    if (int rc = fetch_T(r, hT)) return rc;
+                    if (!best_rmse_accurate) {
+                        if (int rc = eval_T(bestT.data(), false, &theirs, st.best_count)) return rc;
+                        best_rmse_accurate = true;
+                        best_rmse_exact = false;
+                    }
+                    if (int rc = eval_T(hT, false, &mine, good)) return rc;
+                    mine_accurate = true;
+                    if (std::fabs(mine - theirs) <= 1e-9 * std::max(mine, theirs)) {
+                        if (!best_rmse_exact)
+                            if (int rc = eval_T(bestT.data(), true, &theirs, st.best_count)) return rc;
+                        if (int rc = eval_T(hT, true, &mine, good)) return rc;
+                        best_rmse_exact = true;
+                        mine_exact = true;
+                    }
+                    best_rmse = theirs;
+                }
                 better = mine < theirs;
             }
             if (better) {
@@ -900,7 +922,8 @@ int m3d_ransac_registration(m3d_ctx *ctx, const double *src_xyz, size_t ns, cons
                 st.best_index = (uint64_t)itr;
                 st.best_count = good;
                 best_rmse_known = mine_known;
-                best_rmse_exact = mine_known && mine_exact;
+                best_rmse_accurate = mine_accurate;
+                best_rmse_exact = mine_exact;
                 if (mine_known) best_rmse = mine;
                 found = true;
                 est_k = reg_update_limit(good, m, confidence, est_k);
@@ -911,7 +934,7 @@ int m3d_ransac_registration(m3d_ctx *ctx, const double *src_xyz, size_t ns, cons
     }
     if (found) {
         memcpy(T_out, bestT.data(), sizeof(double) * 16);
-        if (!best_rmse_known || !best_rmse_exact) {
+        if (!best_rmse_accurate) {
             double r = 0;
             if (int rc = eval_T(bestT.data(), false, &r, st.best_count)) return rc;
             best_rmse = r;
