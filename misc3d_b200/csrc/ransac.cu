@@ -87,25 +87,23 @@ int cloud_create(m3d_ctx *ctx, const double *xyz, const double *nrm, size_t n, c
 /* ---- launch of the hot kernel for one (wave, kind) */
 template <int KIND, int THREADS, int HPT>
 int launch_score_t(m3d_ctx *ctx, const ScoreArgs &a, uint32_t ntiles) {
-    const size_t smem = (size_t)kStages * kTile * sizeof(float4) + 2 * kStages * sizeof(uint64_t);
+    const size_t smem = (size_t)kStages * kTile * sizeof(float4) + 2 * kStages * sizeof(uint64_t) + kStages * sizeof(uint32_t) + 16;
     M3D_CUDA(ctx, cudaFuncSetAttribute(score_kernel<KIND, THREADS, HPT>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const uint32_t hb = (a.rows + THREADS * HPT - 1) / (THREADS * HPT);
-    /* point chunks: enough CTAs for >= ~8 balanced waves over the SMs, each chunk a whole number
-     * of tiles.  Grid = hypothesis blocks x point chunks, chunks a multiple of the SM count. */
-    const uint32_t resident = (uint32_t)ctx->sm_count * (THREADS >= 256 ? 2u : 4u);
-    static int waves = 0;
-    if (!waves) {
-        const char *e = getenv("M3D_CHUNK_WAVES");
-        waves = (e && atoi(e) > 0) ? atoi(e) : 8;
-    }
-    uint32_t chunks = std::max<uint32_t>(1, (waves * resident + hb - 1) / hb);
-    chunks = ((chunks + ctx->sm_count - 1) / ctx->sm_count) * ctx->sm_count;
-    chunks = std::min(chunks, ntiles);
+    /* one resident wave: CTAs per hypothesis block = resident CTA slots / hypothesis blocks; every
+     * group pulls tiles from its own cursor */
+    int per_sm = 0;
+    M3D_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, score_kernel<KIND, THREADS, HPT>,
+                                                                 THREADS + 32, smem));
+    const uint32_t slots = (uint32_t)ctx->sm_count * (uint32_t)std::max(per_sm, 1);
+    uint32_t per_hb = std::max<uint32_t>(1, (slots + hb / 2) / hb);
+    per_hb = std::min(per_hb, ntiles);
+    M3D_CUDA(ctx, ctx->d_tiles.reserve(sizeof(uint32_t) * (size_t)hb));
+    M3D_CUDA(ctx, cudaMemsetAsync(ctx->d_tiles.p, 0, sizeof(uint32_t) * (size_t)hb, ctx->stream));
     ScoreArgs b = a;
-    b.chunk_tiles = (ntiles + chunks - 1) / chunks;
-    chunks = (ntiles + b.chunk_tiles - 1) / b.chunk_tiles;
-    dim3 grid(hb, chunks);
+    b.tile_counter = ctx->d_tiles.as<uint32_t>();
+    dim3 grid(hb, per_hb);
     score_kernel<KIND, THREADS, HPT><<<grid, THREADS + 32, smem, ctx->stream>>>(b); /* + producer warp */
     M3D_LAUNCHED(ctx);
     return M3D_OK;

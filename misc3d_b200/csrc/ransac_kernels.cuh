@@ -391,7 +391,8 @@ struct ScoreArgs {
     uint32_t n;
     uint32_t row_begin; /* first row of the wave buffer this launch scores             */
     uint32_t rows;      /* number of rows this launch scores                           */
-    uint32_t chunk_tiles;
+    uint32_t chunk_tiles;    /* score_exact_kernel only */
+    uint32_t *tile_counter;  /* [hypothesis blocks] next unclaimed tile (zeroed before the launch) */
 };
 
 /* the rare path, first half: some lane's hypothesis saw a point of this 32-point sub-tile inside
@@ -463,20 +464,23 @@ __global__ void __launch_bounds__(256) resolve_queue_kernel(const ScoreArgs a) {
     }
 }
 
-/* THREADS consumer threads (HPT hypotheses each) + one producer warp that only feeds the TMA ring:
- * consumers never meet at a CTA-wide barrier inside the main loop, a warp delayed by the rare path
- * only holds back its own ring slot (full[] / empty[] mbarriers, kStages deep). */
+/* Persistent CTAs.  A CTA = THREADS consumer threads (HPT hypotheses each) + one producer warp.
+ * blockIdx.x selects the hypothesis block; all CTAs with the same blockIdx.x pull 1024-point tiles
+ * from one atomic cursor (tile_counter[blockIdx.x]) until the cloud is exhausted, so the grid is one
+ * resident wave with no tail, and the fp64 prologue runs once per CTA.  The producer warp feeds a
+ * kStages-deep TMA ring (full[] / empty[] mbarriers): consumers never meet at a CTA-wide barrier
+ * inside the main loop.  Counts are integer sums, so the dynamic tile order does not affect results. */
+constexpr uint32_t kNoTile = 0xffffffffu;
 template <int KIND, int THREADS, int HPT>
 __global__ void __launch_bounds__(THREADS + 32) score_kernel(const ScoreArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float4 *tiles = reinterpret_cast<float4 *>(smem_raw);
     uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)kStages * kTile * sizeof(float4));
     uint64_t *empty = full + kStages;
+    volatile uint32_t *tile_id = reinterpret_cast<volatile uint32_t *>(empty + kStages);
 
     const int tid = threadIdx.x;
     const uint32_t ntiles = (a.n + kTile - 1) / kTile;
-    const uint32_t t0 = blockIdx.y * a.chunk_tiles;
-    const uint32_t t1 = min(t0 + a.chunk_tiles, ntiles);
 
     if (tid == THREADS) {
 #pragma unroll
@@ -488,12 +492,18 @@ __global__ void __launch_bounds__(THREADS + 32) score_kernel(const ScoreArgs a) 
     }
     __syncthreads(); /* the only CTA-wide barrier: ring barriers are initialised */
 
-    if (tid >= THREADS) { /* ---------------- producer warp: one elected lane issues the bulk copies */
+    if (tid >= THREADS) { /* ---------------- producer warp: one elected lane claims tiles and issues the bulk copies */
         if (tid == THREADS) {
-            for (uint32_t t = t0; t < t1; ++t) {
-                const uint32_t k = t - t0;
+            for (uint32_t k = 0;; ++k) {
                 const int st = k % kStages;
                 if (k >= kStages) mbar_wait(&empty[st], ((k / kStages) - 1) & 1); /* slot released by all warps */
+                const uint32_t t = atomicAdd(&a.tile_counter[blockIdx.x], 1u);
+                if (t >= ntiles) {
+                    tile_id[st] = kNoTile;
+                    mbar_arrive(&full[st]); /* release: consumers see the end marker */
+                    break;
+                }
+                tile_id[st] = t;
                 const uint32_t base = t * kTile;
                 const uint32_t npt = min((uint32_t)kTile, a.n - base);
                 tma_load_1d(tiles + (size_t)st * kTile, a.pts32 + base, npt * (uint32_t)sizeof(float4), &full[st]);
@@ -528,10 +538,11 @@ __global__ void __launch_bounds__(THREADS + 32) score_kernel(const ScoreArgs a) 
     }
 
     uint32_t nres = 0;
-    for (uint32_t t = t0; t < t1; ++t) {
-        const uint32_t k = t - t0;
+    for (uint32_t k = 0;; ++k) {
         const int st = k % kStages;
         mbar_wait(&full[st], (k / kStages) & 1);
+        const uint32_t t = tile_id[st];
+        if (t == kNoTile) break;
         const float4 *sp = tiles + (size_t)st * kTile;
         const uint32_t base = t * kTile;
         const int npt = (int)min((uint32_t)kTile, a.n - base);
