@@ -97,7 +97,7 @@ int launch_score_t(m3d_ctx *ctx, const ScoreArgs &a, uint32_t ntiles) {
     M3D_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, score_kernel<KIND, THREADS, HPT>,
                                                                  THREADS + 32, smem));
     const uint32_t slots = (uint32_t)ctx->sm_count * (uint32_t)std::max(per_sm, 1);
-    uint32_t per_hb = std::max<uint32_t>(1, (slots + hb / 2) / hb);
+    uint32_t per_hb = std::max<uint32_t>(1, (slots + hb - 1) / hb); /* late CTAs find the cursor advanced: work-conserving */
     per_hb = std::min(per_hb, ntiles);
     M3D_CUDA(ctx, ctx->d_tiles.reserve(sizeof(uint32_t) * (size_t)hb));
     M3D_CUDA(ctx, cudaMemsetAsync(ctx->d_tiles.p, 0, sizeof(uint32_t) * (size_t)hb, ctx->stream));

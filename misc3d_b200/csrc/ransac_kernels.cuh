@@ -273,6 +273,26 @@ __device__ __forceinline__ float fast_v(const Fast<KIND> &f, const float4 p) {
     return __fsub_rn(fabsf(fast_eval<KIND>(f, p)), f.T);
 }
 
+/* inner-loop bookkeeping: provisional inlier count (sign bit of v) and min |v|.
+ * M3D_EXP selects timing experiments (wrong results!): 1 = no min tracking, 2 = no count,
+ * 3 = count through the FMA pipe (IMAD.HI) */
+#ifndef M3D_EXP
+#define M3D_EXP 0
+#endif
+__device__ __forceinline__ void accumulate_v(float v, uint32_t &clo, float &mn) {
+#if M3D_EXP == 1
+    clo += __float_as_uint(v) >> 31;
+#elif M3D_EXP == 2
+    mn = fminf(mn, fabsf(v));
+#elif M3D_EXP == 3
+    clo = __umulhi(__float_as_uint(v), 2u) + clo;
+    mn = fminf(mn, fabsf(v));
+#else
+    clo += __float_as_uint(v) >> 31;
+    mn = fminf(mn, fabsf(v));
+#endif
+}
+
 template <int KIND>
 __device__ inline void make_fast(const double *m, bool ok, const CloudMeta &M, double thr, Fast<KIND> &f) {
     constexpr int NC = KIND == kCylinder ? 8 : 4;
@@ -555,8 +575,7 @@ __global__ void __launch_bounds__(THREADS + 32) score_kernel(const ScoreArgs a) 
 #pragma unroll
                     for (int h = 0; h < HPT; ++h) {
                         const float v = fast_v<KIND>(f[h], p);
-                        clo[h] += __float_as_uint(v) >> 31;
-                        mn[h] = fminf(mn[h], fabsf(v));
+                        accumulate_v(v, clo[h], mn[h]);
                     }
                 }
             } else {
@@ -565,8 +584,7 @@ __global__ void __launch_bounds__(THREADS + 32) score_kernel(const ScoreArgs a) 
 #pragma unroll
                     for (int h = 0; h < HPT; ++h) {
                         const float v = fast_v<KIND>(f[h], p);
-                        clo[h] += __float_as_uint(v) >> 31;
-                        mn[h] = fminf(mn[h], fabsf(v));
+                        accumulate_v(v, clo[h], mn[h]);
                     }
                 }
             }

@@ -55,5 +55,25 @@ def run():
         print(json.dumps({"launch": launch, **d}), flush=True)
 
 
+def raw():
+    """wall-clock of m3d_score_samples only (no self-check): for the M3D_EXP timing experiments"""
+    import time
+    import numpy as np
+    from misc3d_b200 import capi, synth
+    xyz, nrm = synth.make_c2()
+    ctx = capi.Context(0)
+    cloud = ctx.upload(xyz, nrm)
+    out = {}
+    for kind, name in ((0, "plane"), (1, "sphere"), (2, "cylinder")):
+        tab = capi.sample_table(1, len(xyz), capi.KSAMPLE[kind], 10000)
+        ts = []
+        for rep in range(5):
+            t0 = time.perf_counter()
+            ctx.score_samples(kind, cloud, tab, 0.01, want_models=False)
+            ts.append(time.perf_counter() - t0)
+        out[name] = round(1e3 * min(ts[1:]), 3)
+    print(json.dumps(out))
+
+
 if __name__ == "__main__":
-    {"build": build, "run": run, "one": one}[sys.argv[1]]()
+    {"build": build, "run": run, "one": one, "raw": raw}[sys.argv[1]]()
