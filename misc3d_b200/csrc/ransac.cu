@@ -42,12 +42,12 @@ int prepare_cloud(m3d_ctx *ctx, m3d_cloud *c) {
     double *mp = reinterpret_cast<double *>(bp + nb);
     bbox_kernel<<<nb, 256, 0, ctx->stream>>>(c->xyz.as<double>(), n, bp);
     M3D_LAUNCHED(ctx);
-    bbox_final_kernel<<<1, 32, 0, ctx->stream>>>(bp, nb, c->meta.as<CloudMeta>());
+    bbox_final_kernel<<<1, 256, 0, ctx->stream>>>(bp, nb, c->meta.as<CloudMeta>());
     M3D_LAUNCHED(ctx);
     convert_kernel<<<nb, 256, 0, ctx->stream>>>(c->xyz.as<double>(), n, c->meta.as<CloudMeta>(),
                                                 c->pts32.as<float4>(), mp);
     M3D_LAUNCHED(ctx);
-    convert_final_kernel<<<1, 32, 0, ctx->stream>>>(mp, nb, c->meta.as<CloudMeta>());
+    convert_final_kernel<<<1, 256, 0, ctx->stream>>>(mp, nb, c->meta.as<CloudMeta>());
     M3D_LAUNCHED(ctx);
     M3D_CUDA(ctx, cudaMemcpyAsync(&c->h_meta, c->meta.p, sizeof(CloudMeta), cudaMemcpyDeviceToHost, ctx->stream));
     M3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

@@ -137,16 +137,47 @@ __global__ void __launch_bounds__(256) bbox_kernel(const double *__restrict__ xy
     }
 }
 
-__global__ void bbox_final_kernel(const BBoxPart *__restrict__ part, int nparts, CloudMeta *meta) {
-    if (threadIdx.x != 0) return;
-    BBoxPart r = part[0];
-    for (int k = 1; k < nparts; ++k) {
+__global__ void __launch_bounds__(256) bbox_final_kernel(const BBoxPart *__restrict__ part, int nparts, CloudMeta *meta) {
+    double mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+    double mraw = 0;
+    int bad = 0;
+    for (int k = threadIdx.x; k < nparts; k += blockDim.x) {
+        const BBoxPart p = part[k];
+#pragma unroll
         for (int c = 0; c < 3; ++c) {
-            r.mn[c] = fmin(r.mn[c], part[k].mn[c]);
-            r.mx[c] = fmax(r.mx[c], part[k].mx[c]);
+            mn[c] = fmin(mn[c], p.mn[c]);
+            mx[c] = fmax(mx[c], p.mx[c]);
         }
-        r.mraw = fmax(r.mraw, part[k].mraw);
-        r.nonfinite |= part[k].nonfinite;
+        mraw = fmax(mraw, p.mraw);
+        bad |= p.nonfinite;
+    }
+    __shared__ BBoxPart sh[8];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        mn[c] = warp_min(mn[c]);
+        mx[c] = warp_max(mx[c]);
+    }
+    mraw = warp_max(mraw);
+    bad = __any_sync(0xffffffffu, bad);
+    if (lane == 0) {
+        for (int c = 0; c < 3; ++c) {
+            sh[w].mn[c] = mn[c];
+            sh[w].mx[c] = mx[c];
+        }
+        sh[w].mraw = mraw;
+        sh[w].nonfinite = bad;
+    }
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    BBoxPart r = sh[0];
+    for (int k = 1; k < 8; ++k) {
+        for (int c = 0; c < 3; ++c) {
+            r.mn[c] = fmin(r.mn[c], sh[k].mn[c]);
+            r.mx[c] = fmax(r.mx[c], sh[k].mx[c]);
+        }
+        r.mraw = fmax(r.mraw, sh[k].mraw);
+        r.nonfinite |= sh[k].nonfinite;
     }
     for (int c = 0; c < 3; ++c) {
         const double ctr = 0.5 * (r.mn[c] + r.mx[c]);
@@ -179,11 +210,17 @@ __global__ void __launch_bounds__(256) convert_kernel(const double *__restrict__
         part[blockIdx.x] = mc;
     }
 }
-__global__ void convert_final_kernel(const double *__restrict__ part, int nparts, CloudMeta *meta) {
-    if (threadIdx.x != 0) return;
+__global__ void __launch_bounds__(256) convert_final_kernel(const double *__restrict__ part, int nparts, CloudMeta *meta) {
     double mc = 0;
-    for (int k = 0; k < nparts; ++k) mc = fmax(mc, part[k]);
-    meta->mc = mc;
+    for (int k = threadIdx.x; k < nparts; k += blockDim.x) mc = fmax(mc, part[k]);
+    __shared__ double sh[8];
+    mc = warp_max(mc);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = mc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 1; k < 8; ++k) mc = fmax(mc, sh[k]);
+        meta->mc = mc;
+    }
 }
 
 __global__ void iota_kernel(uint32_t *out, uint32_t n) {

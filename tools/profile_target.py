@@ -1,5 +1,5 @@
-"""ncu target: one warm + one measured launch of the scoring kernel per primitive on the C2 cloud
-(10k hypotheses, 1M points), plus one full RANSAC fit each so that the refine passes appear."""
+"""ncu target.  `ransac` (default): one warm + one measured RANSAC fit per primitive on the C2 cloud
+(10k hypotheses, 1M points).  `c4`: match_correspondence + compute_transformation_ransac at C4 size."""
 import os
 import sys
 
@@ -7,10 +7,18 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from misc3d_b200 import capi, synth  # noqa: E402
 
-xyz, nrm = synth.make_c2()
+what = sys.argv[1] if len(sys.argv) > 1 else "ransac"
 ctx = capi.Context(0)
-cloud = ctx.upload(xyz, nrm)
-for kind in (0, 1, 2):
-    for rep in range(2):
-        rc, model, inl, st = ctx.ransac_fit_cloud(kind, cloud, 0.01, 10000, 1.0, seed=rep)
-        print(kind, rep, st["score_ms"], st["device_ms"], st["exact_resolves"])
+if what == "ransac":
+    xyz, nrm = synth.make_c2()
+    cloud = ctx.upload(xyz, nrm)
+    for kind in (0, 1, 2):
+        for rep in range(2):
+            rc, model, inl, st = ctx.ransac_fit_cloud(kind, cloud, 0.01, 10000, 1.0, seed=rep)
+            print(kind, rep, st["score_ms"], st["device_ms"], st["exact_resolves"])
+else:
+    d = synth.make_c4()
+    i0, i1, ms = ctx.match_correspondence(d["src_feat"], d["dst_feat"])
+    print("match", ms, len(i0))
+    rc, T, st = ctx.ransac_registration(d["src"], d["dst"], i0, i1, 0.02, 50000, 0.9, 1.0, 1)
+    print("reg", st)
