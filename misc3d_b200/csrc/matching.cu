@@ -19,6 +19,7 @@
 
 #include "context.h"
 #include "exact_math.cuh"
+#include "matching_tc.cuh"
 
 namespace m3d {
 
@@ -362,7 +363,20 @@ struct FeatDev {
     double *f64 = nullptr; /* dim x count, column-major */
     float *tiles = nullptr;
     uint32_t count = 0, ntiles = 0;
+    /* tensor-core path: bf16x3 split tiles in query / database form, fp32 squared norms */
+    __nv_bfloat16 *tq = nullptr, *td = nullptr;
+    float *norms = nullptr;
 };
+
+/* which search kernel: 2 = tcgen05 GEMM (dim <= 47), 1 = fp32 CUDA-core tiles (dim <= 128), 0 = fp64 only */
+static int match_path(int dim) {
+    const char *e = getenv("M3D_MATCH_PATH"); /* "fp32" / "fp64" force the other kernels (tests, A/B timing) */
+    const int KP = (dim + 3) & ~3;
+    if (e && !strcmp(e, "fp64")) return 0;
+    if (e && !strcmp(e, "fp32")) return KP <= kMaxKP ? 1 : 0;
+    if (tc::kprime(dim) <= tc::kMaxKPrime) return 2;
+    return KP <= kMaxKP ? 1 : 0;
+}
 
 struct MatchScratch { /* layout of the small device block */
     unsigned long long mn[kMaxKP], mx[kMaxKP];
@@ -372,9 +386,28 @@ struct MatchScratch { /* layout of the small device block */
     uint32_t total;
 };
 
-static int nn_direction(m3d_ctx *ctx, const FeatDev &A, const FeatDev &B, int dim, int KP, bool fast,
+static int nn_direction(m3d_ctx *ctx, const FeatDev &A, const FeatDev &B, int dim, int KP, int path,
                         const uint32_t *d_maxnorm_B, uint32_t *d_nn, uint32_t *d_amb, uint32_t *d_amb_count) {
-    if (fast) {
+    if (path == 2) {
+        tc::TcArgs ta{};
+        ta.Aq = A.tq;
+        ta.Bd = B.td;
+        ta.a_norms = A.norms;
+        ta.na = A.count;
+        ta.nb = B.count;
+        ta.KPr = tc::kprime(dim);
+        ta.maxnorm_bits = d_maxnorm_B;
+        ta.nn = d_nn;
+        ta.amb_list = d_amb;
+        ta.amb_count = d_amb_count;
+        const size_t smem = (size_t)3 * tc::kRows * ta.KPr * 2 + 128;
+        M3D_CUDA(ctx, cudaFuncSetAttribute(tc::nn_top2_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        tc::nn_top2_tc_kernel<<<A.ntiles, 192, smem, ctx->stream>>>(ta);
+        M3D_LAUNCHED(ctx);
+        nn_exact_kernel<<<ctx->sm_count * 4, 256, sizeof(double) * dim, ctx->stream>>>(
+            A.f64, B.f64, A.count, B.count, dim, d_amb, d_amb_count, d_nn);
+        M3D_LAUNCHED(ctx);
+    } else if (path == 1) {
         const size_t smem = (size_t)3 * (KP + 1) * kMT * sizeof(float) + 3 * sizeof(uint64_t);
         M3D_CUDA(ctx, cudaFuncSetAttribute(nn_top2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         nn_top2_kernel<<<A.ntiles, 256, smem, ctx->stream>>>(A.tiles, B.tiles, A.count, B.count, KP, d_maxnorm_B,
@@ -402,15 +435,21 @@ static int match_impl(m3d_ctx *ctx, const double *src, size_t ns, const double *
     if (device_ms) *device_ms = 0;
     if (ns == 0 || nd == 0) return M3D_OK;
     const int KP = (dim + 3) & ~3;
-    const bool fast = KP <= kMaxKP;
+    const int path = match_path(dim);
+    const bool fast = path != 0;
     FeatDev A, B;
     A.count = (uint32_t)ns;
     B.count = (uint32_t)nd;
     A.ntiles = (A.count + kMT - 1) / kMT;
     B.ntiles = (B.count + kMT - 1) / kMT;
     const size_t fa = sizeof(double) * (size_t)dim * ns, fb = sizeof(double) * (size_t)dim * nd;
-    const size_t ta = fast ? sizeof(float) * (size_t)A.ntiles * (KP + 1) * kMT : 16;
-    const size_t tb = fast ? sizeof(float) * (size_t)B.ntiles * (KP + 1) * kMT : 16;
+    const int KPr = tc::kprime(dim);
+    /* tensor-core path: per set one query-form and one database-form tile array (bf16) */
+    const size_t ta = path == 2 ? (size_t)2 * A.ntiles * tc::kRows * KPr * 2
+                                : (path == 1 ? sizeof(float) * (size_t)A.ntiles * (KP + 1) * kMT : 16);
+    const size_t tb = path == 2 ? (size_t)2 * B.ntiles * tc::kRows * KPr * 2
+                                : (path == 1 ? sizeof(float) * (size_t)B.ntiles * (KP + 1) * kMT : 16);
+    M3D_CUDA(ctx, ctx->d_tmp5.reserve(sizeof(float) * (ns + nd) + 64));
     M3D_CUDA(ctx, ctx->d_tmp0.reserve(fa));
     M3D_CUDA(ctx, ctx->d_tmp1.reserve(fb));
     M3D_CUDA(ctx, ctx->d_tmp2.reserve(ta));
@@ -422,6 +461,12 @@ static int match_impl(m3d_ctx *ctx, const double *src, size_t ns, const double *
     B.f64 = ctx->d_tmp1.as<double>();
     A.tiles = ctx->d_tmp2.as<float>();
     B.tiles = ctx->d_tmp3.as<float>();
+    A.tq = ctx->d_tmp2.as<__nv_bfloat16>();
+    A.td = A.tq + (size_t)A.ntiles * tc::kRows * KPr;
+    B.tq = ctx->d_tmp3.as<__nv_bfloat16>();
+    B.td = B.tq + (size_t)B.ntiles * tc::kRows * KPr;
+    A.norms = ctx->d_tmp5.as<float>();
+    B.norms = A.norms + ns;
     uint32_t *d_nn01 = ctx->d_tmp4.as<uint32_t>();
     uint32_t *d_nn10 = d_nn01 + ns;
     uint32_t *d_amb01 = d_nn10 + nd;
@@ -441,16 +486,33 @@ static int match_impl(m3d_ctx *ctx, const double *src, size_t ns, const double *
         M3D_LAUNCHED(ctx);
         feat_center_kernel<<<1, 128, 0, ctx->stream>>>(sc->mn, sc->mx, dim, sc->center);
         M3D_LAUNCHED(ctx);
-        feat_convert_kernel<<<A.ntiles, kMT, 0, ctx->stream>>>(A.f64, A.count, dim, KP, sc->center, A.tiles,
-                                                              &sc->maxnorm[0]);
-        M3D_LAUNCHED(ctx);
-        feat_convert_kernel<<<B.ntiles, kMT, 0, ctx->stream>>>(B.f64, B.count, dim, KP, sc->center, B.tiles,
-                                                              &sc->maxnorm[1]);
-        M3D_LAUNCHED(ctx);
+        if (path == 2) {
+            tc::feat_split_kernel<<<A.ntiles, tc::kRows, 0, ctx->stream>>>(A.f64, A.count, dim, KPr, sc->center, 0, A.tq,
+                                                                        A.norms, &sc->maxnorm[0]);
+            M3D_LAUNCHED(ctx);
+            tc::feat_split_kernel<<<B.ntiles, tc::kRows, 0, ctx->stream>>>(B.f64, B.count, dim, KPr, sc->center, 1, B.td,
+                                                                        B.norms, &sc->maxnorm[1]);
+            M3D_LAUNCHED(ctx);
+            if (both_directions) {
+                tc::feat_split_kernel<<<B.ntiles, tc::kRows, 0, ctx->stream>>>(B.f64, B.count, dim, KPr, sc->center, 0,
+                                                                            B.tq, B.norms, &sc->maxnorm[1]);
+                M3D_LAUNCHED(ctx);
+                tc::feat_split_kernel<<<A.ntiles, tc::kRows, 0, ctx->stream>>>(A.f64, A.count, dim, KPr, sc->center, 1,
+                                                                            A.td, A.norms, &sc->maxnorm[0]);
+                M3D_LAUNCHED(ctx);
+            }
+        } else {
+            feat_convert_kernel<<<A.ntiles, kMT, 0, ctx->stream>>>(A.f64, A.count, dim, KP, sc->center, A.tiles,
+                                                                  &sc->maxnorm[0]);
+            M3D_LAUNCHED(ctx);
+            feat_convert_kernel<<<B.ntiles, kMT, 0, ctx->stream>>>(B.f64, B.count, dim, KP, sc->center, B.tiles,
+                                                                  &sc->maxnorm[1]);
+            M3D_LAUNCHED(ctx);
+        }
     }
-    if (int rc = nn_direction(ctx, A, B, dim, KP, fast, &sc->maxnorm[1], d_nn01, d_amb01, &sc->amb_count[0])) return rc;
+    if (int rc = nn_direction(ctx, A, B, dim, KP, path, &sc->maxnorm[1], d_nn01, d_amb01, &sc->amb_count[0])) return rc;
     if (both_directions) {
-        if (int rc = nn_direction(ctx, B, A, dim, KP, fast, &sc->maxnorm[0], d_nn10, d_amb10, &sc->amb_count[1]))
+        if (int rc = nn_direction(ctx, B, A, dim, KP, path, &sc->maxnorm[0], d_nn10, d_amb10, &sc->amb_count[1]))
             return rc;
         /* mutual check + stable compaction */
         const uint32_t nblk = ((uint32_t)ns + kMB * kMItems - 1) / (kMB * kMItems);

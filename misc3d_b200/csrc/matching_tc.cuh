@@ -1,0 +1,298 @@
+/*
+ * matching_tc.cuh -- tensor-core (tcgen05 / TMEM / TMA) variant of the brute-force nearest-neighbour
+ * search of matching.cu.
+ *
+ * The squared distance is recast as a dense bf16 GEMM with fp32 accumulation in tensor memory:
+ * every centred fp32 component x is split into three bf16 terms x = h + m + l (24 mantissa bits),
+ * and the six significant cross products of a.b are laid out along K:
+ *     query form    Q(a) = [ h, h, m, h, l, m | 1, 1, 1 | 0.. ]
+ *     database form D(b) = [-2h,-2m,-2h,-2l,-2h,-2m | n_h, n_m, n_l | 0.. ]      (n = |b|^2 split the same way)
+ * so that  Q(a).D(b) = |b|^2 - 2 a.b  up to ~2^-24 relative to |a||b| -- the ranking key of row a
+ * (|a|^2 is constant per row).  K' = 6*dim + 3 padded to a multiple of 16 (dim 33 -> 208 = 13 MMAs of
+ * K = 16).  Rows whose best / second-best gap is inside the error bound are re-searched in fp64 by
+ * nn_exact_kernel exactly as for the fp32 kernel, so the result stays bit-identical to the oracle.
+ *
+ * One CTA = one 128-row block of queries x all database tiles:
+ *   warp 0      TMA producer  (1-D cp.async.bulk of pre-tiled operands, 2-stage ring)
+ *   warp 1      TMEM allocator + single-thread tcgen05.mma issuer (M128 x N128 x K16, kind::f16, bf16 in, f32 out)
+ *   warps 2-5   epilogue: tcgen05.ld 32 lanes x 32 columns -> registers, running (best, index, second best)
+ * Operands sit in shared memory in the canonical no-swizzle K-major UMMA layout
+ *   element (row r, k) at  (k/8)*2048 + r*16 + (k%8)*2  bytes  (LBO = 2048 B, SBO = 128 B),
+ * which is also the global tile layout, so one bulk copy moves a whole 128 x K' tile.
+ */
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+namespace m3d {
+namespace tc {
+
+constexpr int kRows = 128;          /* rows of a tile (UMMA M and N)            */
+constexpr int kChunkBytes = 2048;   /* one 8-wide K chunk of 128 rows           */
+constexpr int kMaxKPrime = 288;     /* 3 tiles of 128 x K' bf16 must fit in smem */
+
+__host__ __device__ inline int kprime(int dim) { return ((6 * dim + 3 + 15) / 16) * 16; }
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    const uint32_t b = smem_u32(bar);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(dst)),
+        "l"(src), "r"(bytes), "r"(b)
+        : "memory");
+}
+
+/* shared-memory matrix descriptor, K-major, no swizzle (cute::UMMA::SmemDescriptor bit layout):
+ * [0,14) start>>4 | [16,30) leading byte offset>>4 | [32,46) stride byte offset>>4 | [46,48) version=1 */
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3fff);
+    d |= (uint64_t)((kChunkBytes >> 4) & 0x3fff) << 16; /* LBO: next 8-wide K chunk          */
+    d |= (uint64_t)((128 >> 4) & 0x3fff) << 32;         /* SBO: next group of 8 rows         */
+    d |= (uint64_t)1 << 46;                             /* descriptor version (Blackwell)    */
+    return d;
+}
+/* instruction descriptor (cute::UMMA::InstrDescriptor): D f32, A/B bf16, both K-major, M x N */
+__host__ __device__ constexpr uint32_t umma_idesc(int M, int N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+/* 32 lanes x 32 columns of fp32 accumulators -> 32 registers per thread (thread = TMEM lane = row) */
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+/* fp64 column-major descriptors -> bf16x3 split tiles in the UMMA layout.  role 0 = query form,
+ * 1 = database form.  Also writes the fp32 squared norms and their max. */
+__global__ void __launch_bounds__(128) feat_split_kernel(const double *__restrict__ F, uint32_t count, int dim,
+                                                         int KPr, const double *__restrict__ center, int role,
+                                                         __nv_bfloat16 *__restrict__ tiles,
+                                                         float *__restrict__ norms,
+                                                         uint32_t *__restrict__ maxnorm_bits) {
+    const uint32_t tile = blockIdx.x, r = threadIdx.x;
+    const uint32_t j = tile * kRows + r;
+    __nv_bfloat16 *t = tiles + (size_t)tile * kRows * KPr;
+    auto put = [&](int kk, float v) { t[(size_t)(kk >> 3) * (kChunkBytes / 2) + r * 8 + (kk & 7)] = __float2bfloat16_rn(v); };
+    const float sc = role ? -2.f : 1.f;
+    double n2 = 0;
+    if (j < count) {
+        for (int k = 0; k < dim; ++k) {
+            const double xd = F[(size_t)j * dim + k] - center[k];
+            n2 += xd * xd;
+            const float x = (float)xd;
+            const float h = __bfloat162float(__float2bfloat16_rn(x));
+            const float r1 = x - h;
+            const float m = __bfloat162float(__float2bfloat16_rn(r1));
+            const float l = r1 - m; /* rounded to bf16 by put() */
+            if (role == 0) {
+                put(0 * dim + k, h);
+                put(1 * dim + k, h);
+                put(2 * dim + k, m);
+                put(3 * dim + k, h);
+                put(4 * dim + k, l);
+                put(5 * dim + k, m);
+            } else {
+                put(0 * dim + k, sc * h);
+                put(1 * dim + k, sc * m);
+                put(2 * dim + k, sc * h);
+                put(3 * dim + k, sc * l);
+                put(4 * dim + k, sc * h);
+                put(5 * dim + k, sc * m);
+            }
+        }
+        const float nf = (float)n2;
+        if (role == 0) {
+            put(6 * dim + 0, 1.f);
+            put(6 * dim + 1, 1.f);
+            put(6 * dim + 2, 1.f);
+        } else {
+            const float h = __bfloat162float(__float2bfloat16_rn(nf));
+            const float r1 = nf - h;
+            const float m = __bfloat162float(__float2bfloat16_rn(r1));
+            put(6 * dim + 0, h);
+            put(6 * dim + 1, m);
+            put(6 * dim + 2, r1 - m);
+        }
+        for (int kk = 6 * dim + 3; kk < KPr; ++kk) put(kk, 0.f);
+        norms[j] = nf;
+        if (nf == nf && nf < 3e38f) atomicMax(maxnorm_bits, __float_as_uint(nf));
+    } else { /* padding rows: zero vector; as a database column its "norm" is huge so it never wins */
+        for (int kk = 0; kk < KPr; ++kk) put(kk, 0.f);
+        if (role == 1) put(6 * dim + 0, 1e30f);
+    }
+}
+
+struct TcArgs {
+    const __nv_bfloat16 *Aq; /* query-form tiles of the rows   */
+    const __nv_bfloat16 *Bd; /* database-form tiles of the columns */
+    const float *a_norms;    /* |a|^2 per row (fp32)           */
+    uint32_t na, nb;
+    int KPr;                 /* padded K'                      */
+    const uint32_t *maxnorm_bits;
+    uint32_t *nn, *amb_list, *amb_count;
+};
+
+__global__ void __launch_bounds__(192, 1) nn_top2_tc_kernel(const TcArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const uint32_t tile_bytes = (uint32_t)kRows * a.KPr * 2;
+    unsigned char *As = smem_raw;
+    unsigned char *Bs = smem_raw + tile_bytes;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + 3 * (size_t)tile_bytes);
+    uint64_t *a_full = bars, *b_full = bars + 1, *b_empty = bars + 3, *t_full = bars + 5, *t_empty = bars + 7;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 9);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t ntb = (a.nb + kRows - 1) / kRows;
+    const int nk = a.KPr / 16;
+
+    if (tid == 0) {
+        mbar_init(a_full, 1);
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&b_full[s], 1);
+            mbar_init(&b_empty[s], 1);
+            mbar_init(&t_full[s], 1);
+            mbar_init(&t_empty[s], 4); /* one arrive per epilogue warp */
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) { /* 256 TMEM columns: two 128 x 128 fp32 accumulators */
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"(256)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) { /* ---------------- TMA producer */
+            tma_load_1d(As, a.Aq + (size_t)blockIdx.x * kRows * a.KPr, tile_bytes, a_full);
+            for (uint32_t t = 0; t < ntb; ++t) {
+                const int st = t & 1;
+                mbar_wait(&b_empty[st], ((t >> 1) & 1) ^ 1);
+                tma_load_1d(Bs + (size_t)st * tile_bytes, a.Bd + (size_t)t * kRows * a.KPr, tile_bytes, &b_full[st]);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) { /* ---------------- MMA issuer */
+            const uint32_t idesc = umma_idesc(128, 128);
+            mbar_wait(a_full, 0);
+            for (uint32_t t = 0; t < ntb; ++t) {
+                const int st = t & 1;
+                mbar_wait(&b_full[st], (t >> 1) & 1);
+                mbar_wait(&t_empty[st], ((t >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t a0 = smem_u32(As), b0 = smem_u32(Bs + (size_t)st * tile_bytes);
+                for (int ks = 0; ks < nk; ++ks)
+                    umma_bf16(tmem_base + (uint32_t)st * 128u, umma_desc(a0 + ks * 2 * kChunkBytes),
+                              umma_desc(b0 + ks * 2 * kChunkBytes), idesc, ks > 0 ? 1u : 0u);
+                umma_commit(&b_empty[st]); /* smem slot reusable once these MMAs have read it */
+                umma_commit(&t_full[st]);  /* accumulator ready for the epilogue             */
+            }
+        }
+    } else { /* ---------------- epilogue warps 2..5: TMEM lane quarter = warp % 4 */
+        const uint32_t q = (uint32_t)warp & 3u;
+        const uint32_t row = blockIdx.x * kRows + q * 32 + lane;
+        float m1 = INFINITY, m2 = INFINITY;
+        uint32_t i1 = 0;
+        for (uint32_t t = 0; t < ntb; ++t) {
+            const int st = t & 1;
+            mbar_wait(&t_full[st], (t >> 1) & 1);
+            tc_fence_after();
+            const uint32_t jbase = t * kRows;
+            const uint32_t ncol = min((uint32_t)kRows, a.nb - jbase);
+#pragma unroll 1
+            for (uint32_t c0 = 0; c0 < (uint32_t)kRows; c0 += 32) {
+                float v[32];
+                tmem_ld32(tmem_base + ((q * 32u) << 16) + (uint32_t)st * 128u + c0, v);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const float d = v[i];
+                    if (c0 + i < ncol && d < m2) {
+                        if (d < m1) {
+                            m2 = m1;
+                            m1 = d;
+                            i1 = jbase + c0 + i;
+                        } else {
+                            m2 = d;
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&t_empty[st]);
+        }
+        if (row < a.na) {
+            a.nn[row] = i1;
+            /* error of the bf16x3 GEMM value against the exact distance:
+             * fp32 input rounding + dropped split terms + fp32 accumulation of K' products */
+            const float bnmax = __uint_as_float(*a.maxnorm_bits);
+            const float E = (float)(a.KPr + 64) * 1.1920929e-07f * (a.a_norms[row] + bnmax);
+            if (!(m2 - m1 > 2.5f * E)) a.amb_list[atomicAdd(a.amb_count, 1u)] = row;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256) : "memory");
+    }
+}
+
+}  // namespace tc
+}  // namespace m3d

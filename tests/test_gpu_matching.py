@@ -19,9 +19,14 @@ def test_golden_reg_small_matches(ctx, capi):
     np.testing.assert_array_equal(i1, g["i1"])
 
 
+@pytest.mark.parametrize("path", ["tc", "fp32", "fp64"])
 @pytest.mark.parametrize("ns,nd,dim", [(1000, 1300, 33), (257, 129, 33), (500, 500, 8), (300, 200, 352), (1, 5, 33),
-                                       (130, 1, 3)])
-def test_nearest_and_match_equal_oracle(ctx, capi, orc, ns, nd, dim):
+                                       (130, 1, 3), (700, 900, 47), (400, 300, 48)])
+def test_nearest_and_match_equal_oracle(ctx, capi, orc, ns, nd, dim, path, monkeypatch):
+    """all three search kernels (tcgen05 bf16x3 GEMM, fp32 CUDA-core tiles, fp64 only) + the fp64
+    re-search of close calls must give the oracle's indices"""
+    if path != "tc":
+        monkeypatch.setenv("M3D_MATCH_PATH", path)
     rng = np.random.default_rng(ns + nd + dim)
     a = np.asfortranarray(rng.uniform(0, 100, size=(dim, ns)))
     b = np.asfortranarray(rng.uniform(0, 100, size=(dim, nd)))
@@ -35,7 +40,10 @@ def test_nearest_and_match_equal_oracle(ctx, capi, orc, ns, nd, dim):
         assert np.all(np.diff(i0.astype(np.int64)) > 0)
 
 
-def test_exact_ties_pick_the_lowest_index(ctx, capi, orc):
+@pytest.mark.parametrize("path", ["tc", "fp32"])
+def test_exact_ties_pick_the_lowest_index(ctx, capi, orc, path, monkeypatch):
+    if path != "tc":
+        monkeypatch.setenv("M3D_MATCH_PATH", path)
     """FPFH histograms repeat on real data: duplicated descriptors must resolve to the lowest index"""
     rng = np.random.default_rng(3)
     base = np.round(rng.uniform(0, 10, size=(33, 40)))  # small integer lattice -> many equal distances
