@@ -400,7 +400,7 @@ static int nn_direction(m3d_ctx *ctx, const FeatDev &A, const FeatDev &B, int di
         ta.nn = d_nn;
         ta.amb_list = d_amb;
         ta.amb_count = d_amb_count;
-        const size_t smem = (size_t)3 * tc::kRows * ta.KPr * 2 + 128;
+        const size_t smem = (size_t)(1 + tc::kBStages) * tc::kRows * ta.KPr * 2 + 128;
         M3D_CUDA(ctx, cudaFuncSetAttribute(tc::nn_top2_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         tc::nn_top2_tc_kernel<<<A.ntiles, 192, smem, ctx->stream>>>(ta);
         M3D_LAUNCHED(ctx);

@@ -13,7 +13,7 @@
  * nn_exact_kernel exactly as for the fp32 kernel, so the result stays bit-identical to the oracle.
  *
  * One CTA = one 128-row block of queries x all database tiles:
- *   warp 0      TMA producer  (1-D cp.async.bulk of pre-tiled operands, 2-stage ring)
+ *   warp 0      TMA producer  (1-D cp.async.bulk of pre-tiled operands, 3-stage ring)
  *   warp 1      TMEM allocator + single-thread tcgen05.mma issuer (M128 x N128 x K16, kind::f16, bf16 in, f32 out)
  *   warps 2-5   epilogue: tcgen05.ld 32 lanes x 32 columns -> registers, running (best, index, second best)
  * Operands sit in shared memory in the canonical no-swizzle K-major UMMA layout
@@ -31,7 +31,8 @@ namespace tc {
 
 constexpr int kRows = 128;          /* rows of a tile (UMMA M and N)            */
 constexpr int kChunkBytes = 2048;   /* one 8-wide K chunk of 128 rows           */
-constexpr int kMaxKPrime = 288;     /* 3 tiles of 128 x K' bf16 must fit in smem */
+constexpr int kBStages = 3;         /* database-tile ring depth                  */
+constexpr int kMaxKPrime = 208;     /* (1 + kBStages) tiles of 128 x K' bf16 must fit in shared memory */
 
 __host__ __device__ inline int kprime(int dim) { return ((6 * dim + 3 + 15) / 16) * 16; }
 
@@ -189,9 +190,10 @@ __global__ void __launch_bounds__(192, 1) nn_top2_tc_kernel(const TcArgs a) {
     const uint32_t tile_bytes = (uint32_t)kRows * a.KPr * 2;
     unsigned char *As = smem_raw;
     unsigned char *Bs = smem_raw + tile_bytes;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + 3 * (size_t)tile_bytes);
-    uint64_t *a_full = bars, *b_full = bars + 1, *b_empty = bars + 3, *t_full = bars + 5, *t_empty = bars + 7;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 9);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + (1 + kBStages) * (size_t)tile_bytes);
+    uint64_t *a_full = bars, *b_full = bars + 1, *b_empty = b_full + kBStages, *t_full = b_empty + kBStages,
+             *t_empty = t_full + 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(t_empty + 2);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t ntb = (a.nb + kRows - 1) / kRows;
@@ -199,9 +201,11 @@ __global__ void __launch_bounds__(192, 1) nn_top2_tc_kernel(const TcArgs a) {
 
     if (tid == 0) {
         mbar_init(a_full, 1);
-        for (int s = 0; s < 2; ++s) {
+        for (int s = 0; s < kBStages; ++s) {
             mbar_init(&b_full[s], 1);
             mbar_init(&b_empty[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
             mbar_init(&t_full[s], 1);
             mbar_init(&t_empty[s], 4); /* one arrive per epilogue warp */
         }
@@ -222,8 +226,8 @@ __global__ void __launch_bounds__(192, 1) nn_top2_tc_kernel(const TcArgs a) {
         if (lane == 0) { /* ---------------- TMA producer */
             tma_load_1d(As, a.Aq + (size_t)blockIdx.x * kRows * a.KPr, tile_bytes, a_full);
             for (uint32_t t = 0; t < ntb; ++t) {
-                const int st = t & 1;
-                mbar_wait(&b_empty[st], ((t >> 1) & 1) ^ 1);
+                const int st = t % kBStages;
+                mbar_wait(&b_empty[st], ((t / kBStages) & 1) ^ 1);
                 tma_load_1d(Bs + (size_t)st * tile_bytes, a.Bd + (size_t)t * kRows * a.KPr, tile_bytes, &b_full[st]);
             }
         }
@@ -232,16 +236,16 @@ __global__ void __launch_bounds__(192, 1) nn_top2_tc_kernel(const TcArgs a) {
             const uint32_t idesc = umma_idesc(128, 128);
             mbar_wait(a_full, 0);
             for (uint32_t t = 0; t < ntb; ++t) {
-                const int st = t & 1;
-                mbar_wait(&b_full[st], (t >> 1) & 1);
-                mbar_wait(&t_empty[st], ((t >> 1) & 1) ^ 1);
+                const int st = t % kBStages, acc = t & 1;
+                mbar_wait(&b_full[st], (t / kBStages) & 1);
+                mbar_wait(&t_empty[acc], ((t >> 1) & 1) ^ 1);
                 tc_fence_after();
                 const uint32_t a0 = smem_u32(As), b0 = smem_u32(Bs + (size_t)st * tile_bytes);
                 for (int ks = 0; ks < nk; ++ks)
-                    umma_bf16(tmem_base + (uint32_t)st * 128u, umma_desc(a0 + ks * 2 * kChunkBytes),
+                    umma_bf16(tmem_base + (uint32_t)acc * 128u, umma_desc(a0 + ks * 2 * kChunkBytes),
                               umma_desc(b0 + ks * 2 * kChunkBytes), idesc, ks > 0 ? 1u : 0u);
                 umma_commit(&b_empty[st]); /* smem slot reusable once these MMAs have read it */
-                umma_commit(&t_full[st]);  /* accumulator ready for the epilogue             */
+                umma_commit(&t_full[acc]); /* accumulator ready for the epilogue             */
             }
         }
     } else { /* ---------------- epilogue warps 2..5: TMEM lane quarter = warp % 4 */
@@ -250,7 +254,7 @@ __global__ void __launch_bounds__(192, 1) nn_top2_tc_kernel(const TcArgs a) {
         float m1 = INFINITY, m2 = INFINITY;
         uint32_t i1 = 0;
         for (uint32_t t = 0; t < ntb; ++t) {
-            const int st = t & 1;
+            const int st = t & 1; /* accumulator buffer */
             mbar_wait(&t_full[st], (t >> 1) & 1);
             tc_fence_after();
             const uint32_t jbase = t * kRows;
@@ -259,6 +263,13 @@ __global__ void __launch_bounds__(192, 1) nn_top2_tc_kernel(const TcArgs a) {
             for (uint32_t c0 = 0; c0 < (uint32_t)kRows; c0 += 32) {
                 float v[32];
                 tmem_ld32(tmem_base + ((q * 32u) << 16) + (uint32_t)st * 128u + c0, v);
+                /* cheap screen: min of the 32 values (FMNMX3 tree); the running (best, second best)
+                 * changes O(log n) times per row, so the update below is the rare path */
+                float lo = fminf(fminf(v[0], v[1]), v[2]);
+#pragma unroll
+                for (int i = 3; i + 1 < 32; i += 2) lo = fminf(fminf(lo, v[i]), v[i + 1]);
+                lo = fminf(lo, v[31]);
+                if (c0 + 32 <= ncol && !(lo < m2)) continue;
 #pragma unroll
                 for (int i = 0; i < 32; ++i) {
                     const float d = v[i];
