@@ -244,51 +244,77 @@ __device__ __forceinline__ double l2_groups4(const double *a, const double *b, i
     return result;
 }
 
-/* exact 1-NN (strict <, lowest index on ties) for the listed rows; one CTA per row.
- * list == nullptr: all rows 0..na-1 */
+/* exact 1-NN (strict <, lowest index on ties) for the listed rows; one CTA per group of kXR rows
+ * (every database descriptor fetched from L2 serves kXR queries).  list == nullptr: all rows */
+constexpr int kXR = 8;
 __global__ void __launch_bounds__(256) nn_exact_kernel(const double *__restrict__ A, const double *__restrict__ B,
                                                        uint32_t na, uint32_t nb, int dim,
                                                        const uint32_t *__restrict__ list,
                                                        const uint32_t *__restrict__ list_count,
                                                        uint32_t *__restrict__ nn) {
-    extern __shared__ double qa[]; /* dim doubles */
-    __shared__ double sd[8];
-    __shared__ uint32_t sj[8];
+    extern __shared__ double qa[]; /* kXR x dim doubles */
+    __shared__ double sd[kXR][8];
+    __shared__ uint32_t sj[kXR][8];
     const uint32_t total = list ? *list_count : na;
-    for (uint32_t it = blockIdx.x; it < total; it += gridDim.x) {
-        const uint32_t row = list ? list[it] : it;
+    const uint32_t groups = (total + kXR - 1) / kXR;
+    for (uint32_t g = blockIdx.x; g < groups; g += gridDim.x) {
+        const uint32_t nr = min((uint32_t)kXR, total - g * kXR);
         __syncthreads();
-        for (int k = threadIdx.x; k < dim; k += blockDim.x) qa[k] = A[(size_t)row * dim + k];
+        for (uint32_t e = threadIdx.x; e < nr * (uint32_t)dim; e += blockDim.x) {
+            const uint32_t r = e / dim, k = e % dim;
+            const uint32_t row = list ? list[g * kXR + r] : g * kXR + r;
+            qa[r * dim + k] = A[(size_t)row * dim + k];
+        }
         __syncthreads();
-        double best = INFINITY;
-        uint32_t bj = 0xffffffffu;
+        double best[kXR];
+        uint32_t bj[kXR];
+#pragma unroll
+        for (int r = 0; r < kXR; ++r) {
+            best[r] = INFINITY;
+            bj[r] = 0xffffffffu;
+        }
         for (uint32_t j = threadIdx.x; j < nb; j += blockDim.x) {
-            const double d = l2_groups4(qa, B + (size_t)j * dim, dim);
-            if (d < best) {
-                best = d;
-                bj = j;
+            const double *b = B + (size_t)j * dim;
+#pragma unroll
+            for (int r = 0; r < kXR; ++r) {
+                if ((uint32_t)r < nr) {
+                    const double d = l2_groups4(qa + r * dim, b, dim);
+                    if (d < best[r]) {
+                        best[r] = d;
+                        bj[r] = j;
+                    }
+                }
             }
         }
-        for (int o = 16; o; o >>= 1) {
-            const double ob = __shfl_xor_sync(0xffffffffu, best, o);
-            const uint32_t oj = __shfl_xor_sync(0xffffffffu, bj, o);
-            if (ob < best || (ob == best && oj < bj)) {
-                best = ob;
-                bj = oj;
+#pragma unroll
+        for (int r = 0; r < kXR; ++r) {
+            double bb = best[r];
+            uint32_t jj = bj[r];
+            for (int o = 16; o; o >>= 1) {
+                const double ob = __shfl_xor_sync(0xffffffffu, bb, o);
+                const uint32_t oj = __shfl_xor_sync(0xffffffffu, jj, o);
+                if (ob < bb || (ob == bb && oj < jj)) {
+                    bb = ob;
+                    jj = oj;
+                }
             }
-        }
-        if ((threadIdx.x & 31) == 0) {
-            sd[threadIdx.x >> 5] = best;
-            sj[threadIdx.x >> 5] = bj;
+            if ((threadIdx.x & 31) == 0) {
+                sd[r][threadIdx.x >> 5] = bb;
+                sj[r][threadIdx.x >> 5] = jj;
+            }
         }
         __syncthreads();
-        if (threadIdx.x == 0) {
+        if (threadIdx.x < nr) {
+            const int r = threadIdx.x;
+            double bb = sd[r][0];
+            uint32_t jj = sj[r][0];
             for (int w = 1; w < 8; ++w)
-                if (sd[w] < best || (sd[w] == best && sj[w] < bj)) {
-                    best = sd[w];
-                    bj = sj[w];
+                if (sd[r][w] < bb || (sd[r][w] == bb && sj[r][w] < jj)) {
+                    bb = sd[r][w];
+                    jj = sj[r][w];
                 }
-            nn[row] = (bj == 0xffffffffu) ? 0u : bj; /* nothing compared below +inf: the reference keeps 0 */
+            const uint32_t row = list ? list[g * kXR + r] : g * kXR + r;
+            nn[row] = (jj == 0xffffffffu) ? 0u : jj; /* nothing compared below +inf: the reference keeps 0 */
         }
     }
 }
@@ -388,6 +414,10 @@ struct MatchScratch { /* layout of the small device block */
 
 static int nn_direction(m3d_ctx *ctx, const FeatDev &A, const FeatDev &B, int dim, int KP, int path,
                         const uint32_t *d_maxnorm_B, uint32_t *d_nn, uint32_t *d_amb, uint32_t *d_amb_count) {
+    const size_t xsmem = sizeof(double) * (size_t)dim * kXR;
+    if (xsmem > 200 * 1024) return ctx->fail(M3D_ERR_INVALID_ARG, "descriptor dimension %d too large", dim);
+    if (xsmem > 48 * 1024)
+        M3D_CUDA(ctx, cudaFuncSetAttribute(nn_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xsmem));
     if (path == 2) {
         tc::TcArgs ta{};
         ta.Aq = A.tq;
@@ -404,7 +434,7 @@ static int nn_direction(m3d_ctx *ctx, const FeatDev &A, const FeatDev &B, int di
         M3D_CUDA(ctx, cudaFuncSetAttribute(tc::nn_top2_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         tc::nn_top2_tc_kernel<<<A.ntiles, 192, smem, ctx->stream>>>(ta);
         M3D_LAUNCHED(ctx);
-        nn_exact_kernel<<<ctx->sm_count * 4, 256, sizeof(double) * dim, ctx->stream>>>(
+        nn_exact_kernel<<<ctx->sm_count * 4, 256, sizeof(double) * dim * kXR, ctx->stream>>>(
             A.f64, B.f64, A.count, B.count, dim, d_amb, d_amb_count, d_nn);
         M3D_LAUNCHED(ctx);
     } else if (path == 1) {
@@ -413,11 +443,11 @@ static int nn_direction(m3d_ctx *ctx, const FeatDev &A, const FeatDev &B, int di
         nn_top2_kernel<<<A.ntiles, 256, smem, ctx->stream>>>(A.tiles, B.tiles, A.count, B.count, KP, d_maxnorm_B,
                                                             d_nn, d_amb, d_amb_count);
         M3D_LAUNCHED(ctx);
-        nn_exact_kernel<<<ctx->sm_count * 4, 256, sizeof(double) * dim, ctx->stream>>>(
+        nn_exact_kernel<<<ctx->sm_count * 4, 256, sizeof(double) * dim * kXR, ctx->stream>>>(
             A.f64, B.f64, A.count, B.count, dim, d_amb, d_amb_count, d_nn);
         M3D_LAUNCHED(ctx);
     } else {
-        nn_exact_kernel<<<ctx->sm_count * 4, 256, sizeof(double) * dim, ctx->stream>>>(
+        nn_exact_kernel<<<ctx->sm_count * 4, 256, sizeof(double) * dim * kXR, ctx->stream>>>(
             A.f64, B.f64, A.count, B.count, dim, nullptr, nullptr, d_nn);
         M3D_LAUNCHED(ctx);
     }

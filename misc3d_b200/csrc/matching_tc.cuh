@@ -110,10 +110,10 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
           "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
         : "r"(taddr)
         : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]); /* valid after tmem_ld_wait() */
 }
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 /* fp64 column-major descriptors -> bf16x3 split tiles in the UMMA layout.  role 0 = query form,
  * 1 = database form.  Also writes the fp32 squared norms and their max. */
@@ -259,20 +259,29 @@ __global__ void __launch_bounds__(192, 1) nn_top2_tc_kernel(const TcArgs a) {
             tc_fence_after();
             const uint32_t jbase = t * kRows;
             const uint32_t ncol = min((uint32_t)kRows, a.nb - jbase);
-#pragma unroll 1
-            for (uint32_t c0 = 0; c0 < (uint32_t)kRows; c0 += 32) {
-                float v[32];
-                tmem_ld32(tmem_base + ((q * 32u) << 16) + (uint32_t)st * 128u + c0, v);
+            /* all four 32-column loads are in flight before the single wait */
+            float v[4][32];
+            const uint32_t tbase = tmem_base + ((q * 32u) << 16) + (uint32_t)st * 128u;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) tmem_ld32(tbase + 32u * g, v[g]);
+            tmem_ld_wait();
+            /* the accumulator buffer is free again as soon as the values sit in registers */
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&t_empty[st]);
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                const uint32_t c0 = 32u * g;
                 /* cheap screen: min of the 32 values (FMNMX3 tree); the running (best, second best)
                  * changes O(log n) times per row, so the update below is the rare path */
-                float lo = fminf(fminf(v[0], v[1]), v[2]);
+                float lo = fminf(fminf(v[g][0], v[g][1]), v[g][2]);
 #pragma unroll
-                for (int i = 3; i + 1 < 32; i += 2) lo = fminf(fminf(lo, v[i]), v[i + 1]);
-                lo = fminf(lo, v[31]);
+                for (int i = 3; i + 1 < 32; i += 2) lo = fminf(fminf(lo, v[g][i]), v[g][i + 1]);
+                lo = fminf(lo, v[g][31]);
                 if (c0 + 32 <= ncol && !(lo < m2)) continue;
 #pragma unroll
                 for (int i = 0; i < 32; ++i) {
-                    const float d = v[i];
+                    const float d = v[g][i];
                     if (c0 + i < ncol && d < m2) {
                         if (d < m1) {
                             m2 = m1;
@@ -284,9 +293,6 @@ __global__ void __launch_bounds__(192, 1) nn_top2_tc_kernel(const TcArgs a) {
                     }
                 }
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&t_empty[st]);
         }
         if (row < a.na) {
             a.nn[row] = i1;
