@@ -244,19 +244,23 @@ __device__ __forceinline__ double l2_groups4(const double *a, const double *b, i
     return result;
 }
 
-/* exact 1-NN (strict <, lowest index on ties) for the listed rows; one CTA per group of kXR rows
- * (every database descriptor fetched from L2 serves kXR queries).  list == nullptr: all rows */
-constexpr int kXR = 8;
+/* exact 1-NN (strict <, lowest index on ties) for the listed rows.  blockIdx.x walks groups of kXR
+ * rows (every database descriptor fetched from L2 serves kXR queries), blockIdx.y owns one of kXS
+ * contiguous column ranges; partial winners go to (pd, pj)[slot][y] and nn_exact_merge_kernel
+ * combines them in ascending column order.  list == nullptr: all rows */
+constexpr int kXR = 4, kXS = 8;
 __global__ void __launch_bounds__(256) nn_exact_kernel(const double *__restrict__ A, const double *__restrict__ B,
                                                        uint32_t na, uint32_t nb, int dim,
                                                        const uint32_t *__restrict__ list,
                                                        const uint32_t *__restrict__ list_count,
-                                                       uint32_t *__restrict__ nn) {
+                                                       double *__restrict__ pd, uint32_t *__restrict__ pj) {
     extern __shared__ double qa[]; /* kXR x dim doubles */
     __shared__ double sd[kXR][8];
     __shared__ uint32_t sj[kXR][8];
     const uint32_t total = list ? *list_count : na;
     const uint32_t groups = (total + kXR - 1) / kXR;
+    const uint32_t per = (nb + kXS - 1) / kXS;
+    const uint32_t j0 = min(nb, blockIdx.y * per), j1 = min(nb, j0 + per);
     for (uint32_t g = blockIdx.x; g < groups; g += gridDim.x) {
         const uint32_t nr = min((uint32_t)kXR, total - g * kXR);
         __syncthreads();
@@ -273,7 +277,7 @@ __global__ void __launch_bounds__(256) nn_exact_kernel(const double *__restrict_
             best[r] = INFINITY;
             bj[r] = 0xffffffffu;
         }
-        for (uint32_t j = threadIdx.x; j < nb; j += blockDim.x) {
+        for (uint32_t j = j0 + threadIdx.x; j < j1; j += blockDim.x) {
             const double *b = B + (size_t)j * dim;
 #pragma unroll
             for (int r = 0; r < kXR; ++r) {
@@ -313,9 +317,27 @@ __global__ void __launch_bounds__(256) nn_exact_kernel(const double *__restrict_
                     bb = sd[r][w];
                     jj = sj[r][w];
                 }
-            const uint32_t row = list ? list[g * kXR + r] : g * kXR + r;
-            nn[row] = (jj == 0xffffffffu) ? 0u : jj; /* nothing compared below +inf: the reference keeps 0 */
+            const size_t slot = (size_t)(g * kXR + r) * kXS + blockIdx.y;
+            pd[slot] = bb;
+            pj[slot] = jj;
         }
+    }
+}
+__global__ void nn_exact_merge_kernel(uint32_t na, const uint32_t *__restrict__ list,
+                                      const uint32_t *__restrict__ list_count, const double *__restrict__ pd,
+                                      const uint32_t *__restrict__ pj, uint32_t *__restrict__ nn) {
+    const uint32_t total = list ? *list_count : na;
+    for (uint32_t it = blockIdx.x * blockDim.x + threadIdx.x; it < total; it += gridDim.x * blockDim.x) {
+        double bb = INFINITY;
+        uint32_t jj = 0xffffffffu;
+        for (int y = 0; y < kXS; ++y) { /* ascending column ranges: strict < keeps the lowest index */
+            const double d = pd[(size_t)it * kXS + y];
+            if (d < bb) {
+                bb = d;
+                jj = pj[(size_t)it * kXS + y];
+            }
+        }
+        nn[list ? list[it] : it] = (jj == 0xffffffffu) ? 0u : jj; /* nothing below +inf: the reference keeps 0 */
     }
 }
 
@@ -412,12 +434,27 @@ struct MatchScratch { /* layout of the small device block */
     uint32_t total;
 };
 
-static int nn_direction(m3d_ctx *ctx, const FeatDev &A, const FeatDev &B, int dim, int KP, int path,
-                        const uint32_t *d_maxnorm_B, uint32_t *d_nn, uint32_t *d_amb, uint32_t *d_amb_count) {
+static int launch_exact(m3d_ctx *ctx, const FeatDev &A, const FeatDev &B, int dim, const uint32_t *d_list,
+                        const uint32_t *d_count, uint32_t *d_nn) {
     const size_t xsmem = sizeof(double) * (size_t)dim * kXR;
     if (xsmem > 200 * 1024) return ctx->fail(M3D_ERR_INVALID_ARG, "descriptor dimension %d too large", dim);
     if (xsmem > 48 * 1024)
         M3D_CUDA(ctx, cudaFuncSetAttribute(nn_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xsmem));
+    const size_t slots = ((size_t)A.count + kXR) * kXS;
+    M3D_CUDA(ctx, ctx->d_part.reserve(slots * (sizeof(double) + sizeof(uint32_t)) + 64));
+    double *pd = ctx->d_part.as<double>();
+    uint32_t *pj = reinterpret_cast<uint32_t *>(pd + slots);
+    const int gx = std::max(1, ctx->sm_count * 4 / kXS);
+    nn_exact_kernel<<<dim3(gx, kXS), 256, xsmem, ctx->stream>>>(A.f64, B.f64, A.count, B.count, dim, d_list, d_count,
+                                                               pd, pj);
+    M3D_LAUNCHED(ctx);
+    nn_exact_merge_kernel<<<ctx->sm_count, 256, 0, ctx->stream>>>(A.count, d_list, d_count, pd, pj, d_nn);
+    M3D_LAUNCHED(ctx);
+    return M3D_OK;
+}
+
+static int nn_direction(m3d_ctx *ctx, const FeatDev &A, const FeatDev &B, int dim, int KP, int path,
+                        const uint32_t *d_maxnorm_B, uint32_t *d_nn, uint32_t *d_amb, uint32_t *d_amb_count) {
     if (path == 2) {
         tc::TcArgs ta{};
         ta.Aq = A.tq;
@@ -430,26 +467,20 @@ static int nn_direction(m3d_ctx *ctx, const FeatDev &A, const FeatDev &B, int di
         ta.nn = d_nn;
         ta.amb_list = d_amb;
         ta.amb_count = d_amb_count;
-        const size_t smem = (size_t)(1 + tc::kBStages) * tc::kRows * ta.KPr * 2 + 128;
+        const size_t smem = (size_t)(tc::kRB + tc::kBStages) * tc::kRows * ta.KPr * 2 + 128;
         M3D_CUDA(ctx, cudaFuncSetAttribute(tc::nn_top2_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        tc::nn_top2_tc_kernel<<<A.ntiles, 192, smem, ctx->stream>>>(ta);
+        tc::nn_top2_tc_kernel<<<(A.ntiles + tc::kRB - 1) / tc::kRB, 192, smem, ctx->stream>>>(ta);
         M3D_LAUNCHED(ctx);
-        nn_exact_kernel<<<ctx->sm_count * 4, 256, sizeof(double) * dim * kXR, ctx->stream>>>(
-            A.f64, B.f64, A.count, B.count, dim, d_amb, d_amb_count, d_nn);
-        M3D_LAUNCHED(ctx);
+        if (int rc = launch_exact(ctx, A, B, dim, d_amb, d_amb_count, d_nn)) return rc;
     } else if (path == 1) {
         const size_t smem = (size_t)3 * (KP + 1) * kMT * sizeof(float) + 3 * sizeof(uint64_t);
         M3D_CUDA(ctx, cudaFuncSetAttribute(nn_top2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         nn_top2_kernel<<<A.ntiles, 256, smem, ctx->stream>>>(A.tiles, B.tiles, A.count, B.count, KP, d_maxnorm_B,
                                                             d_nn, d_amb, d_amb_count);
         M3D_LAUNCHED(ctx);
-        nn_exact_kernel<<<ctx->sm_count * 4, 256, sizeof(double) * dim * kXR, ctx->stream>>>(
-            A.f64, B.f64, A.count, B.count, dim, d_amb, d_amb_count, d_nn);
-        M3D_LAUNCHED(ctx);
+        if (int rc = launch_exact(ctx, A, B, dim, d_amb, d_amb_count, d_nn)) return rc;
     } else {
-        nn_exact_kernel<<<ctx->sm_count * 4, 256, sizeof(double) * dim * kXR, ctx->stream>>>(
-            A.f64, B.f64, A.count, B.count, dim, nullptr, nullptr, d_nn);
-        M3D_LAUNCHED(ctx);
+        if (int rc = launch_exact(ctx, A, B, dim, nullptr, nullptr, d_nn)) return rc;
     }
     return M3D_OK;
 }
@@ -475,9 +506,10 @@ static int match_impl(m3d_ctx *ctx, const double *src, size_t ns, const double *
     const size_t fa = sizeof(double) * (size_t)dim * ns, fb = sizeof(double) * (size_t)dim * nd;
     const int KPr = tc::kprime(dim);
     /* tensor-core path: per set one query-form and one database-form tile array (bf16) */
-    const size_t ta = path == 2 ? (size_t)2 * A.ntiles * tc::kRows * KPr * 2
+    const uint32_t at = (A.ntiles + tc::kRB - 1) / tc::kRB * tc::kRB, bt = (B.ntiles + tc::kRB - 1) / tc::kRB * tc::kRB;
+    const size_t ta = path == 2 ? (size_t)2 * at * tc::kRows * KPr * 2
                                 : (path == 1 ? sizeof(float) * (size_t)A.ntiles * (KP + 1) * kMT : 16);
-    const size_t tb = path == 2 ? (size_t)2 * B.ntiles * tc::kRows * KPr * 2
+    const size_t tb = path == 2 ? (size_t)2 * bt * tc::kRows * KPr * 2
                                 : (path == 1 ? sizeof(float) * (size_t)B.ntiles * (KP + 1) * kMT : 16);
     M3D_CUDA(ctx, ctx->d_tmp5.reserve(sizeof(float) * (ns + nd) + 64));
     M3D_CUDA(ctx, ctx->d_tmp0.reserve(fa));
@@ -492,9 +524,9 @@ static int match_impl(m3d_ctx *ctx, const double *src, size_t ns, const double *
     A.tiles = ctx->d_tmp2.as<float>();
     B.tiles = ctx->d_tmp3.as<float>();
     A.tq = ctx->d_tmp2.as<__nv_bfloat16>();
-    A.td = A.tq + (size_t)A.ntiles * tc::kRows * KPr;
+    A.td = A.tq + (size_t)at * tc::kRows * KPr;
     B.tq = ctx->d_tmp3.as<__nv_bfloat16>();
-    B.td = B.tq + (size_t)B.ntiles * tc::kRows * KPr;
+    B.td = B.tq + (size_t)bt * tc::kRows * KPr;
     A.norms = ctx->d_tmp5.as<float>();
     B.norms = A.norms + ns;
     uint32_t *d_nn01 = ctx->d_tmp4.as<uint32_t>();
@@ -517,14 +549,14 @@ static int match_impl(m3d_ctx *ctx, const double *src, size_t ns, const double *
         feat_center_kernel<<<1, 128, 0, ctx->stream>>>(sc->mn, sc->mx, dim, sc->center);
         M3D_LAUNCHED(ctx);
         if (path == 2) {
-            tc::feat_split_kernel<<<A.ntiles, tc::kRows, 0, ctx->stream>>>(A.f64, A.count, dim, KPr, sc->center, 0, A.tq,
+            tc::feat_split_kernel<<<at, tc::kRows, 0, ctx->stream>>>(A.f64, A.count, dim, KPr, sc->center, 0, A.tq,
                                                                         A.norms, &sc->maxnorm[0]);
             M3D_LAUNCHED(ctx);
             tc::feat_split_kernel<<<B.ntiles, tc::kRows, 0, ctx->stream>>>(B.f64, B.count, dim, KPr, sc->center, 1, B.td,
                                                                         B.norms, &sc->maxnorm[1]);
             M3D_LAUNCHED(ctx);
             if (both_directions) {
-                tc::feat_split_kernel<<<B.ntiles, tc::kRows, 0, ctx->stream>>>(B.f64, B.count, dim, KPr, sc->center, 0,
+                tc::feat_split_kernel<<<bt, tc::kRows, 0, ctx->stream>>>(B.f64, B.count, dim, KPr, sc->center, 0,
                                                                             B.tq, B.norms, &sc->maxnorm[1]);
                 M3D_LAUNCHED(ctx);
                 tc::feat_split_kernel<<<A.ntiles, tc::kRows, 0, ctx->stream>>>(A.f64, A.count, dim, KPr, sc->center, 1,

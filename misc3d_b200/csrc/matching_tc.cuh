@@ -31,8 +31,9 @@ namespace tc {
 
 constexpr int kRows = 128;          /* rows of a tile (UMMA M and N)            */
 constexpr int kChunkBytes = 2048;   /* one 8-wide K chunk of 128 rows           */
-constexpr int kBStages = 3;         /* database-tile ring depth                  */
-constexpr int kMaxKPrime = 208;     /* (1 + kBStages) tiles of 128 x K' bf16 must fit in shared memory */
+constexpr int kRB = 2;              /* query row blocks per CTA                  */
+constexpr int kBStages = 2;         /* database-tile ring depth                  */
+constexpr int kMaxKPrime = 208;     /* (kRB + kBStages) tiles of 128 x K' bf16 must fit in shared memory */
 
 __host__ __device__ inline int kprime(int dim) { return ((6 * dim + 3 + 15) / 16) * 16; }
 
@@ -185,12 +186,44 @@ struct TcArgs {
     uint32_t *nn, *amb_list, *amb_count;
 };
 
+/* one tile of the top-2 scan: 128 fp32 keys of this thread's row (4 x 32 TMEM columns) */
+__device__ __forceinline__ void scan_tile(const float (&v)[4][32], uint32_t jbase, uint32_t ncol, float &m1, float &m2,
+                                          uint32_t &i1) {
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        const uint32_t c0 = 32u * g;
+        /* cheap screen: min of the 32 values (FMNMX3 tree); the running (best, second best) changes
+         * O(log n) times per row, so the update below is the rare path */
+        float lo = fminf(fminf(v[g][0], v[g][1]), v[g][2]);
+#pragma unroll
+        for (int i = 3; i + 1 < 32; i += 2) lo = fminf(fminf(lo, v[g][i]), v[g][i + 1]);
+        lo = fminf(lo, v[g][31]);
+        if (c0 + 32 <= ncol && !(lo < m2)) continue;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            const float d = v[g][i];
+            if (c0 + i < ncol && d < m2) {
+                if (d < m1) {
+                    m2 = m1;
+                    m1 = d;
+                    i1 = jbase + c0 + i;
+                } else {
+                    m2 = d;
+                }
+            }
+        }
+    }
+}
+
+/* One CTA = kRB query row blocks (2 x 128 rows) x all database tiles: every database tile fetched
+ * from L2 feeds 2 x 13 MMAs, which halves the L2 -> SM operand traffic (the limiter with one row
+ * block per CTA).  TMEM: (2 buffers) x (kRB row blocks) x 128 columns = all 512 columns. */
 __global__ void __launch_bounds__(192, 1) nn_top2_tc_kernel(const TcArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const uint32_t tile_bytes = (uint32_t)kRows * a.KPr * 2;
     unsigned char *As = smem_raw;
-    unsigned char *Bs = smem_raw + tile_bytes;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + (1 + kBStages) * (size_t)tile_bytes);
+    unsigned char *Bs = smem_raw + kRB * (size_t)tile_bytes;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + (kRB + kBStages) * (size_t)tile_bytes);
     uint64_t *a_full = bars, *b_full = bars + 1, *b_empty = b_full + kBStages, *t_full = b_empty + kBStages,
              *t_empty = t_full + 2;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(t_empty + 2);
@@ -211,9 +244,9 @@ __global__ void __launch_bounds__(192, 1) nn_top2_tc_kernel(const TcArgs a) {
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 1) { /* 256 TMEM columns: two 128 x 128 fp32 accumulators */
+    if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                     "r"(256)
+                     "r"(512)
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -223,8 +256,8 @@ __global__ void __launch_bounds__(192, 1) nn_top2_tc_kernel(const TcArgs a) {
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        if (lane == 0) { /* ---------------- TMA producer */
-            tma_load_1d(As, a.Aq + (size_t)blockIdx.x * kRows * a.KPr, tile_bytes, a_full);
+        if (lane == 0) { /* ---------------- TMA producer (the query tile array is padded to a multiple of kRB tiles) */
+            tma_load_1d(As, a.Aq + (size_t)blockIdx.x * kRB * kRows * a.KPr, kRB * tile_bytes, a_full);
             for (uint32_t t = 0; t < ntb; ++t) {
                 const int st = t % kBStages;
                 mbar_wait(&b_empty[st], ((t / kBStages) & 1) ^ 1);
@@ -236,78 +269,72 @@ __global__ void __launch_bounds__(192, 1) nn_top2_tc_kernel(const TcArgs a) {
             const uint32_t idesc = umma_idesc(128, 128);
             mbar_wait(a_full, 0);
             for (uint32_t t = 0; t < ntb; ++t) {
-                const int st = t % kBStages, acc = t & 1;
+                const int st = t % kBStages, buf = t & 1;
                 mbar_wait(&b_full[st], (t / kBStages) & 1);
-                mbar_wait(&t_empty[acc], ((t >> 1) & 1) ^ 1);
+                mbar_wait(&t_empty[buf], ((t >> 1) & 1) ^ 1);
                 tc_fence_after();
-                const uint32_t a0 = smem_u32(As), b0 = smem_u32(Bs + (size_t)st * tile_bytes);
-                for (int ks = 0; ks < nk; ++ks)
-                    umma_bf16(tmem_base + (uint32_t)acc * 128u, umma_desc(a0 + ks * 2 * kChunkBytes),
-                              umma_desc(b0 + ks * 2 * kChunkBytes), idesc, ks > 0 ? 1u : 0u);
+                const uint32_t b0 = smem_u32(Bs + (size_t)st * tile_bytes);
+#pragma unroll
+                for (int rb = 0; rb < kRB; ++rb) {
+                    const uint32_t a0 = smem_u32(As + (size_t)rb * tile_bytes);
+                    const uint32_t d0 = tmem_base + (uint32_t)(buf * kRB + rb) * 128u;
+                    for (int ks = 0; ks < nk; ++ks)
+                        umma_bf16(d0, umma_desc(a0 + ks * 2 * kChunkBytes), umma_desc(b0 + ks * 2 * kChunkBytes), idesc,
+                                  ks > 0 ? 1u : 0u);
+                }
                 umma_commit(&b_empty[st]); /* smem slot reusable once these MMAs have read it */
-                umma_commit(&t_full[acc]); /* accumulator ready for the epilogue             */
+                umma_commit(&t_full[buf]); /* both accumulators ready for the epilogue       */
             }
         }
-    } else { /* ---------------- epilogue warps 2..5: TMEM lane quarter = warp % 4 */
+    } else { /* ---------------- epilogue warps 2..5: TMEM lane quarter = warp % 4; one row per row block per thread */
         const uint32_t q = (uint32_t)warp & 3u;
-        const uint32_t row = blockIdx.x * kRows + q * 32 + lane;
-        float m1 = INFINITY, m2 = INFINITY;
-        uint32_t i1 = 0;
+        float m1[kRB], m2[kRB];
+        uint32_t i1[kRB];
+#pragma unroll
+        for (int rb = 0; rb < kRB; ++rb) {
+            m1[rb] = INFINITY;
+            m2[rb] = INFINITY;
+            i1[rb] = 0;
+        }
         for (uint32_t t = 0; t < ntb; ++t) {
-            const int st = t & 1; /* accumulator buffer */
-            mbar_wait(&t_full[st], (t >> 1) & 1);
+            const int buf = t & 1;
+            mbar_wait(&t_full[buf], (t >> 1) & 1);
             tc_fence_after();
             const uint32_t jbase = t * kRows;
             const uint32_t ncol = min((uint32_t)kRows, a.nb - jbase);
-            /* all four 32-column loads are in flight before the single wait */
-            float v[4][32];
-            const uint32_t tbase = tmem_base + ((q * 32u) << 16) + (uint32_t)st * 128u;
 #pragma unroll
-            for (int g = 0; g < 4; ++g) tmem_ld32(tbase + 32u * g, v[g]);
-            tmem_ld_wait();
-            /* the accumulator buffer is free again as soon as the values sit in registers */
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&t_empty[st]);
+            for (int rb = 0; rb < kRB; ++rb) {
+                float v[4][32];
+                const uint32_t tbase = tmem_base + ((q * 32u) << 16) + (uint32_t)(buf * kRB + rb) * 128u;
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-                const uint32_t c0 = 32u * g;
-                /* cheap screen: min of the 32 values (FMNMX3 tree); the running (best, second best)
-                 * changes O(log n) times per row, so the update below is the rare path */
-                float lo = fminf(fminf(v[g][0], v[g][1]), v[g][2]);
-#pragma unroll
-                for (int i = 3; i + 1 < 32; i += 2) lo = fminf(fminf(lo, v[g][i]), v[g][i + 1]);
-                lo = fminf(lo, v[g][31]);
-                if (c0 + 32 <= ncol && !(lo < m2)) continue;
-#pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const float d = v[g][i];
-                    if (c0 + i < ncol && d < m2) {
-                        if (d < m1) {
-                            m2 = m1;
-                            m1 = d;
-                            i1 = jbase + c0 + i;
-                        } else {
-                            m2 = d;
-                        }
-                    }
+                for (int g = 0; g < 4; ++g) tmem_ld32(tbase + 32u * g, v[g]); /* four loads in flight */
+                tmem_ld_wait();
+                if (rb == kRB - 1) { /* the buffer pair is free as soon as the values sit in registers */
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&t_empty[buf]);
                 }
+                scan_tile(v, jbase, ncol, m1[rb], m2[rb], i1[rb]);
             }
         }
-        if (row < a.na) {
-            a.nn[row] = i1;
-            /* error of the bf16x3 GEMM value against the exact distance:
-             * fp32 input rounding + dropped split terms + fp32 accumulation of K' products */
-            const float bnmax = __uint_as_float(*a.maxnorm_bits);
-            const float E = (float)(a.KPr + 64) * 1.1920929e-07f * (a.a_norms[row] + bnmax);
-            if (!(m2 - m1 > 2.5f * E)) a.amb_list[atomicAdd(a.amb_count, 1u)] = row;
+        const float bnmax = __uint_as_float(*a.maxnorm_bits);
+#pragma unroll
+        for (int rb = 0; rb < kRB; ++rb) {
+            const uint32_t row = (blockIdx.x * kRB + rb) * kRows + q * 32 + lane;
+            if (row < a.na) {
+                a.nn[row] = i1[rb];
+                /* error of the bf16x3 GEMM value against the exact distance:
+                 * fp32 input rounding + dropped split terms + fp32 accumulation of K' products */
+                const float E = (float)(a.KPr + 64) * 1.1920929e-07f * (a.a_norms[row] + bnmax);
+                if (!(m2[rb] - m1[rb] > 2.5f * E)) a.amb_list[atomicAdd(a.amb_count, 1u)] = row;
+            }
         }
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
     }
 }
 
