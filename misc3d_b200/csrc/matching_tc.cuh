@@ -26,13 +26,17 @@
 
 #include <cstdint>
 
+#ifndef M3D_TC_EXP
+#define M3D_TC_EXP 0
+#endif
+
 namespace m3d {
 namespace tc {
 
 constexpr int kRows = 128;          /* rows of a tile (UMMA M and N)            */
 constexpr int kChunkBytes = 2048;   /* one 8-wide K chunk of 128 rows           */
-constexpr int kRB = 2;              /* query row blocks per CTA                  */
-constexpr int kBStages = 2;         /* database-tile ring depth                  */
+constexpr int kRB = 1;              /* query row blocks per CTA                  */
+constexpr int kBStages = 3;         /* database-tile ring depth                  */
 constexpr int kMaxKPrime = 208;     /* (kRB + kBStages) tiles of 128 x K' bf16 must fit in shared memory */
 
 __host__ __device__ inline int kprime(int dim) { return ((6 * dim + 3 + 15) / 16) * 16; }
@@ -306,15 +310,27 @@ __global__ void __launch_bounds__(192, 1) nn_top2_tc_kernel(const TcArgs a) {
             for (int rb = 0; rb < kRB; ++rb) {
                 float v[4][32];
                 const uint32_t tbase = tmem_base + ((q * 32u) << 16) + (uint32_t)(buf * kRB + rb) * 128u;
+#if M3D_TC_EXP != 1 /* timing experiment 1: no TMEM loads at all (wrong results) */
 #pragma unroll
                 for (int g = 0; g < 4; ++g) tmem_ld32(tbase + 32u * g, v[g]); /* four loads in flight */
                 tmem_ld_wait();
+#else
+                (void)tbase;
+#pragma unroll
+                for (int g = 0; g < 4; ++g)
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[g][i] = 1e30f;
+#endif
                 if (rb == kRB - 1) { /* the buffer pair is free as soon as the values sit in registers */
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&t_empty[buf]);
                 }
+#if M3D_TC_EXP == 2 /* timing experiment 2: TMEM loads but only a token use of the values */
+                m1[rb] = fminf(m1[rb], v[0][lane & 31] + v[1][0] + v[2][0] + v[3][0]);
+#else
                 scan_tile(v, jbase, ncol, m1[rb], m2[rb], i1[rb]);
+#endif
             }
         }
         const float bnmax = __uint_as_float(*a.maxnorm_bits);
