@@ -341,6 +341,43 @@ __global__ void nn_exact_merge_kernel(uint32_t na, const uint32_t *__restrict__ 
     }
 }
 
+/* exact decision among the GEMM pass's candidates of every ambiguous row (thread = slot): fp64
+ * reference-order distance, lowest value then lowest index.  Rows with more candidates than the
+ * list holds go to the full fp64 re-search (list2). */
+__global__ void __launch_bounds__(128) cand_exact_kernel(const double *__restrict__ A, const double *__restrict__ B,
+                                                         int dim, const uint32_t *__restrict__ amb_list,
+                                                         const uint32_t *__restrict__ amb_count,
+                                                         const uint32_t *__restrict__ cand,
+                                                         const uint32_t *__restrict__ cand_count,
+                                                         uint32_t *__restrict__ nn, uint32_t *__restrict__ list2,
+                                                         uint32_t *__restrict__ list2_count) {
+    const uint32_t n = *amb_count;
+    for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) {
+        const uint32_t row = amb_list[s];
+        const uint32_t c = cand_count[s];
+        if (c == 0 || c > (uint32_t)tc::kCandCap) { /* c == 0 cannot happen for finite data (the best column qualifies) */
+            list2[atomicAdd(list2_count, 1u)] = row;
+            continue;
+        }
+        const double *a = A + (size_t)row * dim;
+        double best = INFINITY;
+        uint32_t bj = 0xffffffffu;
+        for (uint32_t k = 0; k < c; ++k) {
+            const uint32_t j = cand[(size_t)s * tc::kCandCap + k];
+            const double d = l2_groups4(a, B + (size_t)j * dim, dim);
+            if (d < best || (d == best && j < bj)) {
+                best = d;
+                bj = j;
+            }
+        }
+        if (bj == 0xffffffffu) { /* all candidates NaN/inf: let the full search apply the reference's rule */
+            list2[atomicAdd(list2_count, 1u)] = row;
+            continue;
+        }
+        nn[row] = bj;
+    }
+}
+
 /* ---- mutual check (correspondence_matching.cpp:67-78) + stable compaction */
 constexpr int kMB = 256, kMItems = 8;
 __device__ __forceinline__ bool mutual(const uint32_t *nn01, const uint32_t *nn10, uint32_t i, uint32_t nd) {
@@ -468,10 +505,42 @@ static int nn_direction(m3d_ctx *ctx, const FeatDev &A, const FeatDev &B, int di
         ta.amb_list = d_amb;
         ta.amb_count = d_amb_count;
         const size_t smem = (size_t)(tc::kRB + tc::kBStages) * tc::kRows * ta.KPr * 2 + 128;
-        M3D_CUDA(ctx, cudaFuncSetAttribute(tc::nn_top2_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        tc::nn_top2_tc_kernel<<<(A.ntiles + tc::kRB - 1) / tc::kRB, 192, smem, ctx->stream>>>(ta);
+        /* scratch of the candidate refinement */
+        const uint32_t atiles = (A.ntiles + tc::kRB - 1) / tc::kRB * tc::kRB;
+        M3D_CUDA(ctx, ctx->d_models.reserve((size_t)atiles * tc::kRows * ta.KPr * 2));                 /* slot tiles */
+        M3D_CUDA(ctx, ctx->d_queue.reserve(sizeof(uint32_t) * (size_t)A.count * tc::kCandCap + 64));  /* candidates */
+        M3D_CUDA(ctx, ctx->d_counts.reserve(sizeof(float) * 3 * (size_t)A.count + 64));               /* cut, slot_cut, cand_count */
+        M3D_CUDA(ctx, ctx->d_counts_all.reserve(sizeof(uint32_t) * ((size_t)A.count + 4)));           /* list2 + its counter */
+        float *d_cut = ctx->d_counts.as<float>();
+        float *d_slot_cut = d_cut + A.count;
+        uint32_t *d_cand_count = reinterpret_cast<uint32_t *>(d_slot_cut + A.count);
+        uint32_t *d_list2_count = ctx->d_counts_all.as<uint32_t>();
+        uint32_t *d_list2 = d_list2_count + 4;
+        ta.cut = d_cut;
+        M3D_CUDA(ctx, cudaMemsetAsync(d_list2_count, 0, sizeof(uint32_t), ctx->stream));
+        M3D_CUDA(ctx, cudaFuncSetAttribute(tc::nn_top2_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        M3D_CUDA(ctx, cudaFuncSetAttribute(tc::nn_top2_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        tc::nn_top2_tc_kernel<false><<<atiles / tc::kRB, 192, smem, ctx->stream>>>(ta);
         M3D_LAUNCHED(ctx);
-        if (int rc = launch_exact(ctx, A, B, dim, d_amb, d_amb_count, d_nn)) return rc;
+        /* rows too close to call: second GEMM pass over just those rows collecting every column within
+         * the error bound of the best key, then the fp64 reference-order decision among the candidates */
+        tc::gather_slots_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(A.tq, ta.KPr, d_amb, d_amb_count, d_cut,
+                                                                        ctx->d_models.as<__nv_bfloat16>(), d_slot_cut,
+                                                                        d_cand_count, A.count);
+        M3D_LAUNCHED(ctx);
+        tc::TcArgs tb = ta;
+        tb.Aq = ctx->d_models.as<__nv_bfloat16>();
+        tb.slot_count = d_amb_count;
+        tb.slot_cut = d_slot_cut;
+        tb.cand = ctx->d_queue.as<uint32_t>();
+        tb.cand_count = d_cand_count;
+        tb.col_splits = 8;
+        tc::nn_top2_tc_kernel<true><<<dim3(atiles / tc::kRB, tb.col_splits), 192, smem, ctx->stream>>>(tb);
+        M3D_LAUNCHED(ctx);
+        cand_exact_kernel<<<ctx->sm_count * 2, 128, 0, ctx->stream>>>(A.f64, B.f64, dim, d_amb, d_amb_count, tb.cand,
+                                                                     d_cand_count, d_nn, d_list2, d_list2_count);
+        M3D_LAUNCHED(ctx);
+        if (int rc = launch_exact(ctx, A, B, dim, d_list2, d_list2_count, d_nn)) return rc;
     } else if (path == 1) {
         const size_t smem = (size_t)3 * (KP + 1) * kMT * sizeof(float) + 3 * sizeof(uint64_t);
         M3D_CUDA(ctx, cudaFuncSetAttribute(nn_top2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -188,7 +188,15 @@ struct TcArgs {
     int KPr;                 /* padded K'                      */
     const uint32_t *maxnorm_bits;
     uint32_t *nn, *amb_list, *amb_count;
+    float *cut;              /* [na] first pass: best key + 2.5 E of every row (candidate cut-off)      */
+    /* candidate pass (CAND): rows are the compacted ambiguous rows ("slots") */
+    const uint32_t *slot_count; /* number of slots (device)                                            */
+    const float *slot_cut;      /* [slots] cut-off of the slot's row                                   */
+    uint32_t *cand;             /* [slots][kCandCap] database columns with key <= cut                   */
+    uint32_t *cand_count;       /* [slots]                                                              */
+    uint32_t col_splits;        /* gridDim.y: each CTA scans 1/col_splits of the database tiles         */
 };
+constexpr int kCandCap = 32;
 
 /* one tile of the top-2 scan: 128 fp32 keys of this thread's row (4 x 32 TMEM columns) */
 __device__ __forceinline__ void scan_tile(const float (&v)[4][32], uint32_t jbase, uint32_t ncol, float &m1, float &m2,
@@ -219,10 +227,33 @@ __device__ __forceinline__ void scan_tile(const float (&v)[4][32], uint32_t jbas
     }
 }
 
+/* candidate pass: every column whose key is within the cut-off of this row */
+__device__ __forceinline__ void collect_tile(const float (&v)[4][32], uint32_t jbase, uint32_t ncol, float cut,
+                                             uint32_t *cand, uint32_t *cand_count) {
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        const uint32_t c0 = 32u * g;
+        float lo = fminf(fminf(v[g][0], v[g][1]), v[g][2]);
+#pragma unroll
+        for (int i = 3; i + 1 < 32; i += 2) lo = fminf(fminf(lo, v[g][i]), v[g][i + 1]);
+        lo = fminf(lo, v[g][31]);
+        if (!(lo <= cut)) continue;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            if (c0 + i < ncol && v[g][i] <= cut) {
+                const uint32_t k = atomicAdd(cand_count, 1u); /* column ranges of one row run in several CTAs */
+                if (k < (uint32_t)kCandCap) cand[k] = jbase + c0 + i;
+            }
+        }
+    }
+}
+
 /* One CTA = kRB query row blocks (2 x 128 rows) x all database tiles: every database tile fetched
  * from L2 feeds 2 x 13 MMAs, which halves the L2 -> SM operand traffic (the limiter with one row
  * block per CTA).  TMEM: (2 buffers) x (kRB row blocks) x 128 columns = all 512 columns. */
+template <bool CAND>
 __global__ void __launch_bounds__(192, 1) nn_top2_tc_kernel(const TcArgs a) {
+    if (CAND && blockIdx.x * kRB * kRows >= *a.slot_count) return; /* fewer ambiguous rows than the grid was sized for */
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const uint32_t tile_bytes = (uint32_t)kRows * a.KPr * 2;
     unsigned char *As = smem_raw;
@@ -233,7 +264,11 @@ __global__ void __launch_bounds__(192, 1) nn_top2_tc_kernel(const TcArgs a) {
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(t_empty + 2);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const uint32_t ntb = (a.nb + kRows - 1) / kRows;
+    const uint32_t ntb_all = (a.nb + kRows - 1) / kRows;
+    /* database tiles of this CTA: all of them, or one of col_splits contiguous ranges (CAND) */
+    const uint32_t per = CAND ? (ntb_all + a.col_splits - 1) / a.col_splits : ntb_all;
+    const uint32_t tb0 = CAND ? min(ntb_all, blockIdx.y * per) : 0u;
+    const uint32_t ntb = min(ntb_all, tb0 + per) - tb0;
     const int nk = a.KPr / 16;
 
     if (tid == 0) {
@@ -265,7 +300,7 @@ __global__ void __launch_bounds__(192, 1) nn_top2_tc_kernel(const TcArgs a) {
             for (uint32_t t = 0; t < ntb; ++t) {
                 const int st = t % kBStages;
                 mbar_wait(&b_empty[st], ((t / kBStages) & 1) ^ 1);
-                tma_load_1d(Bs + (size_t)st * tile_bytes, a.Bd + (size_t)t * kRows * a.KPr, tile_bytes, &b_full[st]);
+                tma_load_1d(Bs + (size_t)st * tile_bytes, a.Bd + (size_t)(tb0 + t) * kRows * a.KPr, tile_bytes, &b_full[st]);
             }
         }
     } else if (warp == 1) {
@@ -292,19 +327,25 @@ __global__ void __launch_bounds__(192, 1) nn_top2_tc_kernel(const TcArgs a) {
         }
     } else { /* ---------------- epilogue warps 2..5: TMEM lane quarter = warp % 4; one row per row block per thread */
         const uint32_t q = (uint32_t)warp & 3u;
-        float m1[kRB], m2[kRB];
+        float m1[kRB], m2[kRB], cutv[kRB];
         uint32_t i1[kRB];
+        const uint32_t nslots = CAND ? *a.slot_count : 0u;
 #pragma unroll
         for (int rb = 0; rb < kRB; ++rb) {
             m1[rb] = INFINITY;
             m2[rb] = INFINITY;
             i1[rb] = 0;
+            cutv[rb] = -INFINITY;
+            if (CAND) {
+                const uint32_t slot = (blockIdx.x * kRB + rb) * kRows + q * 32 + lane;
+                if (slot < nslots) cutv[rb] = a.slot_cut[slot];
+            }
         }
         for (uint32_t t = 0; t < ntb; ++t) {
             const int buf = t & 1;
             mbar_wait(&t_full[buf], (t >> 1) & 1);
             tc_fence_after();
-            const uint32_t jbase = t * kRows;
+            const uint32_t jbase = (tb0 + t) * kRows;
             const uint32_t ncol = min((uint32_t)kRows, a.nb - jbase);
 #pragma unroll
             for (int rb = 0; rb < kRB; ++rb) {
@@ -326,23 +367,28 @@ __global__ void __launch_bounds__(192, 1) nn_top2_tc_kernel(const TcArgs a) {
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&t_empty[buf]);
                 }
-#if M3D_TC_EXP == 2 /* timing experiment 2: TMEM loads but only a token use of the values */
-                m1[rb] = fminf(m1[rb], v[0][lane & 31] + v[1][0] + v[2][0] + v[3][0]);
-#else
-                scan_tile(v, jbase, ncol, m1[rb], m2[rb], i1[rb]);
-#endif
+                if (CAND) {
+                    const uint32_t slot = (blockIdx.x * kRB + rb) * kRows + q * 32 + lane;
+                    if (slot < nslots) collect_tile(v, jbase, ncol, cutv[rb], a.cand + (size_t)slot * kCandCap,
+                                                    a.cand_count + slot);
+                } else {
+                    scan_tile(v, jbase, ncol, m1[rb], m2[rb], i1[rb]);
+                }
             }
         }
-        const float bnmax = __uint_as_float(*a.maxnorm_bits);
+        if (!CAND) {
+            const float bnmax = __uint_as_float(*a.maxnorm_bits);
 #pragma unroll
-        for (int rb = 0; rb < kRB; ++rb) {
-            const uint32_t row = (blockIdx.x * kRB + rb) * kRows + q * 32 + lane;
-            if (row < a.na) {
-                a.nn[row] = i1[rb];
-                /* error of the bf16x3 GEMM value against the exact distance:
-                 * fp32 input rounding + dropped split terms + fp32 accumulation of K' products */
-                const float E = (float)(a.KPr + 64) * 1.1920929e-07f * (a.a_norms[row] + bnmax);
-                if (!(m2[rb] - m1[rb] > 2.5f * E)) a.amb_list[atomicAdd(a.amb_count, 1u)] = row;
+            for (int rb = 0; rb < kRB; ++rb) {
+                const uint32_t row = (blockIdx.x * kRB + rb) * kRows + q * 32 + lane;
+                if (row < a.na) {
+                    a.nn[row] = i1[rb];
+                    /* |GEMM key - exact key| <= E: fp32 input rounding, dropped split
+                     * terms, and 2 K' truncating fp32 accumulations of partial sums <= 2(|a|^2 + |b|^2) */
+                    const float E = (float)(2 * a.KPr + 64) * 1.1920929e-07f * (a.a_norms[row] + bnmax);
+                    a.cut[row] = m1[rb] + 2.5f * E;
+                    if (!(m2[rb] - m1[rb] > 2.5f * E)) a.amb_list[atomicAdd(a.amb_count, 1u)] = row;
+                }
             }
         }
     }
@@ -351,6 +397,35 @@ __global__ void __launch_bounds__(192, 1) nn_top2_tc_kernel(const TcArgs a) {
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    }
+}
+
+/* compacts the query-form vectors of the ambiguous rows into fresh tiles ("slots") for the
+ * candidate pass; thread = (slot, 8-wide K chunk) */
+__global__ void __launch_bounds__(256) gather_slots_kernel(const __nv_bfloat16 *__restrict__ Aq, int KPr,
+                                                           const uint32_t *__restrict__ amb_list,
+                                                           const uint32_t *__restrict__ amb_count,
+                                                           const float *__restrict__ cut,
+                                                           __nv_bfloat16 *__restrict__ Aq2, float *__restrict__ slot_cut,
+                                                           uint32_t *__restrict__ cand_count, uint32_t max_slots) {
+    const uint32_t n = min(*amb_count, max_slots);
+    const uint32_t npad = (n + kRows - 1) / kRows * kRows;
+    const int KC = KPr / 8;
+    const size_t total = (size_t)npad * KC;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t slot = (uint32_t)(e / KC), kc = (uint32_t)(e % KC);
+        uint4 val = make_uint4(0, 0, 0, 0);
+        if (slot < n) {
+            const uint32_t row = amb_list[slot];
+            val = *reinterpret_cast<const uint4 *>(Aq + (size_t)(row / kRows) * kRows * KPr + (size_t)kc * (kChunkBytes / 2) +
+                                                   (row % kRows) * 8);
+            if (kc == 0) {
+                slot_cut[slot] = cut[row];
+                cand_count[slot] = 0;
+            }
+        }
+        *reinterpret_cast<uint4 *>(Aq2 + (size_t)(slot / kRows) * kRows * KPr + (size_t)kc * (kChunkBytes / 2) +
+                                   (slot % kRows) * 8) = val;
     }
 }
 
