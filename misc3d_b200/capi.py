@@ -226,19 +226,24 @@ class Context:
                             int(flags))
 
     def ransac_fit(self, kind, xyz, normals=None, threshold=0.01, max_iteration=1000, probability=0.9999,
-                   seed=0, flags=0, want_inliers=True):
-        """Host-buffer entry point (m3d_ransac_fit). Returns (ret, model[np], inliers, stats)."""
+                   seed=0, flags=0, want_inliers=True, inl_buf=None):
+        """Host-buffer entry point (m3d_ransac_fit). Returns (ret, model[np], inliers, stats).
+        inl_buf: optional caller-owned uint64 buffer of >= n entries (e.g. pinned) for the inlier indices;
+        the returned index array is then a view into it."""
         xyz = _f64(xyz).reshape(-1, 3)
         nrm = None if normals is None else _f64(normals).reshape(-1, 3)
         n = len(xyz)
         model = np.zeros(8)
-        inl = np.empty(max(n, 1), dtype=np.uint64) if want_inliers else None
+        inl = inl_buf if inl_buf is not None else (np.empty(max(n, 1), dtype=np.uint64) if want_inliers else None)
         n_inl = C.c_size_t(0)
         st = RansacStats()
         p = self._params(threshold, max_iteration, probability, seed, flags)
         rc = self._check(lib().m3d_ransac_fit(self.h, C.c_int(kind), _p(xyz), _p(nrm), C.c_size_t(n), C.byref(p),
                                               _p(model), _p(inl, C.c_size_t), C.byref(n_inl), C.byref(st)))
-        return rc, model[:NPARAM[kind]].copy(), (inl[:n_inl.value].copy() if want_inliers else None), st.as_dict()
+        if inl is None:
+            return rc, model[:NPARAM[kind]].copy(), None, st.as_dict()
+        out = inl[:n_inl.value] if inl_buf is not None else inl[:n_inl.value].copy()
+        return rc, model[:NPARAM[kind]].copy(), out, st.as_dict()
 
     def ransac_fit_cloud(self, kind, cloud, threshold=0.01, max_iteration=1000, probability=0.9999, seed=0,
                          flags=0, want_inliers=True, inl_buf=None):

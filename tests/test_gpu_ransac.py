@@ -208,3 +208,37 @@ def test_full_size_properties_c2(ctx, capi, kind):
         d = np.abs((m[0] * xyz[:, 0] + m[2] * xyz[:, 2]) + (m[1] * xyz[:, 1] + m[3])) / np.sqrt(m[0] ** 2 + m[1] ** 2 + m[2] ** 2)
         np.testing.assert_array_equal(np.nonzero(d < 0.01)[0], inl)
     cloud.free()
+
+
+def test_early_exit_in_a_later_wave(ctx, capi, orc):
+    """20 % inliers: the adaptive limit is ~1.1k iterations, i.e. the skip test fires inside the
+    third GPU wave (256, 1024, 4096, ...) -- stop index and iteration count must still be the
+    sequential loop's"""
+    xyz = synth.make_c1(n=40000, seed=6, inlier_frac=0.2)
+    st, ost = _check_fit(ctx, capi, orc, capi.PLANE, xyz, None, 0.01, 20000, 0.9999, seed=5)
+    assert 256 + 1024 < ost["stop_index"] < 20000 and st["evaluated"] >= ost["stop_index"]
+
+
+def test_cloud_from_device_and_reuse(ctx, capi, orc):
+    """a cloud already resident in HBM (torch tensor) is fitted repeatedly without new uploads"""
+    import torch
+    xyz, nrm = synth.make_c2(n=50000, seed=8)
+    dx = torch.from_numpy(xyz).cuda()
+    dn = torch.from_numpy(nrm).cuda()
+    torch.cuda.synchronize()
+    cloud = ctx.cloud_from_device(dx.data_ptr(), dn.data_ptr(), len(xyz))
+    del dx, dn  # the library copied them
+    for kind in KINDS:
+        for seed in (1, 2):
+            rc, model, inl, st = ctx.ransac_fit_cloud(kind, cloud, 0.01, 400, 0.9999, seed=seed)
+            orc_rc, omodel, oinl, ost = orc.ransac_fit(kind, xyz, nrm if kind == 2 else None, thr=0.01, max_it=400,
+                                                       prob=0.9999, seed=seed)
+            assert rc == orc_rc and np.array_equal(inl, oinl) and st["best_index"] == ost["best_index"]
+    cloud.free()
+
+
+def test_launch_count_and_no_silent_fallback(ctx, capi):
+    xyz = synth.make_c1(n=5000, seed=1)
+    before = ctx.launches
+    ctx.ransac_fit(capi.PLANE, xyz, None, 0.01, 100, 0.9999, 1)
+    assert ctx.launches - before >= 8  # cloud preparation, scoring, resolve, refine passes all ran on the GPU
