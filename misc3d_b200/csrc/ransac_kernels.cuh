@@ -310,6 +310,78 @@ __device__ __forceinline__ float fast_v(const Fast<KIND> &f, const float4 p) {
     return __fsub_rn(fabsf(fast_eval<KIND>(f, p)), f.T);
 }
 
+/* ---- packed fp32x2 form (Blackwell FFMA2 / FADD2): one thread evaluates TWO hypotheses at the
+ * same point with one packed instruction per term.  `fma.rn.f32x2` / `add.rn.f32x2` round each half
+ * exactly like the scalar fmaf / __fadd_rn in fast_eval, in the same order, so the value a lane
+ * computes here is bit-identical to what rescan_warp recomputes with the scalar form.  ptxas folds
+ * the point coordinate into the broadcast operand form (`R.F32`) and the negation into `-R.F32x2`,
+ * so packing costs no extra instruction.  M3D_PACKED=0 keeps the scalar inner loop. */
+#ifndef M3D_PACKED
+#define M3D_PACKED 1
+#endif
+typedef unsigned long long f32x2_t;
+__device__ __forceinline__ f32x2_t pack2(float lo, float hi) {
+    f32x2_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(f32x2_t r, float &lo, float &hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(r));
+}
+__device__ __forceinline__ f32x2_t ffma2(f32x2_t a, f32x2_t b, f32x2_t c) {
+    f32x2_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ f32x2_t fadd2(f32x2_t a, f32x2_t b) {
+    f32x2_t d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ f32x2_t fneg2(f32x2_t a) {
+    float lo, hi;
+    unpack2(a, lo, hi);
+    return pack2(-lo, -hi);
+}
+template <int KIND>
+struct Fast2 {
+    f32x2_t c[KIND == kCylinder ? 8 : 4]; /* {hypothesis 2q, hypothesis 2q+1} */
+};
+template <int KIND>
+__device__ __forceinline__ void pack_fast(const Fast<KIND> &f0, const Fast<KIND> &f1, Fast2<KIND> &g) {
+    constexpr int NC = KIND == kCylinder ? 8 : 4;
+#pragma unroll
+    for (int i = 0; i < NC; ++i) g.c[i] = pack2(f0.c[i], f1.c[i]);
+}
+template <int KIND>
+__device__ __forceinline__ void unpack_fast(const Fast2<KIND> &g, int half, float T, float band, Fast<KIND> &f) {
+    constexpr int NC = KIND == kCylinder ? 8 : 4;
+#pragma unroll
+    for (int i = 0; i < NC; ++i) {
+        float lo, hi;
+        unpack2(g.c[i], lo, hi);
+        f.c[i] = half ? hi : lo;
+    }
+    f.T = T;
+    f.band = band;
+}
+/* t of both hypotheses of the pair; same operation order as fast_eval */
+template <int KIND>
+__device__ __forceinline__ void fast_eval2(const Fast2<KIND> &g, const float4 p, float &t0, float &t1) {
+    const f32x2_t px = pack2(p.x, p.x), py = pack2(p.y, p.y), pz = pack2(p.z, p.z);
+    f32x2_t t;
+    if (KIND == kPlane) {
+        t = ffma2(g.c[0], px, ffma2(g.c[1], py, ffma2(g.c[2], pz, g.c[3])));
+    } else if (KIND == kSphere) {
+        t = ffma2(g.c[0], px, ffma2(g.c[1], py, ffma2(g.c[2], pz, fadd2(pack2(p.w, p.w), g.c[3]))));
+    } else {
+        const f32x2_t a = ffma2(g.c[0], px, ffma2(g.c[1], py, ffma2(g.c[2], pz, fadd2(pack2(p.w, p.w), g.c[3]))));
+        const f32x2_t b = ffma2(g.c[4], px, ffma2(g.c[5], py, ffma2(g.c[6], pz, g.c[7])));
+        t = ffma2(fneg2(b), b, a);
+    }
+    unpack2(t, t0, t1);
+}
+
 /* inner-loop bookkeeping: provisional inlier count (sign bit of v) and min |v|.
  * M3D_EXP selects timing experiments (wrong results!): 1 = no min tracking, 2 = no count,
  * 3 = count through the FMA pipe (IMAD.HI) */
@@ -594,6 +666,29 @@ __global__ void __launch_bounds__(THREADS + 32) score_kernel(const ScoreArgs a) 
         mn[h] = INFINITY;
     }
 
+    /* hypothesis pairs share packed coefficient registers (FFMA2); T and band stay per hypothesis */
+    constexpr bool kPacked = (M3D_PACKED != 0) && (HPT % 2 == 0);
+    constexpr int NP = kPacked ? HPT / 2 : 1;
+    Fast2<KIND> f2[NP];
+    if (kPacked) {
+#pragma unroll
+        for (int q = 0; q < NP; ++q) pack_fast<KIND>(f[2 * q], f[2 * q + 1], f2[q]);
+    }
+    auto eval_point = [&](const float4 p) {
+        if (kPacked) {
+#pragma unroll
+            for (int q = 0; q < NP; ++q) {
+                float t0, t1;
+                fast_eval2<KIND>(f2[q], p, t0, t1);
+                accumulate_v(__fsub_rn(fabsf(t0), f[2 * q].T), clo[2 * q], mn[2 * q]);
+                accumulate_v(__fsub_rn(fabsf(t1), f[2 * q + 1].T), clo[2 * q + 1], mn[2 * q + 1]);
+            }
+        } else {
+#pragma unroll
+            for (int h = 0; h < HPT; ++h) accumulate_v(fast_v<KIND>(f[h], p), clo[h], mn[h]);
+        }
+    };
+
     uint32_t nres = 0;
     for (uint32_t k = 0;; ++k) {
         const int st = k % kStages;
@@ -607,23 +702,9 @@ __global__ void __launch_bounds__(THREADS + 32) score_kernel(const ScoreArgs a) 
             const int cnt = min(kSub, npt - s0);
             if (cnt == kSub) {
 #pragma unroll kUnroll
-                for (int j = 0; j < kSub; ++j) {
-                    const float4 p = sp[s0 + j];
-#pragma unroll
-                    for (int h = 0; h < HPT; ++h) {
-                        const float v = fast_v<KIND>(f[h], p);
-                        accumulate_v(v, clo[h], mn[h]);
-                    }
-                }
+                for (int j = 0; j < kSub; ++j) eval_point(sp[s0 + j]);
             } else {
-                for (int j = 0; j < cnt; ++j) {
-                    const float4 p = sp[s0 + j];
-#pragma unroll
-                    for (int h = 0; h < HPT; ++h) {
-                        const float v = fast_v<KIND>(f[h], p);
-                        accumulate_v(v, clo[h], mn[h]);
-                    }
-                }
+                for (int j = 0; j < cnt; ++j) eval_point(sp[s0 + j]);
             }
             bool any_flag = false;
 #pragma unroll
@@ -633,7 +714,15 @@ __global__ void __launch_bounds__(THREADS + 32) score_kernel(const ScoreArgs a) 
                 for (int h = 0; h < HPT; ++h) {
                     const bool flag = mn[h] < f[h].band;
                     const unsigned need = __ballot_sync(0xffffffffu, flag && row[h] < a.rows);
-                    if (need) rescan_warp<KIND>(a, need, row[h], f[h], sp + s0, base + s0, cnt, nres);
+                    if (need) {
+                        if (kPacked) { /* scalar view of this hypothesis' half of the packed registers */
+                            Fast<KIND> g;
+                            unpack_fast<KIND>(f2[h / 2], h & 1, f[h].T, f[h].band, g);
+                            rescan_warp<KIND>(a, need, row[h], g, sp + s0, base + s0, cnt, nres);
+                        } else {
+                            rescan_warp<KIND>(a, need, row[h], f[h], sp + s0, base + s0, cnt, nres);
+                        }
+                    }
                     if (flag) mn[h] = INFINITY;
                 }
             }
