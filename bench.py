@@ -16,7 +16,8 @@ Printed JSON (one line, rank 0):
             cloud -> H2D, fit, inlier indices -> D2H, all inside the timed region
   roofline  the scoring kernel against the HBM roofline (compulsory bytes 24*N + 64*H per launch,
             SURVEY.md §8d) -- and `roofline_alu`, the roofline that actually binds it
-  cpu_baseline  the oracle's OpenMP restatement of the reference loop on the box's host cores
+  cpu_baseline  the reference's own ransac.h (compiled into oracle/_ref with -O3 -fopenmp) on the box's
+            host cores; the oracle's OpenMP restatement if that library is absent
 """
 import argparse
 import json
@@ -93,28 +94,59 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def cpu_path():
+    """The CPU implementation both CPU legs time.  Preferred: the REFERENCE'S OWN sources (ransac.h's
+    OpenMP loop, mutex-guarded sampler and per-hypothesis SelectByIndex included) compiled into
+    oracle/_ref/libm3d_ref_omp.so with the reference's flags (-O3 -fopenmp; Eigen/Open3D stood in by
+    oracle/shim/) -> kind "reference".  Fallback when that library did not travel: the oracle's OpenMP
+    restatement of the same loop -> kind "port".  Returns (kind, cores, fit(kind, xyz, nrm, h, seed), what)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import refc
+    if refc.available(omp=True):
+        cores = refc.omp_threads()
+
+        def fit(kind, xyz, nrm, h, seed):
+            refc.ransac_fit(kind, xyz, nrm if kind == 2 else None, THR, h, 1.0, seed, omp=True)
+        return "reference", cores, fit, ("the reference's own ransac.h compiled with -O3 -fopenmp (oracle/_ref; "
+                                         "Eigen/Open3D stand-ins), RANSAC<>::FitModel incl. RefineModel")
+    import orc
+    orc.build()
+    cores = orc.omp_threads()
+
+    def fit(kind, xyz, nrm, h, seed):
+        orc.ransac_fit(kind, xyz, nrm if kind == 2 else None, thr=THR, max_it=h, prob=1.0, seed=seed, omp=True,
+                       faithful=True)
+    return "port", cores, fit, ("oracle OpenMP restatement of ransac.h:571-614 incl. the per-hypothesis O(N) "
+                                "SelectByIndex pass")
+
+
+def calibrate(fit, xyz, cores, seconds_per_step):
+    """hypotheses per primitive such that one plane+sphere+cylinder step is about `seconds_per_step`
+    (two-point: a call also has O(N) fixed costs -- cloud copy, RefineModel -- that do not scale with H)"""
+    ts = []
+    for h in (cores, 5 * cores):
+        t0 = time.perf_counter()
+        fit(0, xyz, None, h, 1)
+        ts.append(time.perf_counter() - t0)
+    per_hyp = max((ts[1] - ts[0]) / (4 * cores), 1e-6)
+    # plane is the cheapest of the three primitives: sphere + cylinder cost about 4x a plane hypothesis
+    h = (seconds_per_step - 3 * ts[0]) / (5.0 * per_hyp)
+    return int(min(H_PER_PRIM, max(cores, round(h / cores) * cores)))
+
+
 def reference_arm(args, rank, world):
-    """The reference's own CPU algorithm (OpenMP loop of ransac.h:571-614, restated in oracle/) on
-    the host cores: each step = a bounded sample of the C2 workload (H_cpu hypotheses per primitive
-    on the full 1M-point cloud, including the per-hypothesis O(N) SelectByIndex pass)."""
+    """The reference's own CPU implementation of the path on the host cores (see cpu_path): each step =
+    a bounded sample of the C2 workload (H_cpu hypotheses per primitive on the full 1M-point cloud)."""
     if rank != 0:
         return
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import orc
     from misc3d_b200 import synth
-    orc.build()
+    kind_name, cores, fit, what = cpu_path()
     xyz, nrm = synth.make_c2(N_POINTS, SEED)
-    cores = orc.omp_threads()
-    # calibrate the sample so one step is a few seconds of CPU work
-    t0 = time.perf_counter()
-    orc.ransac_fit(orc.PLANE, xyz, None, thr=THR, max_it=cores, prob=1.0, seed=1, omp=True, faithful=True)
-    per_hyp = (time.perf_counter() - t0) / cores
-    h_cpu = int(min(H_PER_PRIM, max(cores, round(1.5 / max(per_hyp, 1e-6) / cores) * cores)))
+    h_cpu = calibrate(fit, xyz, cores, 4.5)
 
     def step(seed):
         for kind in KINDS:
-            orc.ransac_fit(kind, xyz, nrm if kind == 2 else None, thr=THR, max_it=h_cpu, prob=1.0, seed=seed,
-                           omp=True, faithful=True)
+            fit(kind, xyz, nrm, h_cpu, seed)
 
     for w in range(args.warmup):
         step(100 + w)
@@ -123,8 +155,8 @@ def reference_arm(args, rank, world):
         step(200 + s)
     dt = time.perf_counter() - t0
     value = 3 * h_cpu * args.steps / dt
-    sample = (f"{h_cpu} hypotheses per primitive per step (of {H_PER_PRIM}) on the full {N_POINTS}-point cloud, "
-              f"OpenMP loop incl. the per-hypothesis O(N) SelectByIndex pass, {cores} threads")
+    sample = (f"{h_cpu} hypotheses per primitive per step (of {H_PER_PRIM}) on the full {N_POINTS}-point cloud; "
+              f"{what}; {cores} threads")
     print(json.dumps({
         "impl": "reference", "metric": "ransac_hypotheses_per_sec", "value": value, "unit": "hypotheses/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
@@ -132,34 +164,31 @@ def reference_arm(args, rank, world):
         "config": {"workload": "C2: fit_plane+fit_sphere+fit_cylinder, 1M-point cloud, 10k hypotheses each "
                                "(bounded sample per step)", "n_points": N_POINTS, "threshold": THR,
                    "probability": 1.0, "hypotheses_per_primitive_per_step": h_cpu},
-        "cpu_baseline": {"value": value, "unit": "hypotheses/s", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "hypotheses/s", "cores": cores, "kind": kind_name, "sample": sample},
         "e2e": {"value": value, "unit": "hypotheses/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "point_hypotheses_per_sec": value * N_POINTS,
     }))
 
 
 def cpu_baseline(xyz, nrm, budget_s=12.0):
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import orc
-    orc.build()
-    cores = orc.omp_threads()
+    kind_name, cores, fit, what = cpu_path()
+    h_cpu = calibrate(fit, xyz, cores, budget_s)
     t0 = time.perf_counter()
-    orc.ransac_fit(orc.PLANE, xyz, None, thr=THR, max_it=cores, prob=1.0, seed=1, omp=True, faithful=True)
-    per_hyp = (time.perf_counter() - t0) / cores
-    h_cpu = int(min(H_PER_PRIM, max(cores, round(budget_s / 3 / max(per_hyp, 1e-6) / cores) * cores)))
-    res = {}
-    for faithful in (True, False):
+    for kind in KINDS:
+        fit(kind, xyz, nrm, h_cpu, 3)
+    value = 3 * h_cpu / (time.perf_counter() - t0)
+    out = {"value": value, "unit": "hypotheses/s", "cores": cores, "kind": kind_name,
+           "sample": f"{h_cpu} of {H_PER_PRIM} hypotheses per primitive on the full {N_POINTS}-point cloud; {what}"}
+    if kind_name == "reference":   # the oracle port beside it, for continuity with earlier runs
+        import orc
+        orc.build()
         t0 = time.perf_counter()
         for kind in KINDS:
             orc.ransac_fit(kind, xyz, nrm if kind == 2 else None, thr=THR, max_it=h_cpu, prob=1.0, seed=3, omp=True,
-                           faithful=faithful)
-        res[faithful] = 3 * h_cpu / (time.perf_counter() - t0)
-        if not faithful:
-            break
-    return {"value": res[True], "unit": "hypotheses/s", "cores": cores, "kind": "port",
-            "sample": f"{h_cpu} of {H_PER_PRIM} hypotheses per primitive on the full {N_POINTS}-point cloud; oracle "
-                      f"OpenMP loop (ransac.h:571-614) incl. the per-hypothesis O(N) SelectByIndex pass",
-            "lean_value": res.get(False), "lean_note": "same without the SelectByIndex mask pass"}
+                           faithful=True)
+        out["port_value"] = 3 * h_cpu / (time.perf_counter() - t0)
+        out["port_note"] = "oracle OpenMP restatement of the same loop (what earlier runs reported)"
+    return out
 
 
 def main():

@@ -1,8 +1,10 @@
 /*
  * m3d_oracle.cpp -- CPU oracle for the Misc3D RANSAC / registration hot path.
  *
- * TEST INFRASTRUCTURE ONLY (see m3d_oracle.h).  PARITY UNPINNED: the reference
- * holds no golden vectors for this path and cannot be built here; every
+ * TEST INFRASTRUCTURE ONLY (see m3d_oracle.h).  Parity: the RANSAC fit,
+ * segmentation and matching functions are PINNED bit for bit against the
+ * reference's own sources compiled into oracle/_ref (tests/test_reference_pin.py);
+ * the Open3D-defined registration part is UNPINNED (see m3d_oracle.h).  Every
  * function below cites the reference lines (relative to /root/reference) it
  * restates.  No code is copied: Eigen/Open3D expressions are re-expressed as
  * explicit scalar IEEE-754 operations in the evaluation order documented in

@@ -7,12 +7,20 @@
  * reference legs may load it.  The product (libm3d_b200.so) never links,
  * includes or calls anything in this directory.
  *
- * PARITY UNPINNED: the reference ships no tests / golden vectors for this
- * path and cannot be compiled here (needs Open3D + Eigen,
- * absent, no network).  The oracle follows the reference source line by line
- * (citations in m3d_oracle.cpp); arithmetic that the reference delegates to
- * Eigen / Open3D v0.15.1 / nanoflann is restated from their published
- * algorithms.
+ * PARITY STATUS.  The reference ships no tests / golden vectors for this path
+ *  and its normal build needs Open3D + Eigen (absent, no network).
+ *   PINNED against outputs of the reference itself run here: ransac.h
+ *   (sampler, estimators, FitModel loop, RefineModel), iterative_plane_
+ *   segmentation.cpp and correspondence_matching.cpp are compiled UNMODIFIED
+ *   from /root/reference into oracle/_ref (Makefile target `_ref`, Eigen/Open3D
+ *   stood in by oracle/shim/, seed injected) and tests/test_reference_pin.py
+ *   requires this oracle to reproduce them bit for bit.  The stand-ins use the
+ *   Eigen evaluation orders of SURVEY.md Appendix D, so what is pinned is the
+ *   reference's control flow and formulas, not Eigen's instruction selection.
+ *   UNPINNED: orc_ransac_registration / orc_umeyama -- that arithmetic is
+ *   Open3D v0.15.1's RegistrationRANSACBasedOnCorrespondence + Eigen::umeyama,
+ *   not under /root/reference; restated from the published algorithms
+ *    and cross-checked with numpy only.
  */
 #ifndef M3D_ORACLE_H_
 #define M3D_ORACLE_H_

@@ -2,7 +2,8 @@
 
 TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and
 bench.py's cpu_baseline / --impl reference legs.  Never imported by the product
-package (misc3d_b200).  PARITY UNPINNED -- see oracle/m3d_oracle.h.
+package (misc3d_b200).  Parity status (pinned against the compiled reference for the fit /
+segmentation / matching functions, unpinned for the Open3D-defined registration): oracle/m3d_oracle.h.
 """
 import ctypes as C
 import os

@@ -1,6 +1,8 @@
 """CPU tests of the oracle: analytic known answers, independent numpy cross-checks, and the
-committed golden vectors (tests/golden, made by tools/make_golden.py from this oracle -- the
-reference itself ships no tests or fixtures for this path)."""
+committed golden vectors (tests/golden, made by tools/make_golden.py: outputs of the reference's own
+sources compiled into oracle/_ref for the fits, segmentation and matching; the oracle's for the
+Open3D-defined registration -- the reference itself ships no tests or fixtures).
+tests/test_reference_pin.py compares the oracle with the compiled reference directly."""
 import os
 
 import numpy as np
@@ -166,7 +168,10 @@ def test_golden_vectors(orc, name):
         np.testing.assert_array_equal(T, g["T"])
         assert st["best_index"] == int(g["best_index"]) and st["best_count"] == int(g["best_count"])
         return
-    np.testing.assert_array_equal(model, g["model"])
+    if name == "small_sphere":   # golden = the reference's SVD least squares; oracle = normal equations
+        np.testing.assert_allclose(model, g["model"], rtol=1e-9, atol=1e-12)
+    else:
+        np.testing.assert_array_equal(model, g["model"])
     np.testing.assert_array_equal(inl, g["inl"])
     for k in ("best_index", "best_count", "iterations_run", "stop_index"):
         assert st[k] == int(g[k]), k
