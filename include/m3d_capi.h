@@ -109,6 +109,7 @@ typedef struct m3d_ransac_params {
 
 #define M3D_FLAG_EXACT_ONLY 1u /* score with the fp64 reference-order kernel only (slow; debug) */
 #define M3D_FLAG_NO_REFIT 2u   /* skip RefineModel's GeneralFit (model_out = minimal model)     */
+#define M3D_FLAG_DENSE 4u      /* score every point-hypothesis pair (no bounding-sphere culling) */
 
 typedef struct m3d_ransac_stats {
     uint64_t best_index;     /* loop index i of the winning minimal model                      */

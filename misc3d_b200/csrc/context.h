@@ -73,6 +73,11 @@ struct m3d_cloud {
     m3d::DevBuf pts32; /* n float4: centred fp32 x,y,z and |q|^2 of the centred point */
     m3d::DevBuf meta;  /* CloudMeta                                            */
     m3d::CloudMeta h_meta;
+    /* Morton-ordered copy for the culling score kernel (score_cull.cuh), built on first use */
+    mutable m3d::DevBuf blob;  /* tiles x (1024 points + 32 cell spheres + 1 tile sphere) float4 */
+    mutable m3d::DevBuf perm;  /* sorted position -> original point index (u32)                   */
+    mutable m3d::DevBuf keys, hist; /* build scratch                                              */
+    mutable bool sorted = false;
 };
 
 struct m3d_ctx {

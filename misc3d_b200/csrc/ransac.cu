@@ -14,6 +14,7 @@
 
 #include "context.h"
 #include "ransac_kernels.cuh"
+#include "score_cull.cuh"
 #include "scan.h"
 
 using namespace m3d;
@@ -58,6 +59,7 @@ int prepare_cloud(m3d_ctx *ctx, m3d_cloud *c) {
 int cloud_fill(m3d_ctx *ctx, m3d_cloud *c, const double *xyz, const double *nrm, size_t n, cudaMemcpyKind kind) {
     c->ctx = ctx;
     c->n = n;
+    c->sorted = false;
     c->has_normals = nrm != nullptr;
     const size_t bytes = sizeof(double) * 3 * std::max<size_t>(n, 1);
     M3D_CUDA(ctx, c->xyz.reserve(bytes));
@@ -81,6 +83,76 @@ int cloud_create(m3d_ctx *ctx, const double *xyz, const double *nrm, size_t n, c
         return rc;
     }
     *out = c;
+    return M3D_OK;
+}
+
+/* scoring path: M3D_SCORE_PATH=dense keeps every point-hypothesis pair (score_kernel); default
+ * (cull) uses the Morton-ordered copy for clouds of >= kCullMinPoints finite points */
+constexpr size_t kCullMinPoints = 2048;
+bool cull_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("M3D_SCORE_PATH");
+        v = (e && strcmp(e, "dense") == 0) ? 0 : 1;
+    }
+    return v != 0;
+}
+
+/* builds (once per upload) the Morton-ordered tile blob of score_cull.cuh: counting sort over a
+ * 128^3 grid (histogram, 3-kernel scan, scatter) + bounding spheres */
+int ensure_sorted(m3d_ctx *ctx, const m3d_cloud *c) {
+    if (c->sorted) return M3D_OK;
+    if (!cull_enabled() || c->n < kCullMinPoints || c->h_meta.nonfinite) return M3D_OK;
+    const uint32_t n = (uint32_t)c->n;
+    const uint32_t ntiles = (n + kTile - 1) / kTile;
+    constexpr int kScanBlocks = kBins / (kScanBlock * kScanItems);
+    static_assert(kScanBlocks <= kScanBlock, "top-level scan is one block");
+    M3D_CUDA(ctx, c->blob.reserve(sizeof(float4) * (size_t)ntiles * kBlobF4));
+    M3D_CUDA(ctx, c->perm.reserve(sizeof(uint32_t) * (size_t)ntiles * kTile));
+    M3D_CUDA(ctx, c->keys.reserve(sizeof(uint32_t) * (size_t)n));
+    M3D_CUDA(ctx, c->hist.reserve(sizeof(uint32_t) * ((size_t)kBins + kScanBlocks)));
+    uint32_t *hist = c->hist.as<uint32_t>();
+    uint32_t *bsum = hist + kBins;
+    M3D_CUDA(ctx, cudaMemsetAsync(hist, 0, sizeof(uint32_t) * (size_t)kBins, ctx->stream));
+    const int nb = std::max(1, std::min<int>(ctx->sm_count * 8, (int)((n + 255) / 256)));
+    morton_hist_kernel<<<nb, 256, 0, ctx->stream>>>(c->pts32.as<float4>(), n, c->meta.as<CloudMeta>(),
+                                                    c->keys.as<uint32_t>(), hist);
+    M3D_LAUNCHED(ctx);
+    scan_sums_kernel<<<kScanBlocks, kScanBlock, 0, ctx->stream>>>(hist, bsum);
+    M3D_LAUNCHED(ctx);
+    scan_top_kernel<<<1, kScanBlock, 0, ctx->stream>>>(bsum, kScanBlocks);
+    M3D_LAUNCHED(ctx);
+    scan_apply_kernel<<<kScanBlocks, kScanBlock, 0, ctx->stream>>>(hist, bsum);
+    M3D_LAUNCHED(ctx);
+    morton_scatter_kernel<<<nb, 256, 0, ctx->stream>>>(c->pts32.as<float4>(), n, c->keys.as<uint32_t>(), hist,
+                                                       c->blob.as<float4>(), c->perm.as<uint32_t>());
+    M3D_LAUNCHED(ctx);
+    tile_bounds_kernel<<<ntiles, kTile, 0, ctx->stream>>>(c->blob.as<float4>(), n, c->meta.as<CloudMeta>());
+    M3D_LAUNCHED(ctx);
+    c->sorted = true;
+    return M3D_OK;
+}
+
+template <int KIND, int THREADS, int HPT>
+int launch_cull_t(m3d_ctx *ctx, const ScoreArgs &a, uint32_t ntiles) {
+    const size_t smem = (size_t)kStages * kStageF4 * sizeof(float4) + 2 * kStages * sizeof(uint64_t) +
+                        kStages * sizeof(uint32_t) + 16;
+    M3D_CUDA(ctx, cudaFuncSetAttribute(score_cull_kernel<KIND, THREADS, HPT>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const uint32_t hb = (a.rows + THREADS * HPT - 1) / (THREADS * HPT);
+    int per_sm = 0;
+    M3D_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, score_cull_kernel<KIND, THREADS, HPT>,
+                                                                 THREADS + 32, smem));
+    const uint32_t slots = (uint32_t)ctx->sm_count * (uint32_t)std::max(per_sm, 1);
+    uint32_t per_hb = std::max<uint32_t>(1, (slots + hb - 1) / hb);
+    per_hb = std::min(per_hb, ntiles);
+    M3D_CUDA(ctx, ctx->d_tiles.reserve(sizeof(uint32_t) * (size_t)hb));
+    M3D_CUDA(ctx, cudaMemsetAsync(ctx->d_tiles.p, 0, sizeof(uint32_t) * (size_t)hb, ctx->stream));
+    ScoreArgs b = a;
+    b.tile_counter = ctx->d_tiles.as<uint32_t>();
+    dim3 grid(hb, per_hb);
+    score_cull_kernel<KIND, THREADS, HPT><<<grid, THREADS + 32, smem, ctx->stream>>>(b);
+    M3D_LAUNCHED(ctx);
     return M3D_OK;
 }
 
@@ -144,6 +216,21 @@ int launch_score(m3d_ctx *ctx, const m3d_cloud *c, ScoreArgs a, bool exact_only)
     }
     M3D_CUDA(ctx, cudaMemsetAsync(a.queue_count, 0, sizeof(uint32_t), ctx->stream));
     int rc;
+    if (a.blob && cull_enabled()) {
+        switch (score_variant_override()) {
+            case 128 * 16 + 1: rc = launch_cull_t<KIND, 128, 1>(ctx, a, ntiles); break;
+            case 128 * 16 + 2: rc = launch_cull_t<KIND, 128, 2>(ctx, a, ntiles); break;
+            case 256 * 16 + 1: rc = launch_cull_t<KIND, 256, 1>(ctx, a, ntiles); break;
+            case 256 * 16 + 4: rc = launch_cull_t<KIND, 256, 4>(ctx, a, ntiles); break;
+            default:
+                rc = (a.rows >= 2048) ? launch_cull_t<KIND, 256, 2>(ctx, a, ntiles)
+                                      : launch_cull_t<KIND, 128, 1>(ctx, a, ntiles);
+        }
+        if (rc) return rc;
+        resolve_queue_kernel<KIND><<<ctx->sm_count * 2, 256, 0, ctx->stream>>>(a);
+        M3D_LAUNCHED(ctx);
+        return M3D_OK;
+    }
     switch (score_variant_override()) {
         case 128 * 16 + 1: rc = launch_score_t<KIND, 128, 1>(ctx, a, ntiles); break;
         case 128 * 16 + 2: rc = launch_score_t<KIND, 128, 2>(ctx, a, ntiles); break;
@@ -273,6 +360,8 @@ struct CloudView {
     const CloudMeta *meta;
     uint32_t n;
     bool nonfinite;
+    const float4 *blob = nullptr; /* Morton-ordered copy (null: dense scoring only) */
+    const uint32_t *perm = nullptr;
 };
 
 /* one full FitModel on a device-resident cloud.  On return the minimal best model sits in
@@ -365,6 +454,8 @@ int fit_view(m3d_ctx *ctx, int kind, const m3d_cloud *cloud_for_flags, const Clo
         if (my1 > my0) {
             ScoreArgs a{};
             a.pts32 = v.pts32;
+            a.blob = (p.flags & M3D_FLAG_DENSE) ? nullptr : v.blob;
+            a.perm = v.perm;
             a.xyz = v.xyz;
             a.nrm = v.nrm;
             a.meta = v.meta;
@@ -494,6 +585,10 @@ void m3d_cloud_free(m3d_cloud *c) {
     c->nrm.release();
     c->pts32.release();
     c->meta.release();
+    c->blob.release();
+    c->perm.release();
+    c->keys.release();
+    c->hist.release();
     delete c;
 }
 size_t m3d_cloud_size(const m3d_cloud *c) { return c ? c->n : 0; }
@@ -509,6 +604,11 @@ int m3d_ransac_fit_cloud(m3d_ctx *ctx, int kind, const m3d_cloud *cloud, const m
     CloudView v{cloud->xyz.as<double>(), cloud->has_normals ? cloud->nrm.as<double>() : nullptr,
                 cloud->pts32.as<float4>(), cloud->meta.as<CloudMeta>(), (uint32_t)cloud->n,
                 cloud->h_meta.nonfinite != 0};
+    if (int rc = ensure_sorted(ctx, cloud)) return rc;
+    if (cloud->sorted) {
+        v.blob = cloud->blob.as<float4>();
+        v.perm = cloud->perm.as<uint32_t>();
+    }
     FitResult res;
     if (int rc = fit_view(ctx, kind, cloud, v, *p, nullptr, &res)) return rc;
     if (stats) *stats = res.st;
@@ -542,6 +642,16 @@ int m3d_ransac_fit(m3d_ctx *ctx, int kind, const double *xyz, const double *nrm,
     return m3d_ransac_fit_cloud(ctx, kind, ctx->scratch_cloud, p, model_out, inl_out, n_inl, stats);
 }
 
+#ifdef M3D_CULL_STATS
+int m3d_debug_cull_stats(unsigned long long *out) { /* reads and clears the counters of score_cull_kernel */
+    unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out, g_cull_stats, sizeof z);
+    cudaMemcpyToSymbol(g_cull_stats, z, sizeof z);
+    return 0;
+}
+#endif
+
 int m3d_score_samples(m3d_ctx *ctx, int kind, const m3d_cloud *cloud, const uint32_t *samples, size_t rows,
                       double threshold, uint32_t flags, double *models, uint8_t *valid, uint64_t *counts) {
     if (!ctx || !cloud || !samples || !counts) return M3D_ERR_INVALID_ARG;
@@ -562,7 +672,12 @@ int m3d_score_samples(m3d_ctx *ctx, int kind, const m3d_cloud *cloud, const uint
     M3D_CUDA(ctx, cudaMemcpyAsync(ctx->d_samples.p, samples, sizeof(uint32_t) * rows * k, cudaMemcpyHostToDevice, ctx->stream));
     M3D_CUDA(ctx, cudaMemsetAsync(ctx->d_counts.p, 0, sizeof(uint32_t) * rows, ctx->stream));
     M3D_CUDA(ctx, cudaMemsetAsync(&ds->resolves, 0, sizeof(unsigned long long), ctx->stream));
+    if (int rc = ensure_sorted(ctx, cloud)) return rc;
     ScoreArgs a{};
+    if (cloud->sorted && !(flags & M3D_FLAG_DENSE)) {
+        a.blob = cloud->blob.as<float4>();
+        a.perm = cloud->perm.as<uint32_t>();
+    }
     a.pts32 = cloud->pts32.as<float4>();
     a.xyz = cloud->xyz.as<double>();
     a.nrm = cloud->has_normals ? cloud->nrm.as<double>() : nullptr;

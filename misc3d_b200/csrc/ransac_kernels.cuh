@@ -505,6 +505,8 @@ __device__ inline void make_fast(const double *m, bool ok, const CloudMeta &M, d
 }
 
 struct ScoreArgs {
+    const float4 *blob;   /* Morton-ordered tiles + bounding spheres (score_cull.cuh) or null */
+    const uint32_t *perm; /* sorted position -> original index (with blob)                    */
     const float4 *pts32;
     const double *xyz;
     const double *nrm;

@@ -242,3 +242,61 @@ def test_launch_count_and_no_silent_fallback(ctx, capi):
     before = ctx.launches
     ctx.ransac_fit(capi.PLANE, xyz, None, 0.01, 100, 0.9999, 1)
     assert ctx.launches - before >= 8  # cloud preparation, scoring, resolve, refine passes all ran on the GPU
+
+
+# ---------------------------------------------------------------------------------------------------
+# culling score kernel (score_cull.cuh): Morton-ordered copy + bounding spheres.  Counts must equal
+# the dense fp32 kernel's, the fp64 reference-order kernel's and the oracle's on every kind of cloud.
+def _special_clouds():
+    rng = np.random.default_rng(77)
+    n = 9000
+    out = {}
+    xyz, nrm = synth.make_c2(n=50001, seed=5)             # not a multiple of 32 / 1024
+    out["c2_50001"] = (xyz, nrm)
+    out["offset_1e4"] = (xyz[:n] + np.array([1.0e4, -2.0e4, 5.0e3]), nrm[:n])   # far from the origin
+    out["tiny_scale"] = (xyz[:n] * 1e-3, nrm[:n])
+    planar = np.c_[rng.uniform(-1, 1, (n, 2)), np.zeros(n)]          # exactly planar: flat cells
+    out["planar"] = (planar, np.tile([0.0, 0, 1.0], (n, 1)))
+    dup = np.repeat(rng.uniform(-1, 1, (n // 50, 3)), 50, axis=0)     # heavy duplicates: R = 0 cells
+    out["duplicates"] = (dup, rng.normal(size=dup.shape))
+    line = np.outer(np.linspace(-1, 1, n), [1.0, 2.0, -0.5]) + rng.normal(0, 1e-4, (n, 3))
+    out["near_line"] = (line, rng.normal(size=line.shape))
+    clustered = np.r_[rng.normal(0, 1e-3, (n // 2, 3)), rng.normal(0, 1.0, (n // 2, 3)) + 50.0]
+    out["two_scales"] = (clustered, rng.normal(size=clustered.shape))
+    return out
+
+
+@pytest.mark.parametrize("kind", KINDS)
+@pytest.mark.parametrize("name", ["c2_50001", "offset_1e4", "tiny_scale", "planar", "duplicates", "near_line",
+                                  "two_scales"])
+def test_cull_kernel_counts_equal_dense_and_exact(ctx, capi, orc, kind, name):
+    xyz, nrm = _special_clouds()[name]
+    n = len(xyz)
+    thr = 0.01 * (1e-3 if name == "tiny_scale" else 1.0)
+    rows = 2304 if name == "c2_50001" else 600
+    table = capi.sample_table(3 + kind, n, capi.KSAMPLE[kind], rows)
+    cloud = ctx.upload(xyz, nrm)
+    c_cull, m_cull, v_cull = ctx.score_samples(kind, cloud, table, thr)
+    c_dense, m_dense, v_dense = ctx.score_samples(kind, cloud, table, thr, flags=capi.FLAG_DENSE)
+    c_exact, _, _ = ctx.score_samples(kind, cloud, table, thr, flags=capi.FLAG_EXACT_ONLY, want_models=False)
+    np.testing.assert_array_equal(c_cull, c_exact)
+    np.testing.assert_array_equal(c_dense, c_exact)
+    np.testing.assert_array_equal(m_cull.view(np.uint64), m_dense.view(np.uint64))
+    np.testing.assert_array_equal(v_cull, v_dense)
+    # and the oracle, on a subset of the rows (it is a scalar CPU loop)
+    sub = table[:40]
+    ovalid, ocounts, _ = _oracle_rows(orc, kind, xyz, nrm if kind == 2 else None, sub, thr)
+    np.testing.assert_array_equal(c_cull[:40], ocounts)
+    cloud.free()
+
+
+def test_cull_kernel_large_hypothesis_batch(ctx, capi):
+    """C2-like shape at reduced size: 200k points x 6000 hypotheses, cull == dense for all three kinds"""
+    xyz, nrm = synth.make_c2(n=200000, seed=9)
+    cloud = ctx.upload(xyz, nrm)
+    for kind in KINDS:
+        table = capi.sample_table(11 + kind, len(xyz), capi.KSAMPLE[kind], 6000)
+        c_cull, _, _ = ctx.score_samples(kind, cloud, table, 0.01, want_models=False)
+        c_dense, _, _ = ctx.score_samples(kind, cloud, table, 0.01, flags=capi.FLAG_DENSE, want_models=False)
+        np.testing.assert_array_equal(c_cull, c_dense)
+    cloud.free()
