@@ -135,8 +135,7 @@ int ensure_sorted(m3d_ctx *ctx, const m3d_cloud *c) {
 
 template <int KIND, int THREADS, int HPT>
 int launch_cull_t(m3d_ctx *ctx, const ScoreArgs &a, uint32_t ntiles) {
-    const size_t smem = (size_t)kStages * kStageF4 * sizeof(float4) + 2 * kStages * sizeof(uint64_t) +
-                        kStages * sizeof(uint32_t) + 16;
+    const size_t smem = cull_smem_bytes<KIND, THREADS, HPT>();
     M3D_CUDA(ctx, cudaFuncSetAttribute(score_cull_kernel<KIND, THREADS, HPT>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const uint32_t hb = (a.rows + THREADS * HPT - 1) / (THREADS * HPT);

@@ -29,6 +29,10 @@ constexpr int kCellPts = 32;                 /* points per cell = one warp      
 constexpr int kTileCells = kTile / kCellPts; /* 32 cells per tile                                   */
 constexpr int kBlobF4 = kTile + kTileCells + 1; /* float4 per tile in HBM: points, cell spheres, tile sphere */
 constexpr int kStageF4 = kBlobF4 + kCellPts;    /* + one all-NaN dummy cell per smem stage (never TMA-written) */
+#ifndef M3D_CULL_STAGES
+#define M3D_CULL_STAGES 4
+#endif
+constexpr int kCullStages = M3D_CULL_STAGES; /* ring depth: slack between the fastest and the slowest warp of a CTA */
 constexpr int kGridBits = 7;                 /* Morton grid 128^3                                    */
 constexpr uint32_t kBins = 1u << (3 * kGridBits);
 constexpr int kScanBlock = 1024, kScanItems = 2; /* scan: 2048 bins per block                        */
@@ -187,7 +191,8 @@ __global__ void __launch_bounds__(kTile) tile_bounds_kernel(float4 *__restrict__
 /* plane:            a = T + 2*band, b = L >= ||w||            cull iff |t(centre)| >= a + b*R
  * sphere/cylinder:  a = mid, b = error bound of q(centre), c = r_out, d = r_in, with q = squared
  *                   distance to the centre / axis = t + mid;  cull iff the whole sphere lies outside
- *                   radius r_out (sqrt(q - b) - R >= r_out) or inside r_in (sqrt(q + b) + R <= r_in) */
+ *                   radius r_out (sqrt(q - b) - R >= r_out) or inside r_in (sqrt(q + b) + R <= r_in),
+ *                   both tested in squared form (no square root) */
 struct CullP {
     float a, b, c, d;
 };
@@ -246,9 +251,13 @@ __device__ __forceinline__ bool cull_test(const float *c, const CullP &k, const 
             t = fmaf(-b, b, t);
         }
         const float q = t + k.a;
-        const float dlo = sqrtf(fmaxf(q - k.b, 0.f)) * 0.999998f;
-        const float dhi = sqrtf(fmaxf(q + k.b, 0.f)) * 1.000002f;
-        return (dlo - bd.w >= k.c) || (dhi + bd.w <= k.d);
+        /* sqrt(q - b) - R >= r_out  <=>  q - b >= (r_out + R)^2 ;  sqrt(q + b) + R <= r_in  <=>  q + b <= (r_in - R)^2
+         * (r_out + R < 0 only for the always-cull encoding r_out = -inf or an empty cell R = -inf;
+         * a NaN on either side compares false = keep) */
+        const float so = k.c + bd.w, si = k.d - bd.w;
+        const bool outside = (so < 0.f) || (q - k.b >= so * so * 1.000004f);
+        const bool inside = (si > 0.f) && (q + k.b <= si * si * 0.999996f);
+        return outside || inside;
     }
 }
 
@@ -260,29 +269,65 @@ __device__ unsigned long long g_cull_stats[8];
 #endif
 
 /* ------------------------------------------------------------------------------ the hot kernel */
-/* the kernel is latency-bound (dependent shuffle -> test -> ballot -> load -> evaluate chains), so
- * resident warps matter more than registers: at least 2 CTAs of 256+32 threads / 4 of 128+32 per SM */
+/* per-hypothesis parameters as the warp-uniform phases read them: kHypF4 float4 per hypothesis in
+ * shared memory {c[0..3]} {c[4..7]}? {T, band, cull.a, cull.b} {cull.c, cull.d, -, -}? */
+template <int KIND>
+struct HypLayout {
+    static constexpr int kF4 = KIND == kPlane ? 2 : (KIND == kSphere ? 3 : 4);
+};
+template <int KIND>
+__device__ __forceinline__ void load_hyp(const float4 *hp, Fast<KIND> &g, CullP &gk) {
+    constexpr int NC = KIND == kCylinder ? 8 : 4;
+    const float4 q0 = hp[0];
+    g.c[0] = q0.x, g.c[1] = q0.y, g.c[2] = q0.z, g.c[3] = q0.w;
+    if (KIND == kCylinder) {
+        const float4 q1 = hp[1];
+        g.c[NC - 4] = q1.x, g.c[NC - 3] = q1.y, g.c[NC - 2] = q1.z, g.c[NC - 1] = q1.w;
+    }
+    const float4 q2 = hp[NC / 4];
+    g.T = q2.x, g.band = q2.y, gk.a = q2.z, gk.b = q2.w;
+    gk.c = 0.f, gk.d = 0.f;
+    if (KIND != kPlane) {
+        const float4 q3 = hp[NC / 4 + 1];
+        gk.c = q3.x, gk.d = q3.y;
+    }
+}
+constexpr int kListLen = kTileCells + 4; /* per-warp list of surviving cells (+ padding slot), 16 B aligned */
+
+template <int KIND, int THREADS, int HPT>
+constexpr size_t cull_smem_bytes() {
+    return (size_t)kCullStages * kStageF4 * sizeof(float4)                      /* tile ring            */
+           + (size_t)THREADS * HPT * HypLayout<KIND>::kF4 * sizeof(float4)  /* hypothesis parameters */
+           + (size_t)(THREADS / 32) * kListLen * sizeof(uint32_t)           /* surviving-cell lists  */
+           + 2 * kCullStages * sizeof(uint64_t) + kCullStages * sizeof(uint32_t) + 16;
+}
+
+/* the kernel is latency-bound (dependent test -> ballot -> load -> evaluate chains), so resident
+ * warps matter more than registers: at least 2 CTAs of 256+32 threads / 4 of 128+32 per SM */
 template <int KIND, int THREADS, int HPT>
 __global__ void __launch_bounds__(THREADS + 32, (THREADS >= 256 ? 2 : 4)) score_cull_kernel(const ScoreArgs a) {
     constexpr int NC = KIND == kCylinder ? 8 : 4;
+    constexpr int HF4 = HypLayout<KIND>::kF4;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float4 *tiles = reinterpret_cast<float4 *>(smem_raw);
-    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)kStages * kStageF4 * sizeof(float4));
-    uint64_t *empty = full + kStages;
-    volatile uint32_t *tile_id = reinterpret_cast<volatile uint32_t *>(empty + kStages);
+    float4 *hyp = tiles + (size_t)kCullStages * kStageF4;
+    uint32_t *lists = reinterpret_cast<uint32_t *>(hyp + (size_t)THREADS * HPT * HF4);
+    uint64_t *full = reinterpret_cast<uint64_t *>(lists + (THREADS / 32) * kListLen);
+    uint64_t *empty = full + kCullStages;
+    volatile uint32_t *tile_id = reinterpret_cast<volatile uint32_t *>(empty + kCullStages);
 
     const int tid = threadIdx.x;
     const uint32_t ntiles = (a.n + kTile - 1) / kTile;
 
     if (tid == THREADS) {
 #pragma unroll
-        for (int s = 0; s < kStages; ++s) {
+        for (int s = 0; s < kCullStages; ++s) {
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], THREADS / 32);
         }
         mbar_fence_init();
     }
-    if (tid < kStages * kCellPts) { /* the dummy cell of every stage: NaN points count nothing */
+    if (tid < kCullStages * kCellPts) { /* the dummy cell of every stage: NaN points count nothing */
         const float qnan = __int_as_float(0x7fffffff);
         tiles[(size_t)(tid / kCellPts) * kStageF4 + kBlobF4 + (tid % kCellPts)] = make_float4(qnan, qnan, qnan, qnan);
     }
@@ -291,8 +336,8 @@ __global__ void __launch_bounds__(THREADS + 32, (THREADS >= 256 ? 2 : 4)) score_
     if (tid >= THREADS) { /* ---------------- producer: claims tiles, one bulk copy per tile */
         if (tid == THREADS) {
             for (uint32_t k = 0;; ++k) {
-                const int st = k % kStages;
-                if (k >= kStages) mbar_wait(&empty[st], ((k / kStages) - 1) & 1);
+                const int st = k % kCullStages;
+                if (k >= kCullStages) mbar_wait(&empty[st], ((k / kCullStages) - 1) & 1);
                 const uint32_t t = atomicAdd(&a.tile_counter[blockIdx.x], 1u);
                 if (t >= ntiles) {
                     tile_id[st] = kNoTile;
@@ -310,14 +355,13 @@ __global__ void __launch_bounds__(THREADS + 32, (THREADS >= 256 ? 2 : 4)) score_
     /* ---------------- consumers.  Prologue as in score_kernel: gather, MinimalFit (fp64), fp32 form */
     const CloudMeta M = *a.meta;
     const unsigned fullmask = 0xffffffffu;
-    const int lane = tid & 31;
+    const int lane = tid & 31, warp = tid >> 5;
+    uint32_t *wlist = lists + warp * kListLen;
     uint32_t row[HPT];
-    Fast<KIND> f[HPT];
-    CullP ck[HPT];
     uint32_t clo[HPT];
     bool invalid[HPT];
 #pragma unroll
-    for (int h = 0; h < HPT; ++h) {
+    for (int h = 0; h < HPT; ++h) { /* parameters go to shared memory; nothing of them stays in registers */
         row[h] = (blockIdx.x * HPT + h) * THREADS + tid;
         double m[8];
         bool ok = false;
@@ -328,67 +372,83 @@ __global__ void __launch_bounds__(THREADS + 32, (THREADS >= 256 ? 2 : 4)) score_
             for (int i = 0; i < 8; ++i)
                 a.models[(size_t)row[h] * 8 + i] = (ok && i < param_count(KIND)) ? m[i] : 0.0;
         }
-        make_fast<KIND>(m, ok, M, a.thr, f[h]);
-        make_cull<KIND>(f[h], m, M, a.thr, ck[h]);
+        Fast<KIND> f;
+        CullP ck;
+        make_fast<KIND>(m, ok, M, a.thr, f);
+        make_cull<KIND>(f, m, M, a.thr, ck);
         clo[h] = 0;
+        float4 *hp = hyp + (size_t)(h * THREADS + tid) * HF4;
+        hp[0] = make_float4(f.c[0], f.c[1], f.c[2], f.c[3]);
+        if (KIND == kCylinder) hp[1] = make_float4(f.c[4], f.c[5], f.c[6], f.c[7]);
+        hp[NC / 4] = make_float4(f.T, f.band, ck.a, ck.b);
+        if (KIND != kPlane) hp[NC / 4 + 1] = make_float4(ck.c, ck.d, 0.f, 0.f);
     }
+    __syncwarp(); /* a warp only ever reads the parameters its own lanes wrote */
 
     uint32_t nres = 0;
     for (uint32_t k = 0;; ++k) {
-        const int st = k % kStages;
-        mbar_wait(&full[st], (k / kStages) & 1);
+        const int st = k % kCullStages;
+        mbar_wait(&full[st], (k / kCullStages) & 1);
         const uint32_t t = tile_id[st];
         if (t == kNoTile) break;
         const float4 *sp = tiles + (size_t)st * kStageF4;
+        const unsigned char *spb = reinterpret_cast<const unsigned char *>(sp) + lane * sizeof(float4);
         const uint32_t base = t * kTile;
         const float4 tb = sp[kTile + kTileCells]; /* tile sphere (broadcast) */
         const float4 cb = sp[kTile + lane];       /* this lane's cell sphere */
 #pragma unroll
         for (int h = 0; h < HPT; ++h) {
             /* lane = hypothesis: which of the warp's hypotheses can have inliers in this tile? */
-            unsigned live = __ballot_sync(fullmask, !cull_test<KIND>(f[h].c, ck[h], tb));
+            Fast<KIND> g;
+            CullP gk;
+            load_hyp<KIND>(hyp + (size_t)(h * THREADS + tid) * HF4, g, gk);
+            unsigned live = __ballot_sync(fullmask, !cull_test<KIND>(g.c, gk, tb));
             M3D_STAT(0, 32);
             M3D_STAT(1, __popc(live));
             while (live) {
                 const int src = __ffs(live) - 1;
                 live &= live - 1;
-                Fast<KIND> g;
-                CullP gk;
-#pragma unroll
-                for (int i = 0; i < NC; ++i) g.c[i] = __shfl_sync(fullmask, f[h].c[i], src);
-                g.T = __shfl_sync(fullmask, f[h].T, src);
-                g.band = __shfl_sync(fullmask, f[h].band, src);
-                gk.a = __shfl_sync(fullmask, ck[h].a, src);
-                gk.b = __shfl_sync(fullmask, ck[h].b, src);
-                gk.c = __shfl_sync(fullmask, ck[h].c, src);
-                gk.d = __shfl_sync(fullmask, ck[h].d, src);
-                /* lane = cell */
-                const unsigned cells = __ballot_sync(fullmask, !cull_test<KIND>(g.c, gk, cb));
+                /* the hypothesis' parameters, warp-uniform (broadcast loads) */
+                load_hyp<KIND>(hyp + (size_t)(h * THREADS + warp * 32 + src) * HF4, g, gk);
+                /* lane = cell: surviving cells, compacted into the warp's list (byte offsets of the
+                 * cells inside the stage; padded with the NaN cell to a multiple of four) */
+                const bool keep = !cull_test<KIND>(g.c, gk, cb);
+                const unsigned cells = __ballot_sync(fullmask, keep);
                 M3D_STAT(2, __popc(cells));
-                /* lane = point, four surviving cells per trip (exhausted slots read the NaN cell) */
+                if (cells == 0) continue;
+                const int ncell = __popc(cells);
+                __syncwarp(); /* the previous hypothesis' list has been consumed */
+                if (keep) wlist[__popc(cells & ((1u << lane) - 1))] = (uint32_t)(lane * kCellPts * sizeof(float4));
+                if (lane == 0) wlist[ncell] = (uint32_t)(kBlobF4 * sizeof(float4)); /* odd count: pad with the NaN cell */
+                __syncwarp();
+                /* lane = point: four surviving cells per trip, then the remainder two at a time */
                 uint32_t cnt = 0;
                 float mn = INFINITY;
-                unsigned cm = cells;
-                while (cm) {
-                    int ci[4];
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        ci[u] = (int)min((unsigned)(__ffs(cm) - 1), (unsigned)(kTileCells + 1));
-                        cm &= cm - 1;
-                    }
-                    float4 p[4];
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) p[u] = sp[(ci[u] == kTileCells + 1 ? kBlobF4 : ci[u] * kCellPts) + lane];
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const float v = fast_v<KIND>(g, p[u]);
-                        cnt += __float_as_uint(v) >> 31;
-                        mn = fminf(mn, fabsf(v));
-                    }
+                int j = 0;
+                for (; j + 4 <= ncell; j += 4) {
+                    const uint4 off = *reinterpret_cast<const uint4 *>(wlist + j);
+                    const float4 p0 = *reinterpret_cast<const float4 *>(spb + off.x);
+                    const float4 p1 = *reinterpret_cast<const float4 *>(spb + off.y);
+                    const float4 p2 = *reinterpret_cast<const float4 *>(spb + off.z);
+                    const float4 p3 = *reinterpret_cast<const float4 *>(spb + off.w);
+                    const float v0 = fast_v<KIND>(g, p0), v1 = fast_v<KIND>(g, p1);
+                    const float v2 = fast_v<KIND>(g, p2), v3 = fast_v<KIND>(g, p3);
+                    cnt += (__float_as_uint(v0) >> 31) + (__float_as_uint(v1) >> 31);
+                    cnt += (__float_as_uint(v2) >> 31) + (__float_as_uint(v3) >> 31);
+                    mn = fminf(mn, fminf(fabsf(v0), fabsf(v1)));
+                    mn = fminf(mn, fminf(fabsf(v2), fabsf(v3)));
+                }
+                for (; j < ncell; j += 2) {
+                    const uint2 off = *reinterpret_cast<const uint2 *>(wlist + j);
+                    const float4 p0 = *reinterpret_cast<const float4 *>(spb + off.x);
+                    const float4 p1 = *reinterpret_cast<const float4 *>(spb + off.y);
+                    const float v0 = fast_v<KIND>(g, p0), v1 = fast_v<KIND>(g, p1);
+                    cnt += (__float_as_uint(v0) >> 31) + (__float_as_uint(v1) >> 31);
+                    mn = fminf(mn, fminf(fabsf(v0), fabsf(v1)));
                 }
                 if (__any_sync(fullmask, mn < g.band)) { /* rare: queue the guard-band points of these cells */
                     const uint32_t r = __shfl_sync(fullmask, row[h], src);
-                    cm = cells;
+                    unsigned cm = cells;
                     while (cm) {
                         const int c = __ffs(cm) - 1;
                         cm &= cm - 1;
