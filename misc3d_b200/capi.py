@@ -3,7 +3,9 @@
 Thin plumbing only: numpy buffers in, numpy buffers out.  There is no CPU fallback: if the shared
 library is missing, or no CUDA device is usable, the calls raise.
 """
+import atexit
 import ctypes as C
+import weakref
 import os
 
 import numpy as np
@@ -132,13 +134,30 @@ def ordered_scan(counts, valid, err, n_points, k, probability, max_iteration):
     return st.as_dict()
 
 
+_live_contexts = weakref.WeakSet()
+
+
+@atexit.register
+def _close_all():
+    """destroy every context (and its clouds) while the CUDA runtime and this module are still alive"""
+    for c in list(_live_contexts):
+        try:
+            c.close()
+        except Exception:
+            pass
+
+
 class Cloud:
     def __init__(self, ctx, handle, n, has_normals):
         self.ctx, self.handle, self.n, self.has_normals = ctx, handle, n, has_normals
+        ctx._clouds.add(self)
 
     def free(self):
+        """releases the device buffers; a cloud is always freed before its context is destroyed
+        (Context.close frees the clouds it still owns), whatever order the interpreter tears objects down in"""
         if self.handle:
-            lib().m3d_cloud_free(self.handle)
+            if getattr(self.ctx, "h", None):
+                lib().m3d_cloud_free(self.handle)
             self.handle = None
 
     def __del__(self):
@@ -163,9 +182,13 @@ class Context:
         self.h = h
         self.device = device
         self._cb = None
+        self._clouds = weakref.WeakSet()
+        _live_contexts.add(self)
 
     def close(self):
         if getattr(self, "h", None):
+            for c in list(getattr(self, "_clouds", ())):
+                c.free()
             lib().m3d_ctx_destroy(self.h)
             self.h = None
 
