@@ -103,7 +103,7 @@ def cpu_path():
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import refc
     if refc.available(omp=True):
-        cores = refc.omp_threads()
+        cores = refc.use_all_cores()
 
         def fit(kind, xyz, nrm, h, seed):
             refc.ransac_fit(kind, xyz, nrm if kind == 2 else None, THR, h, 1.0, seed, omp=True)
@@ -111,7 +111,7 @@ def cpu_path():
                                          "Eigen/Open3D stand-ins), RANSAC<>::FitModel incl. RefineModel")
     import orc
     orc.build()
-    cores = orc.omp_threads()
+    cores = orc.use_all_cores()
 
     def fit(kind, xyz, nrm, h, seed):
         orc.ransac_fit(kind, xyz, nrm if kind == 2 else None, thr=THR, max_it=h, prob=1.0, seed=seed, omp=True,
@@ -182,6 +182,7 @@ def cpu_baseline(xyz, nrm, budget_s=12.0):
     if kind_name == "reference":   # the oracle port beside it, for continuity with earlier runs
         import orc
         orc.build()
+        orc.use_all_cores()
         t0 = time.perf_counter()
         for kind in KINDS:
             orc.ransac_fit(kind, xyz, nrm if kind == 2 else None, thr=THR, max_it=h_cpu, prob=1.0, seed=3, omp=True,

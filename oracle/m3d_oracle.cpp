@@ -1042,6 +1042,14 @@ int orc_ransac_registration(const double *sx, size_t ns, const double *dx, size_
     return 1;
 }
 
+/* launchers such as torchrun export OMP_NUM_THREADS=1; the timing legs ask for the host's cores explicitly */
+void orc_set_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
 int orc_omp_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

@@ -108,6 +108,7 @@ int orc_ransac_registration(const double *src_xyz, size_t ns, const double *dst_
 void orc_reg_sample_table(uint32_t seed, size_t m, size_t rows, uint32_t *out);
 
 int orc_omp_threads(void);
+void orc_set_threads(int n);
 
 #ifdef __cplusplus
 }

@@ -201,3 +201,10 @@ def ransac_registration(src, dst, c0, c1, thr=0.01, max_iter=100000, edge_thr=0.
 
 def omp_threads():
     return lib().orc_omp_threads()
+
+
+def use_all_cores():
+    """OpenMP threads := the cores this process may run on (launchers like torchrun export OMP_NUM_THREADS=1)"""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    lib().orc_set_threads(int(n))
+    return omp_threads()

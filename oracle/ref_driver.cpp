@@ -86,6 +86,11 @@ extern "C" {
 /* 1/0 = FitModel's return value, -1 = the reference threw (message in m3dref_last_error) */
 static std::string g_err;
 const char *m3dref_last_error() { return g_err.c_str(); }
+void m3dref_set_threads(int n) { /* torchrun exports OMP_NUM_THREADS=1: the timing legs ask for the cores explicitly */
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#endif
+}
 int m3dref_openmp() {
 #ifdef _OPENMP
     return omp_get_max_threads();

@@ -153,3 +153,10 @@ def match_correspondence(src, dst, method=FLANN, n_trees=4, omp=False):
 
 def omp_threads():
     return int(lib(True).m3dref_openmp())
+
+
+def use_all_cores():
+    """OpenMP threads := the cores this process may run on (launchers like torchrun export OMP_NUM_THREADS=1)"""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    lib(True).m3dref_set_threads(int(n))
+    return omp_threads()
