@@ -301,7 +301,9 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = 3.0 * H * args.steps / float(t.item())
-    h2d = 3 * xyz.nbytes + nrm.nbytes + (3 + 4 + 2) * 4 * H  # three cloud uploads (+normals once) + sample tables
+    # three cloud uploads + the sample tables + the normals of the cylinder's sample points (2 per hypothesis; the
+    # caller's normal array itself stays on the host)
+    h2d = 3 * xyz.nbytes + (3 + 4 + 2) * 4 * H + 2 * 24 * H
 
     if rank != 0:
         if world > 1:

@@ -73,6 +73,9 @@ struct m3d_cloud {
     m3d::DevBuf pts32; /* n float4: centred fp32 x,y,z and |q|^2 of the centred point */
     m3d::DevBuf meta;  /* CloudMeta                                            */
     m3d::CloudMeta h_meta;
+    /* host-buffer entry points only: the caller's normal array stays on the host (borrowed for the
+     * call); the normals of the sampled points are uploaded per wave instead of all n of them */
+    const double *h_nrm = nullptr;
     /* Morton-ordered copy for the culling score kernel (score_cull.cuh), built on first use */
     mutable m3d::DevBuf blob;  /* tiles x (1024 points + 32 cell spheres + 1 tile sphere) float4 */
     mutable m3d::DevBuf perm;  /* sorted position -> original point index (u32)                   */
@@ -91,8 +94,8 @@ struct m3d_ctx {
 
     /* scratch (grow-only) */
     m3d::DevBuf d_samples, d_counts, d_counts_all, d_blk, d_part, d_small, d_inl, d_models, d_valid;
-    m3d::DevBuf d_tmp0, d_tmp1, d_tmp2, d_tmp3, d_tmp4, d_tmp5, d_queue, d_tiles;
-    m3d::PinBuf h_samples, h_counts, h_small, h_stage;
+    m3d::DevBuf d_tmp0, d_tmp1, d_tmp2, d_tmp3, d_tmp4, d_tmp5, d_queue, d_tiles, d_rownrm;
+    m3d::PinBuf h_samples, h_counts, h_small, h_stage, h_rownrm;
     m3d_cloud *scratch_cloud = nullptr; /* staging cloud of the host-buffer entry points */
 
     /* sharding / exchange */

@@ -31,6 +31,7 @@ struct SmallDev { /* layout of ctx->d_small */
     double seq_err;     /* seq_err_kernel output                                      */
     unsigned long long resolves;
     uint32_t sample[8]; /* one sample row                                             */
+    double row_nrm[12]; /* its normals in draw order (host-normals mode)              */
 };
 
 int prepare_cloud(m3d_ctx *ctx, m3d_cloud *c) {
@@ -60,6 +61,7 @@ int cloud_fill(m3d_ctx *ctx, m3d_cloud *c, const double *xyz, const double *nrm,
     c->ctx = ctx;
     c->n = n;
     c->sorted = false;
+    c->h_nrm = nullptr;
     c->has_normals = nrm != nullptr;
     const size_t bytes = sizeof(double) * 3 * std::max<size_t>(n, 1);
     M3D_CUDA(ctx, c->xyz.reserve(bytes));
@@ -320,17 +322,17 @@ int write_pass_kind(m3d_ctx *ctx, int kind, const double *xyz, uint32_t n, const
     }
 }
 int fit_rows_kind(m3d_ctx *ctx, int kind, const double *xyz, const double *nrm, const uint32_t *d_samples,
-                  uint32_t rows, double *d_models, uint8_t *d_valid) {
+                  uint32_t rows, double *d_models, uint8_t *d_valid, const double *d_row_nrm = nullptr) {
     const int nb = (rows + 127) / 128;
     switch (kind) {
         case kPlane:
-            minimal_fit_rows_kernel<kPlane><<<nb, 128, 0, ctx->stream>>>(xyz, nrm, d_samples, rows, d_models, d_valid);
+            minimal_fit_rows_kernel<kPlane><<<nb, 128, 0, ctx->stream>>>(xyz, nrm, d_samples, rows, d_models, d_valid, d_row_nrm);
             break;
         case kSphere:
-            minimal_fit_rows_kernel<kSphere><<<nb, 128, 0, ctx->stream>>>(xyz, nrm, d_samples, rows, d_models, d_valid);
+            minimal_fit_rows_kernel<kSphere><<<nb, 128, 0, ctx->stream>>>(xyz, nrm, d_samples, rows, d_models, d_valid, d_row_nrm);
             break;
         default:
-            minimal_fit_rows_kernel<kCylinder><<<nb, 128, 0, ctx->stream>>>(xyz, nrm, d_samples, rows, d_models, d_valid);
+            minimal_fit_rows_kernel<kCylinder><<<nb, 128, 0, ctx->stream>>>(xyz, nrm, d_samples, rows, d_models, d_valid, d_row_nrm);
     }
     M3D_LAUNCHED(ctx);
     return M3D_OK;
@@ -361,6 +363,7 @@ struct CloudView {
     bool nonfinite;
     const float4 *blob = nullptr; /* Morton-ordered copy (null: dense scoring only) */
     const uint32_t *perm = nullptr;
+    const double *h_nrm = nullptr; /* normals left on the host (host-buffer entry point): upload per sample */
 };
 
 /* one full FitModel on a device-resident cloud.  On return the minimal best model sits in
@@ -401,12 +404,27 @@ int fit_view(m3d_ctx *ctx, int kind, const m3d_cloud *cloud_for_flags, const Clo
     float score_ms = 0;
     uint64_t evaluated = 0;
 
+    /* host-normals mode: only the cylinder reads normals, and only those of its sample points */
+    const bool host_nrm = (kind == kCylinder) && v.nrm == nullptr && v.h_nrm != nullptr;
+    const double *one_row_nrm = host_nrm ? ds->row_nrm : nullptr;
+    /* sample row `row` (+ its normals) -> ds->sample / ds->row_nrm; pageable 48-byte copies are staged by the
+     * driver before cudaMemcpyAsync returns, so the stack buffer may go out of scope */
+    auto stage_row = [&](uint64_t row) -> int {
+        M3D_CUDA(ctx, cudaMemcpyAsync(ds->sample, &table[(size_t)row * k], sizeof(uint32_t) * k,
+                                      cudaMemcpyHostToDevice, ctx->stream));
+        if (host_nrm) {
+            double tmp[12];
+            for (int j = 0; j < k; ++j)
+                for (int c = 0; c < 3; ++c) tmp[3 * j + c] = v.h_nrm[3 * (size_t)table[(size_t)row * k + j] + c];
+            M3D_CUDA(ctx, cudaMemcpyAsync(ds->row_nrm, tmp, sizeof(double) * 3 * k, cudaMemcpyHostToDevice, ctx->stream));
+        }
+        return 0;
+    };
     /* evaluates hypothesis `row` alone (tie-breaks, final best): model -> ds->model, then
      * pass 1+2 -> ds->mid; optionally the index-order error */
     auto eval_row = [&](uint64_t row, bool exact, uint64_t expect_cnt, double *rmse) -> int {
-        M3D_CUDA(ctx, cudaMemcpyAsync(ds->sample, &table[(size_t)row * k], sizeof(uint32_t) * k,
-                                      cudaMemcpyHostToDevice, ctx->stream));
-        if (int rc = fit_rows_kind(ctx, kind, v.xyz, v.nrm, ds->sample, 1, ds->model, ds->valid)) return rc;
+        if (int rc = stage_row(row)) return rc;
+        if (int rc = fit_rows_kind(ctx, kind, v.xyz, v.nrm, ds->sample, 1, ds->model, ds->valid, one_row_nrm)) return rc;
         if (int rc = count_pass_kind(ctx, kind, v.xyz, n, ds->model, p.threshold, rb, &ds->mid)) return rc;
         if (exact) {
             RefineOut *scratch_out = &ds->out;
@@ -442,6 +460,18 @@ int fit_view(m3d_ctx *ctx, int kind, const m3d_cloud *cloud_for_flags, const Clo
         M3D_CUDA(ctx, ctx->d_samples.reserve(sizeof(uint32_t) * (size_t)rows * k));
         M3D_CUDA(ctx, cudaMemcpyAsync(ctx->d_samples.p, ctx->h_samples.p, sizeof(uint32_t) * (size_t)rows * k,
                                       cudaMemcpyHostToDevice, ctx->stream));
+        if (host_nrm) { /* normals of this wave's sample points only: rows x k x 3 doubles */
+            const size_t cnt = (size_t)rows * k * 3;
+            M3D_CUDA(ctx, ctx->h_rownrm.reserve(sizeof(double) * cnt));
+            M3D_CUDA(ctx, ctx->d_rownrm.reserve(sizeof(double) * cnt));
+            double *dst = ctx->h_rownrm.as<double>();
+            const uint32_t *tab = &table[(size_t)done * k];
+            for (size_t e = 0; e < (size_t)rows * k; ++e) {
+                const double *src = v.h_nrm + 3 * (size_t)tab[e];
+                dst[3 * e] = src[0], dst[3 * e + 1] = src[1], dst[3 * e + 2] = src[2];
+            }
+            M3D_CUDA(ctx, cudaMemcpyAsync(ctx->d_rownrm.p, dst, sizeof(double) * cnt, cudaMemcpyHostToDevice, ctx->stream));
+        }
         /* shard: rank r scores rows [r*S, (r+1)*S) of the wave */
         const uint32_t S = (rows + R - 1) / R;
         const uint32_t my0 = std::min<uint32_t>(rows, (uint32_t)rank * S);
@@ -457,6 +487,7 @@ int fit_view(m3d_ctx *ctx, int kind, const m3d_cloud *cloud_for_flags, const Clo
             a.perm = v.perm;
             a.xyz = v.xyz;
             a.nrm = v.nrm;
+            a.row_nrm = host_nrm ? ctx->d_rownrm.as<double>() : nullptr;
             a.meta = v.meta;
             a.samples = ctx->d_samples.as<uint32_t>();
             a.counts = ctx->d_counts.as<uint32_t>();
@@ -512,9 +543,8 @@ int fit_view(m3d_ctx *ctx, int kind, const m3d_cloud *cloud_for_flags, const Clo
     if (scan.found) {
         /* RefineModel (ransac.h:534-549) on the winning minimal model */
         const uint64_t bi = scan.best_index;
-        M3D_CUDA(ctx, cudaMemcpyAsync(ds->sample, &table[(size_t)bi * k], sizeof(uint32_t) * k,
-                                      cudaMemcpyHostToDevice, ctx->stream));
-        if (int rc = fit_rows_kind(ctx, kind, v.xyz, v.nrm, ds->sample, 1, ds->model, ds->valid)) return rc;
+        if (int rc = stage_row(bi)) return rc;
+        if (int rc = fit_rows_kind(ctx, kind, v.xyz, v.nrm, ds->sample, 1, ds->model, ds->valid, one_row_nrm)) return rc;
         if (int rc = count_pass_kind(ctx, kind, v.xyz, n, ds->model, p.threshold, rb, &ds->mid)) return rc;
         if (seg) {
             if (int rc = write_pass<kPlane, true>(ctx, v.xyz, n, ds->model, p.threshold, rb, &ds->mid,
@@ -600,9 +630,10 @@ int m3d_ransac_fit_cloud(m3d_ctx *ctx, int kind, const m3d_cloud *cloud, const m
     if (stats) memset(stats, 0, sizeof *stats);
     if (int rc = check_params(ctx, kind, cloud->n, cloud->has_normals, p)) return rc;
     M3D_CUDA(ctx, cudaSetDevice(ctx->device));
-    CloudView v{cloud->xyz.as<double>(), cloud->has_normals ? cloud->nrm.as<double>() : nullptr,
+    CloudView v{cloud->xyz.as<double>(), (cloud->has_normals && !cloud->h_nrm) ? cloud->nrm.as<double>() : nullptr,
                 cloud->pts32.as<float4>(), cloud->meta.as<CloudMeta>(), (uint32_t)cloud->n,
                 cloud->h_meta.nonfinite != 0};
+    v.h_nrm = cloud->h_nrm;
     if (int rc = ensure_sorted(ctx, cloud)) return rc;
     if (cloud->sorted) {
         v.blob = cloud->blob.as<float4>();
@@ -637,8 +668,15 @@ int m3d_ransac_fit(m3d_ctx *ctx, int kind, const double *xyz, const double *nrm,
     M3D_CUDA(ctx, cudaSetDevice(ctx->device));
     /* the staging cloud lives in the context: repeated calls re-use its device buffers */
     if (!ctx->scratch_cloud) ctx->scratch_cloud = new m3d_cloud();
-    if (int rc = cloud_fill(ctx, ctx->scratch_cloud, xyz, nrm, n, cudaMemcpyHostToDevice)) return rc;
-    return m3d_ransac_fit_cloud(ctx, kind, ctx->scratch_cloud, p, model_out, inl_out, n_inl, stats);
+    /* the normals stay on the host: the fit reads them at the sample points only (cylinder MinimalFit,
+     * ransac.h:376-383), so rows x 2 normals per wave are uploaded instead of all n */
+    if (int rc = cloud_fill(ctx, ctx->scratch_cloud, xyz, nullptr, n, cudaMemcpyHostToDevice)) return rc;
+    ctx->scratch_cloud->has_normals = nrm != nullptr;
+    ctx->scratch_cloud->h_nrm = nrm;
+    const int rc = m3d_ransac_fit_cloud(ctx, kind, ctx->scratch_cloud, p, model_out, inl_out, n_inl, stats);
+    ctx->scratch_cloud->h_nrm = nullptr; /* borrowed for this call only */
+    ctx->scratch_cloud->has_normals = false;
+    return rc;
 }
 
 #ifdef M3D_CULL_STATS

@@ -232,11 +232,19 @@ __global__ void iota_kernel(uint32_t *out, uint32_t n) {
  * pass) -> MinimalFit.  Returns MinimalFit's bool. */
 template <int KIND>
 __device__ __forceinline__ bool fit_row(const double *__restrict__ xyz, const double *__restrict__ nrm,
-                                        const uint32_t *__restrict__ samples, uint32_t row, double *m) {
+                                        const uint32_t *__restrict__ samples, uint32_t row, double *m,
+                                        const double *__restrict__ row_nrm = nullptr) {
+    /* row_nrm (optional): the normals of exactly the sampled points, [row][draw position][3] -- what the
+     * host-buffer entry point uploads instead of the whole normal array (only the cylinder's two sample
+     * normals are ever read, ransac.h:376-383) */
     constexpr int K = sample_size(KIND);
     uint32_t s[K];
+    int ord[K];
 #pragma unroll
-    for (int i = 0; i < K; ++i) s[i] = samples[(size_t)row * K + i];
+    for (int i = 0; i < K; ++i) {
+        s[i] = samples[(size_t)row * K + i];
+        ord[i] = i;
+    }
 #pragma unroll
     for (int i = 1; i < K; ++i) /* K <= 4: sorting network by insertion */
 #pragma unroll
@@ -245,6 +253,9 @@ __device__ __forceinline__ bool fit_row(const double *__restrict__ xyz, const do
                 const uint32_t t = s[j];
                 s[j] = s[j - 1];
                 s[j - 1] = t;
+                const int o = ord[j];
+                ord[j] = ord[j - 1];
+                ord[j - 1] = o;
             }
     double pts[3 * K];
     double nr[KIND == kCylinder ? 3 * K : 1];
@@ -253,7 +264,8 @@ __device__ __forceinline__ bool fit_row(const double *__restrict__ xyz, const do
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
             pts[3 * i + c] = xyz[3 * (size_t)s[i] + c];
-            if (KIND == kCylinder) nr[3 * i + c] = nrm[3 * (size_t)s[i] + c];
+            if (KIND == kCylinder)
+                nr[3 * i + c] = row_nrm ? row_nrm[((size_t)row * K + ord[i]) * 3 + c] : nrm[3 * (size_t)s[i] + c];
         }
     return ex::minimal_fit<KIND>(pts, nr, m);
 }
@@ -261,11 +273,12 @@ __device__ __forceinline__ bool fit_row(const double *__restrict__ xyz, const do
 template <int KIND>
 __global__ void minimal_fit_rows_kernel(const double *__restrict__ xyz, const double *__restrict__ nrm,
                                         const uint32_t *__restrict__ samples, uint32_t rows,
-                                        double *__restrict__ models, uint8_t *__restrict__ valid) {
+                                        double *__restrict__ models, uint8_t *__restrict__ valid,
+                                        const double *__restrict__ row_nrm) {
     const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= rows) return;
     double m[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    const bool ok = fit_row<KIND>(xyz, nrm, samples, r, m);
+    const bool ok = fit_row<KIND>(xyz, nrm, samples, r, m, row_nrm);
 #pragma unroll
     for (int i = 0; i < 8; ++i) models[(size_t)r * 8 + i] = ok ? m[i] : 0.0;
     valid[r] = ok ? 1 : 0;
@@ -510,6 +523,7 @@ struct ScoreArgs {
     const float4 *pts32;
     const double *xyz;
     const double *nrm;
+    const double *row_nrm;   /* optional: normals of the sampled points only, [row][k][3] (see fit_row) */
     const CloudMeta *meta;
     const uint32_t *samples; /* rows x k of this wave (device)                          */
     uint32_t *counts;        /* [rows]: inlier count (atomicAdd per chunk), bit31 = MinimalFit false */
@@ -564,7 +578,7 @@ __device__ __forceinline__ void rescan_warp(const ScoreArgs &a, unsigned need, u
                 a.queue[pos] = make_uint2(r, (gbase + lane) | (prov << 31));
             } else { /* queue full: decide here with the reference arithmetic */
                 double m[8];
-                const bool ok = fit_row<KIND>(a.xyz, a.nrm, a.samples, a.row_begin + r, m);
+                const bool ok = fit_row<KIND>(a.xyz, a.nrm, a.samples, a.row_begin + r, m, a.row_nrm);
                 uint32_t in = 0;
                 if (ok) {
                     ex::Dist<KIND> dist;
@@ -656,7 +670,7 @@ __global__ void __launch_bounds__(THREADS + 32) score_kernel(const ScoreArgs a) 
         row[h] = (blockIdx.x * HPT + h) * THREADS + tid;
         double m[8];
         bool ok = false;
-        if (row[h] < a.rows) ok = fit_row<KIND>(a.xyz, a.nrm, a.samples, a.row_begin + row[h], m);
+        if (row[h] < a.rows) ok = fit_row<KIND>(a.xyz, a.nrm, a.samples, a.row_begin + row[h], m, a.row_nrm);
         invalid[h] = (row[h] < a.rows) && !ok;
         if (blockIdx.y == 0 && row[h] < a.rows) {
 #pragma unroll
@@ -753,7 +767,7 @@ __global__ void __launch_bounds__(128) score_exact_kernel(const ScoreArgs a) {
     (void)ntiles;
     if (row >= a.rows) return;
     double m[8];
-    const bool ok = fit_row<KIND>(a.xyz, a.nrm, a.samples, a.row_begin + row, m);
+    const bool ok = fit_row<KIND>(a.xyz, a.nrm, a.samples, a.row_begin + row, m, a.row_nrm);
     if (blockIdx.y == 0) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) a.models[(size_t)row * 8 + i] = (ok && i < param_count(KIND)) ? m[i] : 0.0;

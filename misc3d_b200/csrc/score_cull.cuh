@@ -365,7 +365,7 @@ __global__ void __launch_bounds__(THREADS + 32, (THREADS >= 256 ? 2 : 4)) score_
         row[h] = (blockIdx.x * HPT + h) * THREADS + tid;
         double m[8];
         bool ok = false;
-        if (row[h] < a.rows) ok = fit_row<KIND>(a.xyz, a.nrm, a.samples, a.row_begin + row[h], m);
+        if (row[h] < a.rows) ok = fit_row<KIND>(a.xyz, a.nrm, a.samples, a.row_begin + row[h], m, a.row_nrm);
         invalid[h] = (row[h] < a.rows) && !ok;
         if (blockIdx.y == 0 && row[h] < a.rows) {
 #pragma unroll
@@ -470,7 +470,7 @@ __global__ void __launch_bounds__(THREADS + 32, (THREADS >= 256 ? 2 : 4)) score_
                                 a.queue[pos] = make_uint2(r, pt | (prov << 31));
                             } else { /* queue full: decide here with the reference arithmetic */
                                 double m[8];
-                                const bool ok = fit_row<KIND>(a.xyz, a.nrm, a.samples, a.row_begin + r, m);
+                                const bool ok = fit_row<KIND>(a.xyz, a.nrm, a.samples, a.row_begin + r, m, a.row_nrm);
                                 uint32_t in = 0;
                                 if (ok) {
                                     ex::Dist<KIND> dist;
