@@ -598,7 +598,9 @@ __global__ void __launch_bounds__(256) resolve_queue_kernel(const ScoreArgs a) {
     const uint32_t total = min(*a.queue_count, a.queue_cap);
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         const uint2 e = a.queue[i];
-        const uint32_t prov = e.y >> 31, pt = e.y & 0x7fffffffu;
+        const uint32_t prov = e.y >> 31;
+        uint32_t pt = e.y & 0x7fffffffu;
+        if (a.blob) pt = a.perm[pt]; /* the culling kernel queues positions in the Morton-ordered copy */
         double m[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) m[k] = a.models[(size_t)e.x * 8 + k];

@@ -292,6 +292,7 @@ __device__ __forceinline__ void load_hyp(const float4 *hp, Fast<KIND> &g, CullP 
         gk.c = q3.x, gk.d = q3.y;
     }
 }
+constexpr int kQBuf = 96; /* guard-band pairs a warp stages in shared memory before one global atomicAdd */
 constexpr int kListLen = kTileCells + 4; /* per-warp list of surviving cells (+ padding slot), 16 B aligned */
 
 template <int KIND, int THREADS, int HPT>
@@ -299,6 +300,7 @@ constexpr size_t cull_smem_bytes() {
     return (size_t)kCullStages * kStageF4 * sizeof(float4)                      /* tile ring            */
            + (size_t)THREADS * HPT * HypLayout<KIND>::kF4 * sizeof(float4)  /* hypothesis parameters */
            + (size_t)(THREADS / 32) * kListLen * sizeof(uint32_t)           /* surviving-cell lists  */
+           + (size_t)(THREADS / 32) * kQBuf * sizeof(uint2)                 /* guard-band staging    */
            + 2 * kCullStages * sizeof(uint64_t) + kCullStages * sizeof(uint32_t) + 16;
 }
 
@@ -312,7 +314,8 @@ __global__ void __launch_bounds__(THREADS + 32, (THREADS >= 256 ? 2 : 4)) score_
     float4 *tiles = reinterpret_cast<float4 *>(smem_raw);
     float4 *hyp = tiles + (size_t)kCullStages * kStageF4;
     uint32_t *lists = reinterpret_cast<uint32_t *>(hyp + (size_t)THREADS * HPT * HF4);
-    uint64_t *full = reinterpret_cast<uint64_t *>(lists + (THREADS / 32) * kListLen);
+    uint2 *qbufs = reinterpret_cast<uint2 *>(lists + (THREADS / 32) * kListLen);
+    uint64_t *full = reinterpret_cast<uint64_t *>(qbufs + (THREADS / 32) * kQBuf);
     uint64_t *empty = full + kCullStages;
     volatile uint32_t *tile_id = reinterpret_cast<volatile uint32_t *>(empty + kCullStages);
 
@@ -357,6 +360,37 @@ __global__ void __launch_bounds__(THREADS + 32, (THREADS >= 256 ? 2 : 4)) score_
     const unsigned fullmask = 0xffffffffu;
     const int lane = tid & 31, warp = tid >> 5;
     uint32_t *wlist = lists + warp * kListLen;
+    uint2 *qbuf = qbufs + warp * kQBuf;
+    uint32_t qn = 0; /* entries staged in qbuf (warp-uniform) */
+    /* staged guard-band pairs -> the global queue: one atomicAdd per flush instead of one per cell */
+    auto flush_queue = [&]() {
+        __syncwarp();
+        if (qn) {
+            uint32_t pos0 = 0;
+            if (lane == 0) pos0 = atomicAdd(a.queue_count, qn);
+            pos0 = __shfl_sync(fullmask, pos0, 0);
+            for (uint32_t i = lane; i < qn; i += 32) {
+                const uint2 e = qbuf[i];
+                const uint32_t pos = pos0 + i;
+                if (pos < a.queue_cap) {
+                    a.queue[pos] = e;
+                } else { /* queue full: decide here with the reference arithmetic */
+                    const uint32_t prov = e.y >> 31, pt = a.perm[e.y & 0x7fffffffu];
+                    double m[8];
+                    const bool ok = fit_row<KIND>(a.xyz, a.nrm, a.samples, a.row_begin + e.x, m, a.row_nrm);
+                    uint32_t in = 0;
+                    if (ok) {
+                        ex::Dist<KIND> dist;
+                        dist.set(m);
+                        in = dist(ex::ld3(a.xyz + 3 * (size_t)pt)) < a.thr ? 1u : 0u;
+                    }
+                    if (in != prov) atomicAdd(&a.counts[e.x], in - prov);
+                }
+            }
+            qn = 0;
+        }
+        __syncwarp();
+    };
     uint32_t row[HPT];
     uint32_t clo[HPT];
     bool invalid[HPT];
@@ -456,30 +490,15 @@ __global__ void __launch_bounds__(THREADS + 32, (THREADS >= 256 ? 2 : 4)) score_
                         const bool amb = fabsf(v) < g.band; /* false for the NaN padding */
                         const unsigned am = __ballot_sync(fullmask, amb);
                         if (am == 0) continue;
-                        uint32_t pos0 = 0;
-                        if (lane == 0) {
-                            pos0 = atomicAdd(a.queue_count, (uint32_t)__popc(am));
-                            nres += __popc(am);
-                        }
-                        pos0 = __shfl_sync(fullmask, pos0, 0);
+                        const uint32_t na = __popc(am);
+                        if (qn + na > (uint32_t)kQBuf) flush_queue();
                         if (amb) {
                             const uint32_t prov = __float_as_uint(v) >> 31;
-                            const uint32_t pt = a.perm[base + c * kCellPts + lane]; /* original index */
-                            const uint32_t pos = pos0 + __popc(am & ((1u << lane) - 1));
-                            if (pos < a.queue_cap) {
-                                a.queue[pos] = make_uint2(r, pt | (prov << 31));
-                            } else { /* queue full: decide here with the reference arithmetic */
-                                double m[8];
-                                const bool ok = fit_row<KIND>(a.xyz, a.nrm, a.samples, a.row_begin + r, m, a.row_nrm);
-                                uint32_t in = 0;
-                                if (ok) {
-                                    ex::Dist<KIND> dist;
-                                    dist.set(m);
-                                    in = dist(ex::ld3(a.xyz + 3 * (size_t)pt)) < a.thr ? 1u : 0u;
-                                }
-                                if (in != prov) atomicAdd(&a.counts[r], in - prov);
-                            }
+                            const uint32_t pt = base + c * kCellPts + lane; /* SORTED position: resolve_queue_kernel maps it through perm */
+                            qbuf[qn + __popc(am & ((1u << lane) - 1))] = make_uint2(r, pt | (prov << 31));
                         }
+                        qn += na;
+                        nres += (lane == 0) ? na : 0u;
                     }
                 }
                 const uint32_t tot = __reduce_add_sync(fullmask, cnt);
@@ -490,6 +509,7 @@ __global__ void __launch_bounds__(THREADS + 32, (THREADS >= 256 ? 2 : 4)) score_
         if (lane == 0) mbar_arrive(&empty[st]);
     }
 
+    flush_queue();
 #pragma unroll
     for (int h = 0; h < HPT; ++h) {
         if (row[h] < a.rows) {
