@@ -59,6 +59,25 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
         "r"(parity)
         : "memory");
 }
+/* the producer thread is whole tiles ahead of the consumers: it polls with a sleep in between so that
+ * its spin loop does not take issue slots from the consumer warps that share its scheduler */
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t *bar, uint32_t parity) {
+    const uint32_t b = smem_u32(bar);
+    for (;;) {
+        uint32_t done;
+        asm volatile(
+            "{\n"
+            ".reg .pred P1;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, P1;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(b), "r"(parity)
+            : "memory");
+        if (done) break;
+        __nanosleep(256);
+    }
+}
 /* cp.async.bulk (TMA, SASS UBLKCP): global -> shared, completion on an mbarrier */
 __device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
     const uint32_t b = smem_u32(bar);
@@ -643,7 +662,7 @@ __global__ void __launch_bounds__(THREADS + 32) score_kernel(const ScoreArgs a) 
         if (tid == THREADS) {
             for (uint32_t k = 0;; ++k) {
                 const int st = k % kStages;
-                if (k >= kStages) mbar_wait(&empty[st], ((k / kStages) - 1) & 1); /* slot released by all warps */
+                if (k >= kStages) mbar_wait_relaxed(&empty[st], ((k / kStages) - 1) & 1); /* slot released by all warps */
                 const uint32_t t = atomicAdd(&a.tile_counter[blockIdx.x], 1u);
                 if (t >= ntiles) {
                     tile_id[st] = kNoTile;

@@ -301,6 +301,8 @@ constexpr size_t cull_smem_bytes() {
            + (size_t)THREADS * HPT * HypLayout<KIND>::kF4 * sizeof(float4)  /* hypothesis parameters */
            + (size_t)(THREADS / 32) * kListLen * sizeof(uint32_t)           /* surviving-cell lists  */
            + (size_t)(THREADS / 32) * kQBuf * sizeof(uint2)                 /* guard-band staging    */
+           + (size_t)THREADS * HPT * sizeof(uint32_t)                       /* per-hypothesis counts */
+           + (size_t)kCullStages * sizeof(uint32_t)                         /* group cursor per stage */
            + 2 * kCullStages * sizeof(uint64_t) + kCullStages * sizeof(uint32_t) + 16;
 }
 
@@ -318,6 +320,8 @@ __global__ void __launch_bounds__(THREADS + 32, (THREADS >= 256 ? 2 : 4)) score_
     uint64_t *full = reinterpret_cast<uint64_t *>(qbufs + (THREADS / 32) * kQBuf);
     uint64_t *empty = full + kCullStages;
     volatile uint32_t *tile_id = reinterpret_cast<volatile uint32_t *>(empty + kCullStages);
+    uint32_t *scnt = const_cast<uint32_t *>(tile_id) + kCullStages; /* inlier counts of the CTA's hypotheses */
+    uint32_t *grp_next = scnt + THREADS * HPT;                      /* next unclaimed hypothesis group of a stage's tile */
 
     const int tid = threadIdx.x;
     const uint32_t ntiles = (a.n + kTile - 1) / kTile;
@@ -340,7 +344,7 @@ __global__ void __launch_bounds__(THREADS + 32, (THREADS >= 256 ? 2 : 4)) score_
         if (tid == THREADS) {
             for (uint32_t k = 0;; ++k) {
                 const int st = k % kCullStages;
-                if (k >= kCullStages) mbar_wait(&empty[st], ((k / kCullStages) - 1) & 1);
+                if (k >= kCullStages) mbar_wait_relaxed(&empty[st], ((k / kCullStages) - 1) & 1);
                 const uint32_t t = atomicAdd(&a.tile_counter[blockIdx.x], 1u);
                 if (t >= ntiles) {
                     tile_id[st] = kNoTile;
@@ -348,6 +352,7 @@ __global__ void __launch_bounds__(THREADS + 32, (THREADS >= 256 ? 2 : 4)) score_
                     break;
                 }
                 tile_id[st] = t;
+                grp_next[st] = 0; /* published with tile_id by the barrier's release/acquire */
                 tma_load_1d(tiles + (size_t)st * kStageF4, a.blob + (size_t)t * kBlobF4,
                             (uint32_t)(kBlobF4 * sizeof(float4)), &full[st]);
             }
@@ -392,7 +397,6 @@ __global__ void __launch_bounds__(THREADS + 32, (THREADS >= 256 ? 2 : 4)) score_
         __syncwarp();
     };
     uint32_t row[HPT];
-    uint32_t clo[HPT];
     bool invalid[HPT];
 #pragma unroll
     for (int h = 0; h < HPT; ++h) { /* parameters go to shared memory; nothing of them stays in registers */
@@ -410,15 +414,21 @@ __global__ void __launch_bounds__(THREADS + 32, (THREADS >= 256 ? 2 : 4)) score_
         CullP ck;
         make_fast<KIND>(m, ok, M, a.thr, f);
         make_cull<KIND>(f, m, M, a.thr, ck);
-        clo[h] = 0;
         float4 *hp = hyp + (size_t)(h * THREADS + tid) * HF4;
         hp[0] = make_float4(f.c[0], f.c[1], f.c[2], f.c[3]);
         if (KIND == kCylinder) hp[1] = make_float4(f.c[4], f.c[5], f.c[6], f.c[7]);
         hp[NC / 4] = make_float4(f.T, f.band, ck.a, ck.b);
         if (KIND != kPlane) hp[NC / 4 + 1] = make_float4(ck.c, ck.d, 0.f, 0.f);
+        scnt[h * THREADS + tid] = 0;
     }
-    __syncwarp(); /* a warp only ever reads the parameters its own lanes wrote */
+    /* from here on any consumer warp may work on any of the CTA's hypotheses: consumer-only barrier */
+    asm volatile("bar.sync 1, %0;" ::"n"(THREADS) : "memory");
 
+    /* The CTA's THREADS*HPT hypotheses form groups of 32 (CTA-local index = h*THREADS + thread).  For every
+     * tile the consumer warps claim groups from the stage's cursor, so a tile's work is balanced over the
+     * warps whatever the per-hypothesis cost; counts are accumulated in shared memory. */
+    constexpr uint32_t kGroups = THREADS * HPT / 32;
+    const uint32_t cta_row0 = blockIdx.x * HPT * THREADS; /* local index + cta_row0 = row of the launch */
     uint32_t nres = 0;
     for (uint32_t k = 0;; ++k) {
         const int st = k % kCullStages;
@@ -430,12 +440,16 @@ __global__ void __launch_bounds__(THREADS + 32, (THREADS >= 256 ? 2 : 4)) score_
         const uint32_t base = t * kTile;
         const float4 tb = sp[kTile + kTileCells]; /* tile sphere (broadcast) */
         const float4 cb = sp[kTile + lane];       /* this lane's cell sphere */
-#pragma unroll
-        for (int h = 0; h < HPT; ++h) {
-            /* lane = hypothesis: which of the warp's hypotheses can have inliers in this tile? */
+        for (;;) {
+            uint32_t grp = 0;
+            if (lane == 0) grp = atomicAdd(&grp_next[st], 1u);
+            grp = __shfl_sync(fullmask, grp, 0);
+            if (grp >= kGroups) break;
+            const uint32_t hbase = grp * 32; /* CTA-local index of the group's first hypothesis */
+            /* lane = hypothesis: which of the group's hypotheses can have inliers in this tile? */
             Fast<KIND> g;
             CullP gk;
-            load_hyp<KIND>(hyp + (size_t)(h * THREADS + tid) * HF4, g, gk);
+            load_hyp<KIND>(hyp + (size_t)(hbase + lane) * HF4, g, gk);
             unsigned live = __ballot_sync(fullmask, !cull_test<KIND>(g.c, gk, tb));
             M3D_STAT(0, 32);
             M3D_STAT(1, __popc(live));
@@ -443,9 +457,9 @@ __global__ void __launch_bounds__(THREADS + 32, (THREADS >= 256 ? 2 : 4)) score_
                 const int src = __ffs(live) - 1;
                 live &= live - 1;
                 /* the hypothesis' parameters, warp-uniform (broadcast loads) */
-                load_hyp<KIND>(hyp + (size_t)(h * THREADS + warp * 32 + src) * HF4, g, gk);
+                load_hyp<KIND>(hyp + (size_t)(hbase + src) * HF4, g, gk);
                 /* lane = cell: surviving cells, compacted into the warp's list (byte offsets of the
-                 * cells inside the stage; padded with the NaN cell to a multiple of four) */
+                 * cells inside the stage) */
                 const bool keep = !cull_test<KIND>(g.c, gk, cb);
                 const unsigned cells = __ballot_sync(fullmask, keep);
                 M3D_STAT(2, __popc(cells));
@@ -480,8 +494,8 @@ __global__ void __launch_bounds__(THREADS + 32, (THREADS >= 256 ? 2 : 4)) score_
                     cnt += (__float_as_uint(v0) >> 31) + (__float_as_uint(v1) >> 31);
                     mn = fminf(mn, fminf(fabsf(v0), fabsf(v1)));
                 }
-                if (__any_sync(fullmask, mn < g.band)) { /* rare: queue the guard-band points of these cells */
-                    const uint32_t r = __shfl_sync(fullmask, row[h], src);
+                if (__any_sync(fullmask, mn < g.band)) { /* rare: stage the guard-band points of these cells */
+                    const uint32_t r = cta_row0 + hbase + src;
                     unsigned cm = cells;
                     while (cm) {
                         const int c = __ffs(cm) - 1;
@@ -502,7 +516,7 @@ __global__ void __launch_bounds__(THREADS + 32, (THREADS >= 256 ? 2 : 4)) score_
                     }
                 }
                 const uint32_t tot = __reduce_add_sync(fullmask, cnt);
-                if (lane == src) clo[h] += tot;
+                if (lane == 0 && tot) atomicAdd(&scnt[hbase + src], tot);
             }
         }
         __syncwarp();
@@ -510,10 +524,12 @@ __global__ void __launch_bounds__(THREADS + 32, (THREADS >= 256 ? 2 : 4)) score_
     }
 
     flush_queue();
+    asm volatile("bar.sync 1, %0;" ::"n"(THREADS) : "memory"); /* all shared-memory counts are final */
 #pragma unroll
     for (int h = 0; h < HPT; ++h) {
         if (row[h] < a.rows) {
-            if (clo[h]) atomicAdd(&a.counts[row[h]], clo[h]);
+            const uint32_t c = scnt[h * THREADS + tid];
+            if (c) atomicAdd(&a.counts[row[h]], c);
             if (invalid[h] && blockIdx.y == 0) atomicOr(&a.counts[row[h]], kInvalidBit);
         }
     }

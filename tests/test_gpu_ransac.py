@@ -300,3 +300,44 @@ def test_cull_kernel_large_hypothesis_batch(ctx, capi):
         c_dense, _, _ = ctx.score_samples(kind, cloud, table, 0.01, flags=capi.FLAG_DENSE, want_models=False)
         np.testing.assert_array_equal(c_cull, c_dense)
     cloud.free()
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_cull_kernel_randomized(ctx, capi, seed):
+    """random mixtures, scales, offsets, thresholds and sizes: the culling kernel's counts equal the fp64
+    reference-order kernel's for all three primitives"""
+    rng = np.random.default_rng(1000 + seed)
+    n = int(rng.integers(2048, 70000))
+    scale = 10.0 ** rng.uniform(-2, 3)
+    offset = rng.uniform(-1, 1, 3) * scale * 10.0 ** rng.uniform(-1, 2)
+    parts = []
+    m = n
+    for _ in range(int(rng.integers(1, 5))):          # a few primitives ...
+        k = int(m * rng.uniform(0.1, 0.5))
+        m -= k
+        kind = rng.integers(0, 3)
+        if kind == 0:
+            u = rng.uniform(-1, 1, (k, 2))
+            pts = np.c_[u, 0.01 * rng.normal(size=k) * rng.integers(0, 2)]
+            q, _ = np.linalg.qr(rng.normal(size=(3, 3)))
+            pts = pts @ q.T
+        elif kind == 1:
+            d = rng.normal(size=(k, 3))
+            pts = d / np.linalg.norm(d, axis=1, keepdims=True) * rng.uniform(0.05, 1.0) + rng.uniform(-0.5, 0.5, 3)
+        else:
+            a = rng.uniform(0, 2 * np.pi, k)
+            pts = np.c_[0.2 * np.cos(a), 0.2 * np.sin(a), rng.uniform(-1, 1, k)]
+        parts.append(pts + 0.003 * rng.normal(size=(k, 3)))
+    parts.append(rng.uniform(-1, 1, (m, 3)))          # ... and uniform outliers
+    xyz = np.concatenate(parts) * scale + offset
+    xyz = xyz[rng.permutation(len(xyz))]
+    nrm = rng.normal(size=xyz.shape)
+    nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
+    thr = scale * 10.0 ** rng.uniform(-3, -1)
+    cloud = ctx.upload(xyz, nrm)
+    for kind in KINDS:
+        table = capi.sample_table(seed * 7 + kind, len(xyz), capi.KSAMPLE[kind], 640)
+        c_cull, m_cull, v_cull = ctx.score_samples(kind, cloud, table, thr)
+        c_exact, _, _ = ctx.score_samples(kind, cloud, table, thr, flags=capi.FLAG_EXACT_ONLY, want_models=False)
+        np.testing.assert_array_equal(c_cull, c_exact, err_msg=f"seed {seed} kind {kind} n {len(xyz)} scale {scale} thr {thr}")
+    cloud.free()
