@@ -15,17 +15,59 @@ namespace m3d {
 
 /* RandomSampler<size_t> (utils.h:72-97) with an injected seed: std::mt19937, idx = rng() % size,
  * duplicates rejected, k accepted draws per call, draw order kept (SelectByIndex re-orders later). */
+/* std::mt19937's output stream, produced 624 numbers at a time (vectorisable twist + tempering loops)
+ * instead of one call at a time: the table of a 10k-hypothesis wave is drawn on the host while the GPU
+ * waits for it, so the generator's speed is on the critical path of a fit. */
+struct Mt19937Bulk {
+    uint32_t mt[624];
+    uint32_t out[624];
+    int pos = 624;
+    explicit Mt19937Bulk(uint32_t seed) {
+        mt[0] = seed;
+        for (uint32_t i = 1; i < 624; ++i) mt[i] = 1812433253u * (mt[i - 1] ^ (mt[i - 1] >> 30)) + i;
+    }
+    static inline uint32_t twist(uint32_t hi, uint32_t lo, uint32_t far) {
+        const uint32_t y = (hi & 0x80000000u) | (lo & 0x7fffffffu);
+        return far ^ (y >> 1) ^ ((0u - (y & 1u)) & 0x9908b0dfu);
+    }
+    void refill() {
+        for (int i = 0; i < 227; ++i) mt[i] = twist(mt[i], mt[i + 1], mt[i + 397]);
+        for (int i = 227; i < 623; ++i) mt[i] = twist(mt[i], mt[i + 1], mt[i - 227]);
+        mt[623] = twist(mt[623], mt[0], mt[396]);
+        for (int i = 0; i < 624; ++i) {
+            uint32_t y = mt[i];
+            y ^= y >> 11;
+            y ^= (y << 7) & 0x9d2c5680u;
+            y ^= (y << 15) & 0xefc60000u;
+            y ^= y >> 18;
+            out[i] = y;
+        }
+        pos = 0;
+    }
+    inline uint32_t next() {
+        if (pos == 624) refill();
+        return out[pos++];
+    }
+};
+
 struct SampleStream {
-    std::mt19937 rng;
-    size_t size;
-    SampleStream(uint32_t seed, size_t n) : rng(seed), size(n) {}
+    Mt19937Bulk rng;
+    uint32_t size;
+    uint64_t magic; /* exact x % size for 32-bit x by two multiplications (Lemire's fastmod) */
+    SampleStream(uint32_t seed, size_t n) : rng(seed), size((uint32_t)n), magic(n ? UINT64_MAX / (uint32_t)n + 1 : 0) {}
+    inline uint32_t mod(uint32_t x) const {
+        if (size == 1) return 0;
+        const uint64_t low = magic * x;
+        return (uint32_t)(((unsigned __int128)low * size) >> 64);
+    }
+    /* utils.h:81-97: idx = rng() % size (size_t arithmetic on a 32-bit draw), reject duplicates */
     void draw(int k, uint32_t *out) {
         int have = 0;
         while (have < k) {
-            const size_t idx = rng() % size;
+            const uint32_t idx = mod(rng.next());
             bool dup = false;
-            for (int j = 0; j < have; ++j) dup = dup || (out[j] == (uint32_t)idx);
-            if (!dup) out[have++] = (uint32_t)idx;
+            for (int j = 0; j < have; ++j) dup = dup || (out[j] == idx);
+            if (!dup) out[have++] = idx;
         }
     }
 };
