@@ -110,6 +110,7 @@ typedef struct m3d_ransac_params {
 #define M3D_FLAG_EXACT_ONLY 1u /* score with the fp64 reference-order kernel only (slow; debug) */
 #define M3D_FLAG_NO_REFIT 2u   /* skip RefineModel's GeneralFit (model_out = minimal model)     */
 #define M3D_FLAG_DENSE 4u      /* score every point-hypothesis pair (no bounding-sphere culling) */
+#define M3D_FLAG_CLASSIFY 8u   /* always pre-sort the hypotheses into culled / dense ones (default: waves >= 16384 rows) */
 
 typedef struct m3d_ransac_stats {
     uint64_t best_index;     /* loop index i of the winning minimal model                      */

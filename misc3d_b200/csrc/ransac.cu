@@ -195,6 +195,57 @@ int score_variant_override() {
     return v;
 }
 
+/* one scoring launch + its guard-band resolve; `cull` selects score_cull_kernel (needs a.blob) */
+template <int KIND>
+int launch_one(m3d_ctx *ctx, ScoreArgs a, uint32_t ntiles, bool cull) {
+    if (a.rows == 0) return M3D_OK;
+    if (!cull) a.blob = nullptr; /* resolve_queue_kernel: the dense kernel queues original point indices */
+    M3D_CUDA(ctx, cudaMemsetAsync(a.queue_count, 0, sizeof(uint32_t), ctx->stream));
+    int rc;
+    const int var = score_variant_override();
+    if (cull) {
+        switch (var) {
+            case 128 * 16 + 1: rc = launch_cull_t<KIND, 128, 1>(ctx, a, ntiles); break;
+            case 128 * 16 + 2: rc = launch_cull_t<KIND, 128, 2>(ctx, a, ntiles); break;
+            case 256 * 16 + 1: rc = launch_cull_t<KIND, 256, 1>(ctx, a, ntiles); break;
+            case 256 * 16 + 4: rc = launch_cull_t<KIND, 256, 4>(ctx, a, ntiles); break;
+            default:
+                rc = (a.rows >= 2048) ? launch_cull_t<KIND, 256, 2>(ctx, a, ntiles)
+                                      : launch_cull_t<KIND, 128, 1>(ctx, a, ntiles);
+        }
+    } else {
+        switch (var) {
+            case 128 * 16 + 1: rc = launch_score_t<KIND, 128, 1>(ctx, a, ntiles); break;
+            case 128 * 16 + 2: rc = launch_score_t<KIND, 128, 2>(ctx, a, ntiles); break;
+            case 128 * 16 + 4: rc = launch_score_t<KIND, 128, 4>(ctx, a, ntiles); break;
+            case 256 * 16 + 1: rc = launch_score_t<KIND, 256, 1>(ctx, a, ntiles); break;
+            case 256 * 16 + 2: rc = launch_score_t<KIND, 256, 2>(ctx, a, ntiles); break;
+            case 256 * 16 + 4: rc = launch_score_t<KIND, 256, 4>(ctx, a, ntiles); break;
+            default:
+                rc = (a.rows >= 2048) ? launch_score_t<KIND, 256, 2>(ctx, a, ntiles)
+                                      : launch_score_t<KIND, 128, 1>(ctx, a, ntiles);
+        }
+    }
+    if (rc) return rc;
+    resolve_queue_kernel<KIND><<<ctx->sm_count * 2, 256, 0, ctx->stream>>>(a);
+    M3D_LAUNCHED(ctx);
+    return M3D_OK;
+}
+
+/* waves of at least this many rows are pre-sorted into culled / dense hypotheses (cull_classify_kernel):
+ * costs one small kernel + a 8-byte read-back, pays when part of the hypotheses pass through most of the
+ * cloud.  A hypothesis goes to the dense kernel when more than kDenseAbove of its sampled cells survive
+ * (measured break-even of the two kernels: ~25 % surviving pairs). */
+constexpr float kDenseAbove = 0.25f;
+uint32_t classify_min_rows() { /* M3D_CLASSIFY_MIN_ROWS overrides (tuning) */
+    static uint32_t v = 0;
+    if (!v) {
+        const char *e = getenv("M3D_CLASSIFY_MIN_ROWS");
+        v = e ? (uint32_t)std::max(1l, atol(e)) : 16384u;
+    }
+    return v;
+}
+
 template <int KIND>
 int launch_score(m3d_ctx *ctx, const m3d_cloud *c, ScoreArgs a, bool exact_only) {
     const uint32_t ntiles = std::max<uint32_t>(1, (a.n + kTile - 1) / kTile);
@@ -215,38 +266,28 @@ int launch_score(m3d_ctx *ctx, const m3d_cloud *c, ScoreArgs a, bool exact_only)
         M3D_LAUNCHED(ctx);
         return M3D_OK;
     }
-    M3D_CUDA(ctx, cudaMemsetAsync(a.queue_count, 0, sizeof(uint32_t), ctx->stream));
-    int rc;
-    if (a.blob && cull_enabled()) {
-        switch (score_variant_override()) {
-            case 128 * 16 + 1: rc = launch_cull_t<KIND, 128, 1>(ctx, a, ntiles); break;
-            case 128 * 16 + 2: rc = launch_cull_t<KIND, 128, 2>(ctx, a, ntiles); break;
-            case 256 * 16 + 1: rc = launch_cull_t<KIND, 256, 1>(ctx, a, ntiles); break;
-            case 256 * 16 + 4: rc = launch_cull_t<KIND, 256, 4>(ctx, a, ntiles); break;
-            default:
-                rc = (a.rows >= 2048) ? launch_cull_t<KIND, 256, 2>(ctx, a, ntiles)
-                                      : launch_cull_t<KIND, 128, 1>(ctx, a, ntiles);
-        }
-        if (rc) return rc;
-        resolve_queue_kernel<KIND><<<ctx->sm_count * 2, 256, 0, ctx->stream>>>(a);
+    const bool cull = a.blob && cull_enabled();
+    if (cull && (a.rows >= classify_min_rows() || (a.flags & M3D_FLAG_CLASSIFY))) {
+        /* row_map: [rows for the culling kernel ...   ... rows for the dense kernel], part = the two sizes */
+        M3D_CUDA(ctx, ctx->d_rowmap.reserve(sizeof(uint32_t) * ((size_t)a.rows + 2)));
+        uint32_t *map = ctx->d_rowmap.as<uint32_t>() + 2, *part = ctx->d_rowmap.as<uint32_t>();
+        M3D_CUDA(ctx, cudaMemsetAsync(part, 0, 2 * sizeof(uint32_t), ctx->stream));
+        const uint32_t stride = std::max<uint32_t>(1, ntiles / 96); /* ~96 sampled tiles per hypothesis */
+        cull_classify_kernel<KIND><<<(a.rows + 127) / 128, 128, 0, ctx->stream>>>(a, ntiles, stride, kDenseAbove, map, part);
         M3D_LAUNCHED(ctx);
-        return M3D_OK;
+        uint32_t h_part[2] = {0, 0};
+        M3D_CUDA(ctx, cudaMemcpyAsync(h_part, part, sizeof h_part, cudaMemcpyDeviceToHost, ctx->stream));
+        M3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (h_part[0] + h_part[1] != a.rows) return ctx->fail(M3D_ERR_INTERNAL, "hypothesis classification lost rows");
+        ScoreArgs lo = a, hi = a;
+        lo.row_map = map;
+        lo.rows = h_part[0];
+        hi.row_map = map + (a.rows - h_part[1]);
+        hi.rows = h_part[1];
+        if (int rc = launch_one<KIND>(ctx, lo, ntiles, true)) return rc;
+        return launch_one<KIND>(ctx, hi, ntiles, false);
     }
-    switch (score_variant_override()) {
-        case 128 * 16 + 1: rc = launch_score_t<KIND, 128, 1>(ctx, a, ntiles); break;
-        case 128 * 16 + 2: rc = launch_score_t<KIND, 128, 2>(ctx, a, ntiles); break;
-        case 128 * 16 + 4: rc = launch_score_t<KIND, 128, 4>(ctx, a, ntiles); break;
-        case 256 * 16 + 1: rc = launch_score_t<KIND, 256, 1>(ctx, a, ntiles); break;
-        case 256 * 16 + 2: rc = launch_score_t<KIND, 256, 2>(ctx, a, ntiles); break;
-        case 256 * 16 + 4: rc = launch_score_t<KIND, 256, 4>(ctx, a, ntiles); break;
-        default:
-            rc = (a.rows >= 2048) ? launch_score_t<KIND, 256, 2>(ctx, a, ntiles)
-                                  : launch_score_t<KIND, 128, 1>(ctx, a, ntiles);
-    }
-    if (rc) return rc;
-    resolve_queue_kernel<KIND><<<ctx->sm_count * 2, 256, 0, ctx->stream>>>(a);
-    M3D_LAUNCHED(ctx);
-    return M3D_OK;
+    return launch_one<KIND>(ctx, a, ntiles, cull);
 }
 
 int launch_score_kind(m3d_ctx *ctx, int kind, const m3d_cloud *c, const ScoreArgs &a, bool exact_only) {
@@ -485,6 +526,7 @@ int fit_view(m3d_ctx *ctx, int kind, const m3d_cloud *cloud_for_flags, const Clo
             a.pts32 = v.pts32;
             a.blob = (p.flags & M3D_FLAG_DENSE) ? nullptr : v.blob;
             a.perm = v.perm;
+            a.flags = p.flags;
             a.xyz = v.xyz;
             a.nrm = v.nrm;
             a.row_nrm = host_nrm ? ctx->d_rownrm.as<double>() : nullptr;
@@ -715,6 +757,7 @@ int m3d_score_samples(m3d_ctx *ctx, int kind, const m3d_cloud *cloud, const uint
         a.blob = cloud->blob.as<float4>();
         a.perm = cloud->perm.as<uint32_t>();
     }
+    a.flags = flags;
     a.pts32 = cloud->pts32.as<float4>();
     a.xyz = cloud->xyz.as<double>();
     a.nrm = cloud->has_normals ? cloud->nrm.as<double>() : nullptr;

@@ -554,6 +554,12 @@ struct ScoreArgs {
     double thr;
     uint32_t n;
     uint32_t row_begin; /* first row of the wave buffer this launch scores             */
+    const uint32_t *row_map; /* optional: launch-local row -> row of the wave buffer (a subset of
+                              * [row_begin, ...) in any order); null = row_begin + local row           */
+    uint32_t flags;          /* M3D_FLAG_* of the call (host side only)                               */
+    /* row of the wave buffer (samples / row_nrm index) and index into `counts` of launch-local row r */
+    __device__ __forceinline__ uint32_t src_row(uint32_t r) const { return row_map ? row_map[r] : row_begin + r; }
+    __device__ __forceinline__ uint32_t cnt_row(uint32_t r) const { return row_map ? row_map[r] - row_begin : r; }
     uint32_t rows;      /* number of rows this launch scores                           */
     uint32_t chunk_tiles;    /* score_exact_kernel only */
     uint32_t *tile_counter;  /* [hypothesis blocks] next unclaimed tile (zeroed before the launch) */
@@ -597,14 +603,14 @@ __device__ __forceinline__ void rescan_warp(const ScoreArgs &a, unsigned need, u
                 a.queue[pos] = make_uint2(r, (gbase + lane) | (prov << 31));
             } else { /* queue full: decide here with the reference arithmetic */
                 double m[8];
-                const bool ok = fit_row<KIND>(a.xyz, a.nrm, a.samples, a.row_begin + r, m, a.row_nrm);
+                const bool ok = fit_row<KIND>(a.xyz, a.nrm, a.samples, a.src_row(r), m, a.row_nrm);
                 uint32_t in = 0;
                 if (ok) {
                     ex::Dist<KIND> dist;
                     dist.set(m);
                     in = dist(ex::ld3(a.xyz + 3 * (size_t)(gbase + lane))) < a.thr ? 1u : 0u;
                 }
-                if (in != prov) atomicAdd(&a.counts[r], in - prov);
+                if (in != prov) atomicAdd(&a.counts[a.cnt_row(r)], in - prov);
             }
         }
     }
@@ -626,7 +632,7 @@ __global__ void __launch_bounds__(256) resolve_queue_kernel(const ScoreArgs a) {
         ex::Dist<KIND> dist;
         dist.set(m);
         const uint32_t in = (dist(ex::ld3(a.xyz + 3 * (size_t)pt)) < a.thr) ? 1u : 0u;
-        if (in != prov) atomicAdd(&a.counts[e.x], in - prov); /* +1 or -1 (mod 2^32) */
+        if (in != prov) atomicAdd(&a.counts[a.cnt_row(e.x)], in - prov); /* +1 or -1 (mod 2^32) */
     }
 }
 
@@ -691,7 +697,7 @@ __global__ void __launch_bounds__(THREADS + 32) score_kernel(const ScoreArgs a) 
         row[h] = (blockIdx.x * HPT + h) * THREADS + tid;
         double m[8];
         bool ok = false;
-        if (row[h] < a.rows) ok = fit_row<KIND>(a.xyz, a.nrm, a.samples, a.row_begin + row[h], m, a.row_nrm);
+        if (row[h] < a.rows) ok = fit_row<KIND>(a.xyz, a.nrm, a.samples, a.src_row(row[h]), m, a.row_nrm);
         invalid[h] = (row[h] < a.rows) && !ok;
         if (blockIdx.y == 0 && row[h] < a.rows) {
 #pragma unroll
@@ -771,8 +777,9 @@ __global__ void __launch_bounds__(THREADS + 32) score_kernel(const ScoreArgs a) 
 #pragma unroll
     for (int h = 0; h < HPT; ++h) {
         if (row[h] < a.rows) {
-            if (clo[h]) atomicAdd(&a.counts[row[h]], clo[h]);
-            if (invalid[h] && blockIdx.y == 0) atomicOr(&a.counts[row[h]], kInvalidBit);
+            const uint32_t ci = a.cnt_row(row[h]);
+            if (clo[h]) atomicAdd(&a.counts[ci], clo[h]);
+            if (invalid[h] && blockIdx.y == 0) atomicOr(&a.counts[ci], kInvalidBit);
         }
     }
     if (nres) atomicAdd(a.resolves, (unsigned long long)nres);
@@ -788,20 +795,20 @@ __global__ void __launch_bounds__(128) score_exact_kernel(const ScoreArgs a) {
     (void)ntiles;
     if (row >= a.rows) return;
     double m[8];
-    const bool ok = fit_row<KIND>(a.xyz, a.nrm, a.samples, a.row_begin + row, m, a.row_nrm);
+    const bool ok = fit_row<KIND>(a.xyz, a.nrm, a.samples, a.src_row(row), m, a.row_nrm);
     if (blockIdx.y == 0) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) a.models[(size_t)row * 8 + i] = (ok && i < param_count(KIND)) ? m[i] : 0.0;
     }
     if (!ok) {
-        if (blockIdx.y == 0) atomicOr(&a.counts[row], kInvalidBit);
+        if (blockIdx.y == 0) atomicOr(&a.counts[a.cnt_row(row)], kInvalidBit);
         return;
     }
     ex::Dist<KIND> dist;
     dist.set(m);
     uint32_t c = 0;
     for (uint32_t i = p0; i < p1; ++i) c += (dist(ex::ld3(a.xyz + 3 * (size_t)i)) < a.thr) ? 1u : 0u;
-    if (c) atomicAdd(&a.counts[row], c);
+    if (c) atomicAdd(&a.counts[a.cnt_row(row)], c);
     atomicAdd(a.resolves, (unsigned long long)(p1 - p0));
 }
 

@@ -382,14 +382,14 @@ __global__ void __launch_bounds__(THREADS + 32, (THREADS >= 256 ? 2 : 4)) score_
                 } else { /* queue full: decide here with the reference arithmetic */
                     const uint32_t prov = e.y >> 31, pt = a.perm[e.y & 0x7fffffffu];
                     double m[8];
-                    const bool ok = fit_row<KIND>(a.xyz, a.nrm, a.samples, a.row_begin + e.x, m, a.row_nrm);
+                    const bool ok = fit_row<KIND>(a.xyz, a.nrm, a.samples, a.src_row(e.x), m, a.row_nrm);
                     uint32_t in = 0;
                     if (ok) {
                         ex::Dist<KIND> dist;
                         dist.set(m);
                         in = dist(ex::ld3(a.xyz + 3 * (size_t)pt)) < a.thr ? 1u : 0u;
                     }
-                    if (in != prov) atomicAdd(&a.counts[e.x], in - prov);
+                    if (in != prov) atomicAdd(&a.counts[a.cnt_row(e.x)], in - prov);
                 }
             }
             qn = 0;
@@ -403,7 +403,7 @@ __global__ void __launch_bounds__(THREADS + 32, (THREADS >= 256 ? 2 : 4)) score_
         row[h] = (blockIdx.x * HPT + h) * THREADS + tid;
         double m[8];
         bool ok = false;
-        if (row[h] < a.rows) ok = fit_row<KIND>(a.xyz, a.nrm, a.samples, a.row_begin + row[h], m, a.row_nrm);
+        if (row[h] < a.rows) ok = fit_row<KIND>(a.xyz, a.nrm, a.samples, a.src_row(row[h]), m, a.row_nrm);
         invalid[h] = (row[h] < a.rows) && !ok;
         if (blockIdx.y == 0 && row[h] < a.rows) {
 #pragma unroll
@@ -529,11 +529,57 @@ __global__ void __launch_bounds__(THREADS + 32, (THREADS >= 256 ? 2 : 4)) score_
     for (int h = 0; h < HPT; ++h) {
         if (row[h] < a.rows) {
             const uint32_t c = scnt[h * THREADS + tid];
-            if (c) atomicAdd(&a.counts[row[h]], c);
-            if (invalid[h] && blockIdx.y == 0) atomicOr(&a.counts[row[h]], kInvalidBit);
+            const uint32_t ci = a.cnt_row(row[h]);
+            if (c) atomicAdd(&a.counts[ci], c);
+            if (invalid[h] && blockIdx.y == 0) atomicOr(&a.counts[ci], kInvalidBit);
         }
     }
     if (nres) atomicAdd(a.resolves, (unsigned long long)nres);
+}
+
+/* ------------------------------------------------------------------------- hypothesis classification
+ * Culling cannot remove pairs that are inliers: a hypothesis whose shell passes through most of the cloud
+ * (e.g. THE dominant plane of the scene) is cheaper in the dense kernel, where one point load serves 32-64
+ * hypotheses.  For large waves one thread per hypothesis estimates the fraction of cells that would survive
+ * (every `stride`-th tile: tile sphere, then its 32 cell spheres) and files the row in the front (cull) or
+ * back (dense) part of `row_map`.  The order inside the two parts is whatever the atomics give; counts do
+ * not depend on it.  part[0] = rows for the culling kernel, part[1] = rows for the dense kernel. */
+template <int KIND>
+__global__ void __launch_bounds__(128) cull_classify_kernel(const ScoreArgs a, uint32_t ntiles, uint32_t stride,
+                                                            float dense_above, uint32_t *__restrict__ row_map,
+                                                            uint32_t *__restrict__ part) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = r < a.rows;
+    const CloudMeta M = *a.meta;
+    double m[8];
+    bool ok = false;
+    if (active) ok = fit_row<KIND>(a.xyz, a.nrm, a.samples, a.row_begin + r, m, a.row_nrm);
+    Fast<KIND> f;
+    CullP ck;
+    make_fast<KIND>(m, ok, M, a.thr, f);
+    make_cull<KIND>(f, m, M, a.thr, ck);
+    uint32_t seen = 0, kept = 0;
+    for (uint32_t t = (r % stride); t < ntiles; t += stride) { /* staggered so that a warp covers all tiles */
+        const float4 *tb = a.blob + (size_t)t * kBlobF4 + kTile;
+        seen += kTileCells;
+        if (cull_test<KIND>(f.c, ck, tb[kTileCells])) continue;
+#pragma unroll 4
+        for (int c = 0; c < kTileCells; ++c) kept += cull_test<KIND>(f.c, ck, tb[c]) ? 0u : 1u;
+    }
+    const bool dense = active && seen && ((float)kept > dense_above * (float)seen);
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const unsigned md = __ballot_sync(full, dense), mc = __ballot_sync(full, active && !dense);
+    uint32_t bd = 0, bc = 0;
+    if (lane == 0) {
+        if (md) bd = atomicAdd(&part[1], (uint32_t)__popc(md));
+        if (mc) bc = atomicAdd(&part[0], (uint32_t)__popc(mc));
+    }
+    bd = __shfl_sync(full, bd, 0);
+    bc = __shfl_sync(full, bc, 0);
+    const unsigned lt = (1u << lane) - 1;
+    if (dense) row_map[a.rows - 1 - (bd + __popc(md & lt))] = a.row_begin + r;
+    if (active && !dense) row_map[bc + __popc(mc & lt)] = a.row_begin + r;
 }
 
 }  // namespace m3d

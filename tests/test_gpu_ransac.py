@@ -341,3 +341,30 @@ def test_cull_kernel_randomized(ctx, capi, seed):
         c_exact, _, _ = ctx.score_samples(kind, cloud, table, thr, flags=capi.FLAG_EXACT_ONLY, want_models=False)
         np.testing.assert_array_equal(c_cull, c_exact, err_msg=f"seed {seed} kind {kind} n {len(xyz)} scale {scale} thr {thr}")
     cloud.free()
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_classified_split_counts_equal_exact(ctx, capi, orc, kind):
+    """M3D_FLAG_CLASSIFY: hypotheses whose shell passes through much of the cloud go to the dense kernel, the
+    rest to the culling kernel (what large waves do by default); the counts are those of the fp64 kernel.
+    The C1-style cloud (70 % of the points on one plane) makes the dense part non-trivial."""
+    for name, (xyz, nrm) in {"c1": (synth.make_c1(n=60000, seed=3), None), "c2": synth.make_c2(n=60000, seed=4)}.items():
+        if nrm is None:
+            rng = np.random.default_rng(1)
+            nrm = rng.normal(size=xyz.shape)
+            nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
+        table = capi.sample_table(21 + kind, len(xyz), capi.KSAMPLE[kind], 3000)
+        cloud = ctx.upload(xyz, nrm)
+        c_split, m_split, v_split = ctx.score_samples(kind, cloud, table, 0.01, flags=capi.FLAG_CLASSIFY)
+        c_exact, m_exact, v_exact = ctx.score_samples(kind, cloud, table, 0.01, flags=capi.FLAG_EXACT_ONLY)
+        np.testing.assert_array_equal(c_split, c_exact, err_msg=name)
+        np.testing.assert_array_equal(v_split, v_exact)
+        np.testing.assert_array_equal(m_split.view(np.uint64), m_exact.view(np.uint64))
+        cloud.free()
+    # a whole fit through the split path equals the oracle's
+    xyz = synth.make_c1(n=60000, seed=3)
+    if kind == 0:
+        rc, model, inl, st = ctx.ransac_fit(kind, xyz, None, 0.01, 3000, 1.0, seed=5, flags=capi.FLAG_CLASSIFY)
+        orc_rc, omodel, oinl, ost = orc.ransac_fit(kind, xyz, None, thr=0.01, max_it=3000, prob=1.0, seed=5)
+        assert rc == orc_rc and st["best_index"] == ost["best_index"] and st["best_count"] == ost["best_count"]
+        np.testing.assert_array_equal(inl, oinl)
