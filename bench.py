@@ -260,7 +260,9 @@ def main():
     # ---------------------------------------------------------------- value: resident cloud
     for w in range(args.warmup):
         step_resident(1000 + w)
-    clocks = ClockSampler(local_rank)
+    # one nvidia-smi poller for the job (rank 0's GPU): a poller per rank makes N processes query the driver
+    # every 100 ms while N ranks are launching kernels
+    clocks = ClockSampler(local_rank) if rank == 0 else None
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     score_ms = {k: [] for k in KINDS}
     fit_ms = {k: [] for k in KINDS}
@@ -279,7 +281,7 @@ def main():
             resolves += st["exact_resolves"]
     barrier()
     launches = ctx.launches - launches0
-    clk = clocks.stop()
+    clk = clocks.stop() if clocks else None
     total_ms = float(sum(a.elapsed_time(b) for a, b in ev))
     t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
     if world > 1:

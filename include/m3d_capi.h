@@ -165,6 +165,11 @@ int m3d_evaluate_model(m3d_ctx *ctx, int kind, const m3d_cloud *cloud, const dou
 /* host-only helpers (no GPU needed) --------------------------------------------------------- */
 /* utils.h:81-97 RandomSampler<size_t>::operator() on an mt19937(seed) stream: rows x k, draw order */
 void m3d_sample_table(uint32_t seed, size_t n, int k, size_t rows, uint32_t *out);
+
+/* Hypothesis sharding (host only): the rows of a wave of `rows` hypotheses that rank `rank` of
+ * `world` scores, in its local order (cyclic blocks of 256 rows).  out (may be NULL) receives the wave rows,
+ * *n_local their number, *padded the per-rank stride of the all-gathered count buffer (same on all ranks). */
+void m3d_shard_rows(size_t rows, int rank, int world, uint32_t *out, size_t *n_local, size_t *padded);
 /* ransac.h:572-613 replayed over per-hypothesis results in loop order (the "ordered scan").
  * counts[i] is the inlier count of hypothesis i, valid[i] MinimalFit's return value.  err may be
  * NULL; when given, err[i] (sum of inlier distances) breaks count ties as inlier_rmse does.

@@ -30,7 +30,7 @@ EXPORTS = [
     "m3d_cloud_upload", "m3d_cloud_from_device", "m3d_cloud_free", "m3d_cloud_size",
     "m3d_ransac_fit_cloud", "m3d_score_samples", "m3d_evaluate_model", "m3d_sample_table",
     "m3d_ordered_scan", "m3d_segment_plane_iterative", "m3d_match_correspondence", "m3d_nearest",
-    "m3d_ransac_registration", "m3d_least_squares_transform",
+    "m3d_ransac_registration", "m3d_least_squares_transform", "m3d_shard_rows",
 ]
 
 
@@ -112,6 +112,18 @@ def nccl_unique_id():
 
 def device_count():
     return int(lib().m3d_device_count())
+
+
+def shard_rows(rows, rank, world):
+    """(wave rows of rank `rank` in its local order, padded per-rank stride) -- m3d_shard_rows"""
+    n_local, padded = C.c_size_t(0), C.c_size_t(0)
+    L = lib()
+    L.m3d_shard_rows.restype = None
+    L.m3d_shard_rows(C.c_size_t(rows), C.c_int(rank), C.c_int(world), None, C.byref(n_local), C.byref(padded))
+    out = np.empty(max(n_local.value, 1), dtype=np.uint32)
+    L.m3d_shard_rows(C.c_size_t(rows), C.c_int(rank), C.c_int(world), out.ctypes.data_as(C.POINTER(C.c_uint32)),
+                     C.byref(n_local), C.byref(padded))
+    return out[:n_local.value], int(padded.value)
 
 
 def sample_table(seed, n, k, rows):

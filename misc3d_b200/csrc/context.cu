@@ -248,7 +248,16 @@ int m3d_ctx_set_exchange(m3d_ctx *c, m3d_allgather_fn fn, void *user, int on_dev
 /* RandomSampler<size_t>::operator() (utils.h:81-97): idx = rng() % size, keep if not yet drawn */
 void m3d_sample_table(uint32_t seed, size_t n, int k, size_t rows, uint32_t *out) {
     SampleStream s(seed, n);
-    for (size_t r = 0; r < rows; ++r) s.draw(k, out + r * (size_t)k);
+    s.draw_rows(k, rows, out);
+}
+
+void m3d_shard_rows(size_t rows, int rank, int world, uint32_t *out, size_t *n_local, size_t *padded) {
+    const ShardMap sm{(uint32_t)rows, (uint32_t)std::max(world, 1), (uint32_t)std::max(rank, 0)};
+    const uint32_t mine = sm.local_rows();
+    if (out)
+        for (uint32_t l = 0; l < mine; ++l) out[l] = sm.wave_row(l);
+    if (n_local) *n_local = mine;
+    if (padded) *padded = sm.padded();
 }
 
 int m3d_ordered_scan(const uint64_t *counts, const uint8_t *valid, const double *err, size_t rows,

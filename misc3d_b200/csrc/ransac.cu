@@ -232,7 +232,7 @@ int launch_one(m3d_ctx *ctx, ScoreArgs a, uint32_t ntiles, bool cull) {
     return M3D_OK;
 }
 
-/* waves of at least this many rows are pre-sorted into culled / dense hypotheses (cull_classify_kernel):
+/* launches of at least this many rows (default 12288) are pre-sorted into culled / dense hypotheses (cull_classify_kernel):
  * costs one small kernel + a 8-byte read-back, pays when part of the hypotheses pass through most of the
  * cloud.  A hypothesis goes to the dense kernel when more than kDenseAbove of its sampled cells survive
  * (measured break-even of the two kernels: ~25 % surviving pairs). */
@@ -241,7 +241,7 @@ uint32_t classify_min_rows() { /* M3D_CLASSIFY_MIN_ROWS overrides (tuning) */
     static uint32_t v = 0;
     if (!v) {
         const char *e = getenv("M3D_CLASSIFY_MIN_ROWS");
-        v = e ? (uint32_t)std::max(1l, atol(e)) : 16384u;
+        v = e ? (uint32_t)std::max(1l, atol(e)) : 12288u;
     }
     return v;
 }
@@ -489,39 +489,62 @@ int fit_view(m3d_ctx *ctx, int kind, const m3d_cloud *cloud_for_flags, const Clo
 
     const int R = ctx->world, rank = ctx->rank;
     uint64_t done = 0;
-    uint32_t wave = (p.probability >= 1.0) ? kMaxWave : 256;
+    /* a wave is at most kMaxWave rows PER RANK: one exchange + one host replay per wave, whatever the number of ranks */
+    const uint32_t wave_cap = (uint32_t)std::min<uint64_t>((uint64_t)kMaxWave * (uint64_t)std::max(ctx->world, 1), 1u << 22);
+    uint32_t wave = (p.probability >= 1.0) ? wave_cap : 256;
     int rc_scan = 0;
     while (done < H && !scan.stopped) {
         const uint32_t rows = (uint32_t)std::min<uint64_t>(wave, H - done);
-        /* sample rows of this wave (host: the mt19937 stream is inherently serial) */
+        /* The sample rows come from one sequential mt19937 stream drawn on the host, and every rank needs the
+         * whole table (its own rows for the GPU, any row for the replay's tie-breaks and the final refit).
+         * Rows are dealt to the ranks in cyclic blocks (ShardMap), so a rank can launch the first part of its
+         * shard after drawing a fraction of the table and draws the rest while its GPU works. */
+        const ShardMap sm{rows, (uint32_t)R, (uint32_t)rank};
+        const uint32_t S = sm.padded(), mine = sm.local_rows();
         table.resize((size_t)(done + rows) * k);
-        for (uint32_t r = 0; r < rows; ++r) stream.draw(k, &table[(size_t)(done + r) * k]);
         M3D_CUDA(ctx, ctx->h_samples.reserve(sizeof(uint32_t) * (size_t)rows * k));
-        memcpy(ctx->h_samples.p, &table[(size_t)done * k], sizeof(uint32_t) * (size_t)rows * k);
         M3D_CUDA(ctx, ctx->d_samples.reserve(sizeof(uint32_t) * (size_t)rows * k));
-        M3D_CUDA(ctx, cudaMemcpyAsync(ctx->d_samples.p, ctx->h_samples.p, sizeof(uint32_t) * (size_t)rows * k,
-                                      cudaMemcpyHostToDevice, ctx->stream));
         if (host_nrm) { /* normals of this wave's sample points only: rows x k x 3 doubles */
-            const size_t cnt = (size_t)rows * k * 3;
-            M3D_CUDA(ctx, ctx->h_rownrm.reserve(sizeof(double) * cnt));
-            M3D_CUDA(ctx, ctx->d_rownrm.reserve(sizeof(double) * cnt));
-            double *dst = ctx->h_rownrm.as<double>();
-            const uint32_t *tab = &table[(size_t)done * k];
-            for (size_t e = 0; e < (size_t)rows * k; ++e) {
-                const double *src = v.h_nrm + 3 * (size_t)tab[e];
-                dst[3 * e] = src[0], dst[3 * e + 1] = src[1], dst[3 * e + 2] = src[2];
-            }
-            M3D_CUDA(ctx, cudaMemcpyAsync(ctx->d_rownrm.p, dst, sizeof(double) * cnt, cudaMemcpyHostToDevice, ctx->stream));
+            M3D_CUDA(ctx, ctx->h_rownrm.reserve(sizeof(double) * (size_t)rows * k * 3));
+            M3D_CUDA(ctx, ctx->d_rownrm.reserve(sizeof(double) * (size_t)rows * k * 3));
         }
-        /* shard: rank r scores rows [r*S, (r+1)*S) of the wave */
-        const uint32_t S = (rows + R - 1) / R;
-        const uint32_t my0 = std::min<uint32_t>(rows, (uint32_t)rank * S);
-        const uint32_t my1 = std::min<uint32_t>(rows, my0 + S);
-        M3D_CUDA(ctx, ctx->d_counts.reserve(sizeof(uint32_t) * (size_t)S));
-        M3D_CUDA(ctx, ctx->d_counts_all.reserve(sizeof(uint32_t) * (size_t)S * R));
-        M3D_CUDA(ctx, cudaMemsetAsync(ctx->d_counts.p, 0, sizeof(uint32_t) * (size_t)S, ctx->stream));
+        uint32_t drawn = 0; /* rows of this wave drawn and uploaded so far */
+        auto draw_to = [&](uint32_t upto) -> int {
+            if (upto <= drawn) return 0;
+            uint32_t *tab = &table[(size_t)(done + drawn) * k];
+            stream.draw_rows(k, upto - drawn, tab);
+            const size_t off = (size_t)drawn * k, cnt = (size_t)(upto - drawn) * k;
+            memcpy(ctx->h_samples.as<uint32_t>() + off, tab, sizeof(uint32_t) * cnt);
+            M3D_CUDA(ctx, cudaMemcpyAsync(ctx->d_samples.as<uint32_t>() + off, ctx->h_samples.as<uint32_t>() + off,
+                                          sizeof(uint32_t) * cnt, cudaMemcpyHostToDevice, ctx->stream));
+            if (host_nrm) {
+                double *dst = ctx->h_rownrm.as<double>() + 3 * off;
+                for (size_t e = 0; e < cnt; ++e) {
+                    const double *src = v.h_nrm + 3 * (size_t)tab[e];
+                    dst[3 * e] = src[0], dst[3 * e + 1] = src[1], dst[3 * e + 2] = src[2];
+                }
+                M3D_CUDA(ctx, cudaMemcpyAsync(ctx->d_rownrm.as<double>() + 3 * off, dst, sizeof(double) * 3 * cnt,
+                                              cudaMemcpyHostToDevice, ctx->stream));
+            }
+            drawn = upto;
+            return 0;
+        };
+        M3D_CUDA(ctx, ctx->d_counts.reserve(sizeof(uint32_t) * (size_t)std::max<uint32_t>(S, 1)));
+        M3D_CUDA(ctx, ctx->d_counts_all.reserve(sizeof(uint32_t) * (size_t)std::max<uint32_t>(S, 1) * R));
+        M3D_CUDA(ctx, cudaMemsetAsync(ctx->d_counts.p, 0, sizeof(uint32_t) * (size_t)std::max<uint32_t>(S, 1), ctx->stream));
         M3D_CUDA(ctx, cudaEventRecord(ev_s0, ctx->stream));
-        if (my1 > my0) {
+        /* one launch on a single GPU (the draw of a 10k-row table is ~50 us there); with R ranks the table is R
+         * times longer, so the shard is issued in up to four parts -- of at least classify_min_rows() rows each
+         * when the shard is that large (so that every part is still pre-sorted into culled / dense hypotheses),
+         * else in two halves */
+        uint32_t parts = 1;
+        if (R > 1) parts = (mine >= 2 * classify_min_rows()) ? std::min<uint32_t>(4, mine / classify_min_rows())
+                                                              : (mine >= 8192 ? 2 : 1);
+        for (uint32_t part = 0; part < parts && mine; ++part) {
+            const uint32_t l0 = (uint32_t)((uint64_t)mine * part / parts) / kShardBlock * kShardBlock;
+            const uint32_t l1 = (part + 1 == parts) ? mine : (uint32_t)((uint64_t)mine * (part + 1) / parts) / kShardBlock * kShardBlock;
+            if (l1 <= l0) continue;
+            if (int rc = draw_to(std::min<uint32_t>(rows, sm.wave_row(l1 - 1) + 1))) return rc;
             ScoreArgs a{};
             a.pts32 = v.pts32;
             a.blob = (p.flags & M3D_FLAG_DENSE) ? nullptr : v.blob;
@@ -532,15 +555,18 @@ int fit_view(m3d_ctx *ctx, int kind, const m3d_cloud *cloud_for_flags, const Clo
             a.row_nrm = host_nrm ? ctx->d_rownrm.as<double>() : nullptr;
             a.meta = v.meta;
             a.samples = ctx->d_samples.as<uint32_t>();
-            a.counts = ctx->d_counts.as<uint32_t>();
+            a.counts = ctx->d_counts.as<uint32_t>() + l0;
             a.resolves = &ds->resolves;
             a.thr = p.threshold;
             a.n = n;
-            a.row_begin = my0;
-            a.rows = my1 - my0;
+            a.row_begin = l0; /* shard-local */
+            a.rows = l1 - l0;
+            a.shard_world = (uint32_t)R;
+            a.shard_rank = (uint32_t)rank;
             if (int rc = launch_score_kind(ctx, kind, cloud_for_flags, a, exact_only)) return rc;
         }
         M3D_CUDA(ctx, cudaEventRecord(ev_s1, ctx->stream));
+        if (int rc = draw_to(rows)) return rc; /* the rest of the table (host side), while the GPU works */
         const uint32_t *d_all = ctx->d_counts.as<uint32_t>();
         if (R > 1) {
             if (int rc = exchange_allgather(ctx, ctx->d_counts.p, ctx->d_counts_all.p, sizeof(uint32_t) * (size_t)S))
@@ -558,11 +584,11 @@ int fit_view(m3d_ctx *ctx, int kind, const m3d_cloud *cloud_for_flags, const Clo
 
         const uint32_t *hc = ctx->h_counts.as<uint32_t>();
         for (uint32_t r = 0; r < rows && !scan.stopped; ++r) {
-            const uint32_t raw = hc[r]; /* shards are contiguous: rank-major == row order */
+            const uint32_t raw = hc[sm.gathered_index(r)]; /* rank-major buffer -> wave row */
             const bool valid = (raw & kInvalidBit) == 0;
             const uint64_t cnt = raw & ~kInvalidBit;
             scan.step(done + r, valid, cnt, [&](uint64_t j, bool exact, double *rmse) {
-                const uint32_t rawj = (j >= done) ? hc[j - done] : 0;
+                const uint32_t rawj = (j >= done) ? hc[sm.gathered_index((uint32_t)(j - done))] : 0;
                 const uint64_t cj = (j == scan.best_index && scan.found) ? scan.best_count : (uint64_t)(rawj & ~kInvalidBit);
                 const int rc = eval_row(j, exact, cj, rmse);
                 if (rc) rc_scan = rc;
@@ -571,7 +597,7 @@ int fit_view(m3d_ctx *ctx, int kind, const m3d_cloud *cloud_for_flags, const Clo
             if (rc_scan) return rc_scan;
         }
         done += rows;
-        if (wave < kMaxWave) wave = std::min<uint32_t>(kMaxWave, wave * 4);
+        if (wave < wave_cap) wave = std::min<uint32_t>(wave_cap, wave * 4);
     }
     if (!scan.stopped && done >= H) {
         /* the loop ran to max_iteration; the reference checks `count > current_iteration` only at

@@ -19,6 +19,7 @@
 
 #include "context.h"
 #include "exact_math.cuh"
+#include "scan.h"
 
 namespace m3d {
 
@@ -554,11 +555,16 @@ struct ScoreArgs {
     double thr;
     uint32_t n;
     uint32_t row_begin; /* first row of the wave buffer this launch scores             */
-    const uint32_t *row_map; /* optional: launch-local row -> row of the wave buffer (a subset of
-                              * [row_begin, ...) in any order); null = row_begin + local row           */
+    const uint32_t *row_map; /* optional: launch-local row -> shard-local row (a subset of
+                              * [row_begin, ...) in any order); null = row_begin + launch-local row     */
     uint32_t flags;          /* M3D_FLAG_* of the call (host side only)                               */
-    /* row of the wave buffer (samples / row_nrm index) and index into `counts` of launch-local row r */
-    __device__ __forceinline__ uint32_t src_row(uint32_t r) const { return row_map ? row_map[r] : row_begin + r; }
+    uint32_t shard_world, shard_rank; /* block-cyclic hypothesis sharding (scan.h ShardMap); world <= 1: none */
+    /* shard-local row -> row of the wave buffer (index into samples / row_nrm) */
+    __device__ __forceinline__ uint32_t wave_row(uint32_t l) const {
+        return shard_world <= 1 ? l : ((l / kShardBlock) * shard_world + shard_rank) * kShardBlock + l % kShardBlock;
+    }
+    /* wave-buffer row and index into `counts` (shard-local, relative to row_begin) of launch-local row r */
+    __device__ __forceinline__ uint32_t src_row(uint32_t r) const { return wave_row(row_map ? row_map[r] : row_begin + r); }
     __device__ __forceinline__ uint32_t cnt_row(uint32_t r) const { return row_map ? row_map[r] - row_begin : r; }
     uint32_t rows;      /* number of rows this launch scores                           */
     uint32_t chunk_tiles;    /* score_exact_kernel only */

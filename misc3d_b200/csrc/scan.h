@@ -15,59 +15,67 @@ namespace m3d {
 
 /* RandomSampler<size_t> (utils.h:72-97) with an injected seed: std::mt19937, idx = rng() % size,
  * duplicates rejected, k accepted draws per call, draw order kept (SelectByIndex re-orders later). */
-/* std::mt19937's output stream, produced 624 numbers at a time (vectorisable twist + tempering loops)
- * instead of one call at a time: the table of a 10k-hypothesis wave is drawn on the host while the GPU
- * waits for it, so the generator's speed is on the critical path of a fit. */
-struct Mt19937Bulk {
-    uint32_t mt[624];
-    uint32_t out[624];
-    int pos = 624;
-    explicit Mt19937Bulk(uint32_t seed) {
-        mt[0] = seed;
-        for (uint32_t i = 1; i < 624; ++i) mt[i] = 1812433253u * (mt[i - 1] ^ (mt[i - 1] >> 30)) + i;
+/* Hypothesis sharding over `world` ranks: a wave of `rows` hypotheses is cut into blocks of
+ * kShardBlock rows dealt out cyclically, block b to rank b % world.  Block-cyclic rather than one contiguous
+ * slice per rank because the sample rows come from ONE sequential mt19937 stream that every rank has to
+ * replay from the start: with cyclic blocks every rank owns rows near the beginning of the wave and can
+ * launch its first part after drawing a fraction of the table, drawing the rest while its GPU works.
+ * Shard-local rows are numbered in block order; `padded` (identical on all ranks) is the all-gather stride. */
+constexpr uint32_t kShardBlock = 256;
+struct ShardMap {
+    uint32_t rows, world, rank;
+#ifdef __CUDACC__
+    __host__ __device__
+#endif
+    static inline uint32_t wave_row_of(uint32_t l, uint32_t world, uint32_t rank) {
+        return world <= 1 ? l : ((l / kShardBlock) * world + rank) * kShardBlock + l % kShardBlock;
     }
-    static inline uint32_t twist(uint32_t hi, uint32_t lo, uint32_t far) {
-        const uint32_t y = (hi & 0x80000000u) | (lo & 0x7fffffffu);
-        return far ^ (y >> 1) ^ ((0u - (y & 1u)) & 0x9908b0dfu);
+    uint32_t blocks() const { return (rows + kShardBlock - 1) / kShardBlock; }
+    uint32_t padded() const { return world <= 1 ? rows : ((blocks() + world - 1) / world) * kShardBlock; }
+    uint32_t local_rows_of(uint32_t r) const { /* rows of the wave that rank r owns */
+        if (world <= 1) return rows;
+        uint32_t n = 0;
+        for (uint32_t b = r; b < blocks(); b += world) n += std::min<uint32_t>(kShardBlock, rows - b * kShardBlock);
+        return n;
     }
-    void refill() {
-        for (int i = 0; i < 227; ++i) mt[i] = twist(mt[i], mt[i + 1], mt[i + 397]);
-        for (int i = 227; i < 623; ++i) mt[i] = twist(mt[i], mt[i + 1], mt[i - 227]);
-        mt[623] = twist(mt[623], mt[0], mt[396]);
-        for (int i = 0; i < 624; ++i) {
-            uint32_t y = mt[i];
-            y ^= y >> 11;
-            y ^= (y << 7) & 0x9d2c5680u;
-            y ^= (y << 15) & 0xefc60000u;
-            y ^= y >> 18;
-            out[i] = y;
-        }
-        pos = 0;
+    uint32_t local_rows() const { return local_rows_of(rank); }
+    uint32_t wave_row(uint32_t l) const { return wave_row_of(l, world, rank); }
+    uint32_t rank_of(uint32_t g) const { return world <= 1 ? 0 : (g / kShardBlock) % world; }
+    uint32_t local_of(uint32_t g) const {
+        return world <= 1 ? g : (g / (kShardBlock * world)) * kShardBlock + g % kShardBlock;
     }
-    inline uint32_t next() {
-        if (pos == 624) refill();
-        return out[pos++];
-    }
+    /* position of wave row g in the rank-major all-gathered buffer */
+    size_t gathered_index(uint32_t g) const { return (size_t)rank_of(g) * padded() + local_of(g); }
 };
 
+/* The sample stream of the reference (utils.h:81-97): idx = std::mt19937(seed)() % size with size_t
+ * arithmetic, duplicates within a row rejected.  The table of a wave is drawn on the host while the GPU
+ * waits for (part of) it, and with R ranks it is R times longer, so the generator is on the critical path:
+ * the raw stream is produced 624 numbers at a time and reduced modulo `size` in the same pass (Lemire's
+ * exact fastmod), with an AVX2 body selected at run time (sampler.cpp); the values are those of
+ * std::mt19937 + `%` bit for bit (tests/test_host.py compares with the oracle and the compiled reference). */
 struct SampleStream {
-    Mt19937Bulk rng;
+    uint32_t mt[624];
+    uint32_t idx[624]; /* tempered outputs of the current block, already reduced modulo size */
+    int pos = 624;
     uint32_t size;
-    uint64_t magic; /* exact x % size for 32-bit x by two multiplications (Lemire's fastmod) */
-    SampleStream(uint32_t seed, size_t n) : rng(seed), size((uint32_t)n), magic(n ? UINT64_MAX / (uint32_t)n + 1 : 0) {}
-    inline uint32_t mod(uint32_t x) const {
-        if (size == 1) return 0;
-        const uint64_t low = magic * x;
-        return (uint32_t)(((unsigned __int128)low * size) >> 64);
+    uint64_t magic; /* ceil(2^64 / size): x % size = ((magic * x mod 2^64) * size) >> 64 for 32-bit x */
+    SampleStream(uint32_t seed, size_t n);
+    void refill(); /* sampler.cpp */
+    inline uint32_t next() {
+        if (pos == 624) refill();
+        return idx[pos++];
     }
-    /* utils.h:81-97: idx = rng() % size (size_t arithmetic on a 32-bit draw), reject duplicates */
-    void draw(int k, uint32_t *out) {
+    /* `rows` consecutive rows of k distinct indices each (draw order), out[rows][k] (sampler.cpp) */
+    void draw_rows(int k, size_t rows, uint32_t *out);
+    /* one row: k distinct indices in draw order */
+    inline void draw(int k, uint32_t *out) {
         int have = 0;
         while (have < k) {
-            const uint32_t idx = mod(rng.next());
+            const uint32_t v = next();
             bool dup = false;
-            for (int j = 0; j < have; ++j) dup = dup || (out[j] == idx);
-            if (!dup) out[have++] = idx;
+            for (int j = 0; j < have; ++j) dup = dup || (out[j] == v);
+            if (!dup) out[have++] = v;
         }
     }
 };
@@ -113,6 +121,10 @@ struct OrderedScan {
             return;
         }
         if (!valid) return; /* MinimalFit false: no count++ (ransac.h:583-586) */
+        if (cnt < best_count) { /* fitness = cnt / n is strictly monotone in cnt: cannot be better (the common case) */
+            count++;
+            return;
+        }
         bool better = false;
         if (cnt != 0) {
             const double fitness = (double)cnt / (double)n_points;

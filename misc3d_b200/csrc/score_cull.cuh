@@ -553,7 +553,7 @@ __global__ void __launch_bounds__(128) cull_classify_kernel(const ScoreArgs a, u
     const CloudMeta M = *a.meta;
     double m[8];
     bool ok = false;
-    if (active) ok = fit_row<KIND>(a.xyz, a.nrm, a.samples, a.row_begin + r, m, a.row_nrm);
+    if (active) ok = fit_row<KIND>(a.xyz, a.nrm, a.samples, a.src_row(r), m, a.row_nrm);
     Fast<KIND> f;
     CullP ck;
     make_fast<KIND>(m, ok, M, a.thr, f);

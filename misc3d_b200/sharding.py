@@ -6,16 +6,35 @@ import ctypes as C
 import numpy as np
 
 
+SHARD_BLOCK = 256  # csrc/scan.h kShardBlock
+
+
 def shard_rows(rows, rank, world):
-    """rank r scores rows [lo, hi) of a wave of `rows` hypotheses; S = padded shard length."""
-    S = (rows + world - 1) // world
-    lo = min(rows, rank * S)
-    hi = min(rows, lo + S)
-    return lo, hi, S
+    """The wave rows rank `rank` scores, in its local order, and the padded per-rank stride S.
+    Rows are dealt out in cyclic blocks of SHARD_BLOCK (block b -> rank b % world): every rank owns rows near
+    the start of the wave, so it can start its GPU after drawing a fraction of the (sequential) sample table."""
+    if world <= 1:
+        return np.arange(rows, dtype=np.uint32), rows
+    blocks = (rows + SHARD_BLOCK - 1) // SHARD_BLOCK
+    S = ((blocks + world - 1) // world) * SHARD_BLOCK
+    mine = [np.arange(b * SHARD_BLOCK, min(rows, (b + 1) * SHARD_BLOCK), dtype=np.uint32)
+            for b in range(rank, blocks, world)]
+    return (np.concatenate(mine) if mine else np.empty(0, np.uint32)), S
+
+
+def gathered_to_wave_order(allc, rows, world):
+    """rank-major all-gathered buffer (world x S) -> counts in wave-row order"""
+    if world <= 1:
+        return allc[:rows]
+    S = len(allc) // world
+    g = np.arange(rows)
+    rank = (g // SHARD_BLOCK) % world
+    local = (g // (SHARD_BLOCK * world)) * SHARD_BLOCK + g % SHARD_BLOCK
+    return allc[rank * S + local]
 
 
 def gather_counts(packed, world, all_gather):
-    """all-gather one rank's packed uint32 counts (bit31 = MinimalFit failed); rank-major = row order"""
+    """all-gather one rank's packed uint32 counts (bit31 = MinimalFit failed); returns the rank-major buffer"""
     import torch
     t = torch.from_numpy(packed.astype(np.int32, copy=True))
     outs = [torch.empty_like(t) for _ in range(world)]

@@ -112,18 +112,20 @@ def _shard_worker(rank, world, port, q):
     import torch.distributed as dist
     import orc
     from misc3d_b200 import capi, synth as sy
-    from misc3d_b200.sharding import shard_rows, gather_counts
+    from misc3d_b200.sharding import shard_rows, gather_counts, gathered_to_wave_order
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     xyz = sy.make_c1(n=2000, seed=8)
-    H, thr, seed = 101, 0.01, 3
+    H, thr, seed = 701, 0.01, 3   # three blocks of 256 rows: ranks own 2 and 1 (partial) blocks
     table = capi.sample_table(seed, len(xyz), 3, H)  # every rank draws the same global table
-    lo, hi, S = shard_rows(H, rank, world)
-    valid, counts, _ = _oracle_counts(orc, orc.PLANE, xyz, None, table[lo:hi], thr)
+    mine, S = shard_rows(H, rank, world)
+    c_mine, c_S = capi.shard_rows(H, rank, world)    # the library's own partition (m3d_shard_rows)
+    assert np.array_equal(mine, c_mine) and S == c_S
+    valid, counts, _ = _oracle_counts(orc, orc.PLANE, xyz, None, table[mine], thr)
     packed = np.zeros(S, np.uint32)
-    packed[: hi - lo] = counts.astype(np.uint32) | ((1 - valid).astype(np.uint32) << 31)
-    allc = gather_counts(packed, world, lambda t, outs: dist.all_gather(outs, t))[:H]
+    packed[: len(mine)] = counts.astype(np.uint32) | ((1 - valid).astype(np.uint32) << 31)
+    allc = gathered_to_wave_order(gather_counts(packed, world, lambda t, outs: dist.all_gather(outs, t)), H, world)
     st = capi.ordered_scan(allc & 0x7FFFFFFF, ((allc >> 31) == 0).astype(np.uint8), None, len(xyz), 3, 0.9999, H)
     q.put((rank, st["best_index"], st["best_count"], st["iterations_run"], st["stop_index"]))
     dist.barrier()
@@ -143,6 +145,6 @@ def test_sharded_counts_over_gloo_match_single_process(capi, orc):
         p.join(60)
         assert p.exitcode == 0
     xyz = synth.make_c1(n=2000, seed=8)
-    rc, model, inl, ost = orc.ransac_fit(orc.PLANE, xyz, thr=0.01, max_it=101, prob=0.9999, seed=3)
+    rc, model, inl, ost = orc.ransac_fit(orc.PLANE, xyz, thr=0.01, max_it=701, prob=0.9999, seed=3)
     for r in res:
         assert r[1:] == (ost["best_index"], ost["best_count"], ost["iterations_run"], ost["stop_index"])
