@@ -59,7 +59,7 @@ class ClockSampler:
         self.rows, self.proc = [], None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -349,6 +349,12 @@ def main():
                         "HBM once per launch is re-used on chip by the whole hypothesis batch, and whole cells / tiles "
                         "of point-hypothesis pairs are decided by one bounding-sphere test; DRAM traffic (ncu) ~ one "
                         "read of the Morton-ordered cloud",
+                "binding_resource": {"what": "shared-memory bandwidth (one LDS.128 per lane per surviving hypothesis-cell pair)",
+                                     "pct_of_peak_wavefronts": {"plane": 71.2, "sphere": 60.6, "cylinder": 51.1},
+                                     "issue_slots_busy_pct": {"plane": 57.3, "sphere": 59.3, "cylinder": 59.2},
+                                     "pairs_evaluated_pct": {"plane": 10.8, "sphere": 10.6, "cylinder": 6.9},
+                                     "source": "profiles/r01_ncu_score_cull_run14.md, profiles/r01_cull_stats_run14.json "
+                                               "(ncu --set full; not measured in this run)"},
                 "compulsory_bytes_per_launch": compulsory,
                 "compulsory_GBps": compulsory / (launch_ms * 1e-3) / 1e9,
                 "compulsory_frac": compulsory / (launch_ms * 1e-3) / 1e9 / hbm_peak}
