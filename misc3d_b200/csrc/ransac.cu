@@ -532,7 +532,7 @@ int fit_view(m3d_ctx *ctx, int kind, const m3d_cloud *cloud_for_flags, const Clo
         M3D_CUDA(ctx, ctx->d_counts.reserve(sizeof(uint32_t) * (size_t)std::max<uint32_t>(S, 1)));
         M3D_CUDA(ctx, ctx->d_counts_all.reserve(sizeof(uint32_t) * (size_t)std::max<uint32_t>(S, 1) * R));
         M3D_CUDA(ctx, cudaMemsetAsync(ctx->d_counts.p, 0, sizeof(uint32_t) * (size_t)std::max<uint32_t>(S, 1), ctx->stream));
-        M3D_CUDA(ctx, cudaEventRecord(ev_s0, ctx->stream));
+        bool s0_recorded = false;
         /* one launch on a single GPU (the draw of a 10k-row table is ~50 us there); with R ranks the table is R
          * times longer, so the shard is issued in up to four parts -- of at least classify_min_rows() rows each
          * when the shard is that large (so that every part is still pre-sorted into culled / dense hypotheses),
@@ -545,6 +545,10 @@ int fit_view(m3d_ctx *ctx, int kind, const m3d_cloud *cloud_for_flags, const Clo
             const uint32_t l1 = (part + 1 == parts) ? mine : (uint32_t)((uint64_t)mine * (part + 1) / parts) / kShardBlock * kShardBlock;
             if (l1 <= l0) continue;
             if (int rc = draw_to(std::min<uint32_t>(rows, sm.wave_row(l1 - 1) + 1))) return rc;
+            if (!s0_recorded) { /* score_ms = the launches of the wave (the first part's table draw is not GPU time) */
+                M3D_CUDA(ctx, cudaEventRecord(ev_s0, ctx->stream));
+                s0_recorded = true;
+            }
             ScoreArgs a{};
             a.pts32 = v.pts32;
             a.blob = (p.flags & M3D_FLAG_DENSE) ? nullptr : v.blob;
@@ -565,6 +569,7 @@ int fit_view(m3d_ctx *ctx, int kind, const m3d_cloud *cloud_for_flags, const Clo
             a.shard_rank = (uint32_t)rank;
             if (int rc = launch_score_kind(ctx, kind, cloud_for_flags, a, exact_only)) return rc;
         }
+        if (!s0_recorded) M3D_CUDA(ctx, cudaEventRecord(ev_s0, ctx->stream)); /* a rank without rows in this wave */
         M3D_CUDA(ctx, cudaEventRecord(ev_s1, ctx->stream));
         if (int rc = draw_to(rows)) return rc; /* the rest of the table (host side), while the GPU works */
         const uint32_t *d_all = ctx->d_counts.as<uint32_t>();
