@@ -368,3 +368,16 @@ def test_classified_split_counts_equal_exact(ctx, capi, orc, kind):
         orc_rc, omodel, oinl, ost = orc.ransac_fit(kind, xyz, None, thr=0.01, max_it=3000, prob=1.0, seed=5)
         assert rc == orc_rc and st["best_index"] == ost["best_index"] and st["best_count"] == ost["best_count"]
         np.testing.assert_array_equal(inl, oinl)
+
+
+def test_large_wave_default_split_equals_dense(ctx, capi):
+    """a wave of >= 12288 rows is pre-sorted into culled / dense hypotheses by default (config C5's shape at
+    reduced size: 70 % of the points on one plane); counts equal the dense kernel's"""
+    xyz = synth.make_c1(n=300000, seed=12)
+    cloud = ctx.upload(xyz, None)
+    table = capi.sample_table(5, len(xyz), 3, 14000)
+    c_default, _, _ = ctx.score_samples(0, cloud, table, 0.01, want_models=False)
+    c_dense, _, _ = ctx.score_samples(0, cloud, table, 0.01, flags=capi.FLAG_DENSE, want_models=False)
+    np.testing.assert_array_equal(c_default, c_dense)
+    assert (c_default > 0.6 * len(xyz)).sum() > 1000   # many hypotheses ARE the dominant plane
+    cloud.free()

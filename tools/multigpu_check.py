@@ -25,7 +25,9 @@ sharded.init_nccl(ids[0], rank, world)
 xyz, nrm = synth.make_c2(n=200000, seed=9)
 ok = True
 for kind in (0, 1, 2):
-    for prob, H in ((0.9999, 3000), (1.0, 5000)):
+    # 5000 rows: one launch per rank; 20000 / 60000 rows: shards issued in parts (pipelined table draw) and,
+    # at 60000, pre-sorted into culled / dense hypotheses
+    for prob, H in ((0.9999, 3000), (1.0, 5000), (1.0, 20000)) + (((1.0, 60000),) if kind == 0 else ()):
         a = single.ransac_fit(kind, xyz, nrm if kind == 2 else None, 0.01, H, prob, seed=11)
         b = sharded.ransac_fit(kind, xyz, nrm if kind == 2 else None, 0.01, H, prob, seed=11)
         same = (a[0] == b[0] and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2]) and
