@@ -148,3 +148,42 @@ def test_sharded_counts_over_gloo_match_single_process(capi, orc):
     rc, model, inl, ost = orc.ransac_fit(orc.PLANE, xyz, thr=0.01, max_it=701, prob=0.9999, seed=3)
     for r in res:
         assert r[1:] == (ost["best_index"], ost["best_count"], ost["iterations_run"], ost["stop_index"])
+
+
+@pytest.mark.parametrize("rows,world", [(1, 1), (101, 2), (256, 2), (257, 3), (10000, 8), (80000, 8), (65536, 4),
+                                        (12345, 5), (511, 8)])
+def test_shard_map_is_a_partition(capi, rows, world):
+    """block-cyclic hypothesis sharding (csrc/scan.h ShardMap, m3d_shard_rows): the ranks' row lists partition
+    the wave, the python restatement agrees, shards are balanced to within one block, and the rank-major
+    all-gathered buffer maps back to wave order"""
+    from misc3d_b200.sharding import shard_rows, gathered_to_wave_order, SHARD_BLOCK
+    seen = np.zeros(rows, np.int32)
+    sizes, S0 = [], None
+    gathered = None
+    for r in range(world):
+        mine, S = capi.shard_rows(rows, r, world)
+        py_mine, py_S = shard_rows(rows, r, world)
+        assert np.array_equal(mine, py_mine) and S == py_S
+        S0 = S if S0 is None else S0
+        assert S == S0 and len(mine) <= S
+        seen[mine] += 1
+        sizes.append(len(mine))
+        if gathered is None:
+            gathered = np.full(world * S, -1, np.int64)
+        gathered[r * S: r * S + len(mine)] = mine          # each rank contributes "its rows" as payload
+    assert np.all(seen == 1)
+    assert max(sizes) - min(sizes) <= SHARD_BLOCK
+    assert np.array_equal(gathered_to_wave_order(gathered, rows, world), np.arange(rows))
+
+
+def test_sampler_blocks_avx2_equals_generic_and_std_mt19937(capi, orc):
+    """the block generator behind the sample tables (csrc/sampler.cpp): the run-time selected AVX2 body equals
+    the generic one, and the tables equal std::mt19937 + `%` (the oracle draws with <random>) including
+    duplicate rejection on tiny clouds and block boundaries"""
+    import ctypes as C
+    L = capi.lib()
+    for seed, n in ((1, 1000000), (2, 7), (3, 2**31 - 1), (4, 3), (5, 50000), (6, 1), (7, 2), (8, 4000000)):
+        assert L.m3d_sampler_selfcheck(C.c_uint32(seed), C.c_size_t(n), 100) == 1
+    for seed, n, k, rows in ((1, 1000000, 3, 30000), (5, 7, 4, 3000), (9, 3, 3, 500), (3, 50000, 2, 30000),
+                             (11, 4, 4, 2000), (13, 5, 2, 5000), (0, 4000000, 3, 100000)):
+        assert np.array_equal(capi.sample_table(seed, n, k, rows), orc.sample_table(seed, n, k, rows)), (seed, n, k)
