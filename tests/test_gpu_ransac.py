@@ -381,3 +381,62 @@ def test_large_wave_default_split_equals_dense(ctx, capi):
     np.testing.assert_array_equal(c_default, c_dense)
     assert (c_default > 0.6 * len(xyz)).sum() > 1000   # many hypotheses ARE the dominant plane
     cloud.free()
+
+
+def test_full_size_properties_c3(ctx, capi, orc):
+    """BASELINE config C3 size (2M points, six-plane scene): size-independent properties of the segmentation --
+    clusters disjoint, the stopping rule of iterative_plane_segmentation.cpp:28-29, the large clusters are faces
+    of the box, labelled points lie near their plane, the same result when run again -- and, since the
+    sequential oracle still finishes in seconds at this size, label-for-label equality with it."""
+    xyz = synth.make_c3()
+    n = len(xyz)
+    rc, planes, labels, ms = ctx.segment_plane_iterative(xyz, 0.01, 100, 0.05, seed=11)
+    assert rc == 0 and len(planes) >= 6
+    none = np.uint64(0xFFFFFFFFFFFFFFFF)
+    assigned = labels != none
+    sizes = np.array([int((labels == k).sum()) for k in range(len(planes))])
+    assert np.all(sizes > 0) and sizes.sum() == int(assigned.sum())
+    target = int((1 - 0.05) * n)                          # while (count < (size_t)((1 - min_ratio) * N))
+    assert sizes.sum() >= target and sizes[:-1].sum() < target
+    faces = set()
+    for k in range(len(planes)):
+        nrm, d = planes[k, :3], planes[k, 3]
+        assert abs(np.linalg.norm(nrm) - 1) < 1e-9
+        dist = np.abs(xyz[labels == k] @ nrm + d)
+        assert np.mean(dist < 0.012) > 0.9                # inliers of the minimal model vs the refitted plane
+        if sizes[k] > 0.05 * n:                           # a big cluster is (part of) a face of [-1, 1]^3
+            axis = int(np.argmax(np.abs(nrm)))
+            assert abs(abs(nrm[axis]) - 1) < 1e-3 and abs(abs(d) - 1) < 1e-2
+            faces.add((axis, int(np.sign(nrm[axis] * d))))
+    assert len(faces) == 6
+    rc2, planes2, labels2, _ = ctx.segment_plane_iterative(xyz, 0.01, 100, 0.05, seed=11)
+    np.testing.assert_array_equal(labels2, labels)
+    np.testing.assert_array_equal(planes2, planes)
+    orc_rc, oplanes, olabels = orc.segment_plane_iterative(xyz, 0.01, 100, 0.05, seed=11)
+    assert orc_rc == 0 and len(oplanes) == len(planes)
+    np.testing.assert_array_equal(labels, olabels)
+    np.testing.assert_allclose(planes, oplanes, rtol=1e-9, atol=1e-12)
+
+
+def test_full_size_properties_c5(ctx, capi):
+    """BASELINE config C5 size (4M points x 100k plane hypotheses, one GPU's view of it): the default path
+    (waves pre-sorted into culled / dense hypotheses) and the dense kernel agree on the winner, the winner's
+    count is the fp64 count of its minimal model, and the inlier list is exactly {d < thr} of that model."""
+    xyz = synth.make_c5()
+    cloud = ctx.upload(xyz, None)
+    rc, model, inl, st = ctx.ransac_fit_cloud(0, cloud, 0.01, 100000, 1.0, seed=1)
+    rc_d, model_d, inl_d, st_d = ctx.ransac_fit_cloud(0, cloud, 0.01, 100000, 1.0, seed=1, flags=capi.FLAG_DENSE)
+    assert rc == rc_d == 1
+    for key in ("best_index", "best_count", "iterations_run", "stop_index"):
+        assert st[key] == st_d[key], key
+    np.testing.assert_array_equal(inl, inl_d)
+    np.testing.assert_array_equal(model, model_d)
+    assert st["iterations_run"] <= 100000 and st["stop_index"] == 100000
+    table = capi.sample_table(1, len(xyz), 3, st["best_index"] + 1)
+    counts, models, valid = ctx.score_samples(0, cloud, table[-1:], 0.01, flags=capi.FLAG_EXACT_ONLY)
+    assert valid[0] == 1 and counts[0] == st["best_count"] == len(inl)
+    m = models[0]
+    d = np.abs((m[0] * xyz[:, 0] + m[2] * xyz[:, 2]) + (m[1] * xyz[:, 1] + m[3])) / np.sqrt(m[0] ** 2 + m[1] ** 2 + m[2] ** 2)
+    np.testing.assert_array_equal(np.nonzero(d < 0.01)[0], inl)
+    assert np.all(np.diff(inl.astype(np.int64)) > 0) and len(inl) > 0.69 * len(xyz)
+    cloud.free()
