@@ -269,8 +269,8 @@ __device__ unsigned long long g_cull_stats[8];
 #endif
 
 /* ------------------------------------------------------------------------------ the hot kernel */
-/* per-hypothesis parameters as the warp-uniform phases read them: kHypF4 float4 per hypothesis in
- * shared memory {c[0..3]} {c[4..7]}? {T, band, cull.a, cull.b} {cull.c, cull.d, -, -}? */
+/* per-hypothesis parameters in shared memory, kF4 float4 each, in the order the phases read them:
+ * {c[0..3]} [cylinder: {c[4..7]}] {T, band, cull.a, cull.b} [sphere, cylinder: {cull.c, cull.d, -, -}] */
 template <int KIND>
 struct HypLayout {
     static constexpr int kF4 = KIND == kPlane ? 2 : (KIND == kSphere ? 3 : 4);
@@ -293,7 +293,7 @@ __device__ __forceinline__ void load_hyp(const float4 *hp, Fast<KIND> &g, CullP 
     }
 }
 constexpr int kQBuf = 96; /* guard-band pairs a warp stages in shared memory before one global atomicAdd */
-constexpr int kListLen = kTileCells + 4; /* per-warp list of surviving cells (+ padding slot), 16 B aligned */
+constexpr int kListLen = kTileCells + 4; /* per-warp list of surviving cells (+ the padding slot), 16 B aligned */
 
 template <int KIND, int THREADS, int HPT>
 constexpr size_t cull_smem_bytes() {
