@@ -3,6 +3,8 @@
   python tools/score_sweep.py build      # compile the library variants (CPU box, nvcc)
   python tools/score_sweep.py run        # time every (library variant x launch variant x primitive)
   python tools/score_sweep.py one        # (internal) one configuration, JSON line on stdout
+  python tools/score_sweep.py raw        # wall clock of m3d_score_samples per primitive (10k hypotheses, C2 cloud);
+                                         # M3D_SCORE_PATH=dense / M3D_SCORE_VARIANT=256x4 / M3D_LIB=... select variants
 """
 import itertools
 import json
@@ -12,11 +14,10 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-LIBS = {  # name -> extra nvcc flags
-    "s32": "-DM3D_SUB=32",
-    "s64": "-DM3D_SUB=64",
-    "s128": "-DM3D_SUB=128",
-    "s256": "-DM3D_SUB=256",
+LIBS = {  # name -> extra nvcc flags (tuning builds land in misc3d_b200/variants/, select with M3D_LIB=...)
+    "scalar": "-DM3D_PACKED=0",        # dense kernel without the fp32x2 inner loop
+    "stats": "-DM3D_CULL_STATS",       # culling kernel with survival counters (tools/cull_stats.py)
+    "st3": "-DM3D_CULL_STAGES=3",      # ring depth of the culling kernel
 }
 LAUNCH = ["256x2", "128x2", "256x1", "128x4", "256x4", "128x1"]
 
