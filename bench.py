@@ -134,6 +134,36 @@ def calibrate(fit, xyz, cores, seconds_per_step):
     return int(min(H_PER_PRIM, max(cores, round(h / cores) * cores)))
 
 
+def pin_to_gpu_numa_node(local_rank):
+    """Opt-in (M3D_BENCH_PIN=1): restrict this rank to the CPUs of its GPU's NUMA node.  Every fit ends with an
+    exchange that waits for the slowest rank, so per-rank host latency jitter costs all ranks; torchrun does not
+    pin its workers.  Off by default until it has been measured on the 8-GPU box."""
+    try:
+        import torch
+        bdf = torch.cuda.get_device_properties(local_rank).pci_bus_id if hasattr(
+            torch.cuda.get_device_properties(local_rank), "pci_bus_id") else None
+        if bdf is None:
+            import pynvml
+            pynvml.nvmlInit()
+            bdf = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(local_rank)).busId
+            bdf = bdf.decode() if isinstance(bdf, bytes) else bdf
+        bdf = bdf.lower()
+        if len(bdf.split(":")[0]) == 8:      # nvml prints a 32-bit domain, sysfs a 16-bit one
+            bdf = bdf[4:]
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read())
+        if node < 0:
+            return
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if len(cpus) >= 2:
+            os.sched_setaffinity(0, cpus)
+    except Exception:
+        pass
+
+
 def reference_arm(args, rank, world):
     """The reference's own CPU implementation of the path on the host cores (see cpu_path): each step =
     a bounded sample of the C2 workload (H_cpu hypotheses per primitive on the full 1M-point cloud)."""
@@ -220,6 +250,8 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
+    if world > 1 and os.environ.get("M3D_BENCH_PIN") == "1":
+        pin_to_gpu_numa_node(local_rank)   # opt-in experiment (not measured yet): see the function
     xyz, nrm = synth.make_c2(N_POINTS, SEED)
     stream = torch.cuda.current_stream()
     ctx = capi.Context(local_rank, stream=stream.cuda_stream)
