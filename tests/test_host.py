@@ -187,3 +187,28 @@ def test_sampler_blocks_avx2_equals_generic_and_std_mt19937(capi, orc):
     for seed, n, k, rows in ((1, 1000000, 3, 30000), (5, 7, 4, 3000), (9, 3, 3, 500), (3, 50000, 2, 30000),
                              (11, 4, 4, 2000), (13, 5, 2, 5000), (0, 4000000, 3, 100000)):
         assert np.array_equal(capi.sample_table(seed, n, k, rows), orc.sample_table(seed, n, k, rows)), (seed, n, k)
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside the GPU arm): one JSON line with the
+    contract's keys, timed on the reference's own compiled sources when oracle/_ref is there"""
+    import json
+    import subprocess
+    import sys
+    env = dict(os.environ, OMP_NUM_THREADS="1")          # as under torchrun: the arm must ask for the cores itself
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                        "--warmup", "0"], capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
+                "scaling", "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert key in line, key
+    assert line["impl"] == "reference" and line["value"] > 0 and line["vs_baseline"] is None
+    assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline"]["cores"] >= 1
+    assert line["cpu_baseline"]["cores"] == len(os.sched_getaffinity(0))
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+    # a non-zero rank of a multi-rank launch prints nothing and exits 0
+    env2 = dict(env, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    r2 = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"],
+                        capture_output=True, text=True, timeout=120, env=env2)
+    assert r2.returncode == 0 and r2.stdout.strip() == ""
