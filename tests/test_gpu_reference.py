@@ -66,3 +66,20 @@ def test_matching_vs_reference_flann(ctx, refc, method):
     r0, r1 = refc.match_correspondence(d["src_feat"], d["dst_feat"], refc.FLANN)
     np.testing.assert_array_equal(i0, r0)
     np.testing.assert_array_equal(i1, r1)
+
+
+def test_real_scan_golden(ctx):
+    """real sensor data: every 4th vertex of the reference's demo scan (tests/golden/real_scan.npz holds the
+    input and the compiled reference's outputs for the demo's parameters, tools/make_golden.py)"""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "real_scan.npz"))
+    xyz = g["xyz"]
+    rc, model, inl, st = ctx.ransac_fit(0, xyz, None, 0.01, 100, 0.9999, 1)
+    assert rc == int(g["rc"]) and st["iterations_run"] == int(g["iterations_run"])
+    assert st["best_index"] == int(g["best_index"]) and st["best_count"] == int(g["best_count"])
+    np.testing.assert_array_equal(inl, g["inl"])
+    np.testing.assert_allclose(model, g["model"], rtol=1e-9, atol=1e-12)
+    rc, planes, labels, _ = ctx.segment_plane_iterative(xyz, 0.01, 100, 0.1, seed=3)
+    assert rc == 0 and len(planes) == len(g["planes"])
+    np.testing.assert_array_equal(labels.astype(np.int64), g["labels"])
+    np.testing.assert_allclose(planes, g["planes"], rtol=1e-9, atol=1e-12)

@@ -175,3 +175,18 @@ def test_golden_vectors(orc, name):
     np.testing.assert_array_equal(inl, g["inl"])
     for k in ("best_index", "best_count", "iterations_run", "stop_index"):
         assert st[k] == int(g[k]), k
+
+
+def test_golden_real_scan(orc):
+    """tests/golden/real_scan.npz: every 4th vertex of the reference's demo scan + the compiled reference's
+    outputs for the demo's parameters (tools/make_golden.py) -- real sensor data"""
+    g = np.load(os.path.join(GOLD, "real_scan.npz"))
+    xyz = g["xyz"]
+    rc, model, inl, st = orc.ransac_fit(orc.PLANE, xyz, thr=0.01, max_it=100, prob=0.9999, seed=1)
+    assert rc == int(g["rc"]) and st["iterations_run"] == int(g["iterations_run"])
+    np.testing.assert_array_equal(inl, g["inl"])
+    np.testing.assert_array_equal(model, g["model"])
+    rc, planes, labels = orc.segment_plane_iterative(xyz, 0.01, 100, 0.1, seed=3)
+    assert rc == 0
+    np.testing.assert_array_equal(planes, g["planes"])
+    np.testing.assert_array_equal(labels.astype(np.int64), g["labels"])

@@ -220,3 +220,32 @@ def test_fit_model_random_small_clouds(orc, refc, kind):
                 assert np.array_equal(bits(r[1]), bits(o[1])), (it, seed)
         done += 1
     assert done > 60
+
+
+def _reference_ply():
+    """examples/data/segmentation/test.ply of the reference (binary PLY, 40 458 x double xyz) -- the only real
+    input data of the path in the reference tree; read where it lies, never copied."""
+    import os
+    path = "/root/reference/examples/data/segmentation/test.ply"
+    if not os.path.exists(path):
+        pytest.skip("the reference tree is not mounted")
+    raw = open(path, "rb").read()
+    end = raw.index(b"end_header\n") + len(b"end_header\n")
+    n = int([ln for ln in raw[:end].decode().splitlines() if ln.startswith("element vertex")][0].split()[-1])
+    return np.frombuffer(raw, dtype="<f8", count=3 * n, offset=end).reshape(n, 3).copy()
+
+
+def test_real_scan_fit_and_segmentation(orc, refc):
+    """the reference's own demo input with the demo's parameters (examples/cpp/segment_plane_iterative.cpp:18:
+    threshold 0.01, 100 iterations, min_ratio 0.1): oracle == compiled reference on real sensor data"""
+    xyz = _reference_ply()
+    assert xyz.shape == (40458, 3) and np.all(np.isfinite(xyz))
+    for seed in (1, 2):
+        r = refc.ransac_fit(0, xyz, None, 0.01, 100, 0.9999, seed)
+        o = orc.ransac_fit(0, xyz, None, 0.01, 100, 0.9999, seed)
+        assert r[0] == o[0] == 1 and np.array_equal(r[2], o[2]) and np.array_equal(bits(r[1]), bits(o[1]))
+        assert r[3]["iterations_run"] == o[3]["iterations_run"]
+    npl, planes, labels = refc.segment_plane_iterative(xyz, 0.01, 100, 0.1, 3)
+    rc, oplanes, olabels = orc.segment_plane_iterative(xyz, 0.01, 100, 0.1, seed=3)
+    assert rc == 0 and npl == len(oplanes) >= 1
+    assert np.array_equal(labels, olabels) and np.array_equal(bits(planes), bits(oplanes))

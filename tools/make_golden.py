@@ -63,4 +63,21 @@ rc, T, st = orc.ransac_registration(d["src"], d["dst"], i0, i1, thr=0.02, max_it
 np.savez_compressed(os.path.join(OUT, "reg_small.npz"), i0=i0, i1=i1, T=T, best_index=st["best_index"],
                     best_count=st["best_count"], best_rmse=st["best_rmse"], evaluated=st["evaluated"],
                     stop_index=st["stop_index"])
+# real sensor data: every 4th vertex of the reference's demo scan (examples/data/segmentation/test.ply, binary PLY,
+# double xyz) with the demo's parameters (examples/cpp/segment_plane_iterative.cpp:18); input + the compiled
+# reference's outputs travel as one small fixture
+ply = os.path.join(refc.REFERENCE_ROOT, "examples", "data", "segmentation", "test.ply")
+if os.path.exists(ply):
+    raw = open(ply, "rb").read()
+    end = raw.index(b"end_header\n") + len(b"end_header\n")
+    nv = int([ln for ln in raw[:end].decode().splitlines() if ln.startswith("element vertex")][0].split()[-1])
+    scan = np.frombuffer(raw, dtype="<f8", count=3 * nv, offset=end).reshape(nv, 3)[::4].copy()
+    r_rc, r_model, r_inl, st = ref_fit(orc.PLANE, scan, None, thr=0.01, max_it=100, prob=0.9999, seed=1)
+    npl, planes, labels = refc.segment_plane_iterative(scan, 0.01, 100, 0.1, 3)
+    rc, oplanes, olabels = orc.segment_plane_iterative(scan, 0.01, 100, 0.1, seed=3)
+    assert rc == 0 and np.array_equal(labels, olabels) and np.array_equal(planes, oplanes)
+    np.savez_compressed(os.path.join(OUT, "real_scan.npz"), xyz=scan.astype(np.float64), rc=r_rc, model=r_model,
+                        inl=r_inl.astype(np.uint32), iterations_run=st["iterations_run"],
+                        best_index=st["best_index"], best_count=st["best_count"], planes=planes,
+                        labels=labels.astype(np.int64))
 print("golden vectors written to", OUT)
