@@ -249,3 +249,37 @@ def test_real_scan_fit_and_segmentation(orc, refc):
     rc, oplanes, olabels = orc.segment_plane_iterative(xyz, 0.01, 100, 0.1, seed=3)
     assert rc == 0 and npl == len(oplanes) >= 1
     assert np.array_equal(labels, olabels) and np.array_equal(bits(planes), bits(oplanes))
+
+
+@pytest.mark.parametrize("kind", [0, 1, 2])
+def test_minimal_fit_extreme_magnitudes(orc, refc, kind):
+    """coordinates from 1e-300 to 1e300, zeros, NaN / inf entries, huge and tiny normals: same MinimalFit verdict,
+    bit-identical models (NaN patterns included), distances bit-identical or NaN in both (a NaN distance is
+    never < threshold in either; only its sign bit may differ between two compilations of the same formula)"""
+    rng = np.random.default_rng(700 + kind)
+    k = {0: 3, 1: 4, 2: 2}[kind]
+    seen_fail = seen_nan = 0
+    for it in range(400):
+        e = int(rng.choice([-300, -160, -150, -100, -20, 0, 20, 100, 150, 153, 160, 300]))
+        pts = rng.uniform(-1, 1, (k, 3)) * 10.0 ** e
+        if it % 11 == 0:
+            pts[rng.integers(k), rng.integers(3)] = rng.choice([np.nan, np.inf, -np.inf, 0.0])
+        nrm = rng.normal(size=(k, 3))
+        nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
+        if it % 13 == 0:
+            nrm[0] *= 10.0 ** int(rng.choice([-200, 200]))
+        with np.errstate(all="ignore"):
+            ok_r, m_r = refc.minimal_fit(kind, pts, nrm if kind == 2 else None)
+            ok_o, m_o = orc.minimal_fit(kind, pts, nrm if kind == 2 else None)
+            assert bool(ok_o) == ok_r, (it, e)
+            seen_fail += not ok_r
+            if not ok_r:
+                continue
+            assert np.array_equal(bits(m_r), bits(m_o)), (it, e, m_r, m_o)
+            q = rng.uniform(-1, 1, (16, 3)) * 10.0 ** e
+            d_r = refc.distances(kind, m_r, q)
+            d_o = np.array([orc.distance(kind, m_o, p) for p in q])
+        both_nan = np.isnan(d_r) & np.isnan(d_o)
+        seen_nan += int(both_nan.any())
+        assert np.array_equal(bits(d_r)[~both_nan], bits(d_o)[~both_nan]), (it, e)
+    assert seen_fail > 0
