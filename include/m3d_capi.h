@@ -166,6 +166,12 @@ int m3d_evaluate_model(m3d_ctx *ctx, int kind, const m3d_cloud *cloud, const dou
 /* utils.h:81-97 RandomSampler<size_t>::operator() on an mt19937(seed) stream: rows x k, draw order */
 void m3d_sample_table(uint32_t seed, size_t n, int k, size_t rows, uint32_t *out);
 
+/* the same table drawn ON THE DEVICE (what m3d_ransac_fit* use when probability == 1): bit-identical rows.
+ * out is a HOST buffer of rows x k.  returns 1 = drawn on the device, 0 = the device draw is not eligible
+ * for these sizes or gave up (too many duplicate draws, i.e. tiny clouds; the host draw is used then),
+ * <0 = m3d_status.  Needs a GPU. */
+int m3d_sample_table_device(m3d_ctx *ctx, uint32_t seed, size_t n, int k, size_t rows, uint32_t *out);
+
 /* Hypothesis sharding (host only): the rows of a wave of `rows` hypotheses that rank `rank` of
  * `world` scores, in its local order (cyclic blocks of 256 rows).  out (may be NULL) receives the wave rows,
  * *n_local their number, *padded the per-rank stride of the all-gathered count buffer (same on all ranks). */

@@ -30,7 +30,7 @@ EXPORTS = [
     "m3d_cloud_upload", "m3d_cloud_from_device", "m3d_cloud_free", "m3d_cloud_size",
     "m3d_ransac_fit_cloud", "m3d_score_samples", "m3d_evaluate_model", "m3d_sample_table",
     "m3d_ordered_scan", "m3d_segment_plane_iterative", "m3d_match_correspondence", "m3d_nearest",
-    "m3d_ransac_registration", "m3d_least_squares_transform", "m3d_shard_rows",
+    "m3d_ransac_registration", "m3d_least_squares_transform", "m3d_shard_rows", "m3d_sample_table_device",
 ]
 
 
@@ -228,6 +228,14 @@ class Context:
         self._check(lib().m3d_probe_fp32_ffma(self.h, C.byref(v)))
         return float(v.value)
 
+    def sample_table_device(self, seed, n, k, rows):
+        """the sample table drawn on the GPU (m3d_sample_table_device): (rows, k) uint32, or None when the
+        device draw is not eligible / gave up for these sizes"""
+        out = np.empty((max(rows, 1), k), dtype=np.uint32)
+        rc = self._check(lib().m3d_sample_table_device(self.h, C.c_uint32(seed & 0xFFFFFFFF), C.c_size_t(n), C.c_int(k),
+                                                       C.c_size_t(rows), _p(out, C.c_uint32)))
+        return out[:rows] if rc == 1 else None
+
     # ------------------------------------------------------------------ multi-GPU
     def init_nccl(self, unique_id, rank, world):
         buf = C.create_string_buffer(bytes(unique_id), 128)
@@ -379,6 +387,8 @@ class Context:
     def least_squares_transform(self, src, dst, with_scaling=False):
         src = _f64(src).reshape(-1, 3)
         dst = _f64(dst).reshape(-1, 3)
+        if len(src) != len(dst):  # transform_estimation.cpp:52-55 "The number of points pair is not equal"
+            raise ValueError("The number of points pair is not equal")
         T = np.zeros(16)
         self._check(lib().m3d_least_squares_transform(self.h, _p(src), _p(dst), C.c_size_t(len(src)),
                                                       C.c_int(1 if with_scaling else 0), _p(T)))

@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "context.h"
+#include "loop_kernels.cuh"
 #include "ransac_kernels.cuh"
 #include "score_cull.cuh"
 #include "scan.h"
@@ -32,6 +33,8 @@ struct SmallDev { /* layout of ctx->d_small */
     unsigned long long resolves;
     uint32_t sample[8]; /* one sample row                                             */
     double row_nrm[12]; /* its normals in draw order (host-normals mode)              */
+    BestRec best;       /* merged arg-best record of the last wave (device-side loop) */
+    RowBreaks draw;     /* outcome of the device-side sample draw                     */
 };
 
 int prepare_cloud(m3d_ctx *ctx, m3d_cloud *c) {
@@ -418,180 +421,200 @@ struct FitResult {
     int ret;
 };
 
-int fit_view(m3d_ctx *ctx, int kind, const m3d_cloud *cloud_for_flags, const CloudView &v,
-             const m3d_ransac_params &p, SegArgs *seg, FitResult *res) {
-    const int k = sample_size(kind);
-    const uint64_t H = p.max_iteration;
-    const uint32_t n = v.n;
-    const bool exact_only = (p.flags & M3D_FLAG_EXACT_ONLY) != 0 || v.nonfinite;
-    memset(res, 0, sizeof *res);
-    res->st.stop_index = H;
+/* tuning / test knobs: M3D_LOOP=host replays every wave on the host (the round-1 path);
+ * M3D_SAMPLER=host draws every sample table on the host */
+bool env_is(const char *name, const char *value) {
+    const char *e = getenv(name);
+    return e && strcmp(e, value) == 0;
+}
+bool loop_on_host() {
+    static const bool v = env_is("M3D_LOOP", "host");
+    return v;
+}
+bool sampler_on_host() {
+    static const bool v = env_is("M3D_SAMPLER", "host");
+    return v;
+}
 
-    M3D_CUDA(ctx, ctx->d_small.reserve(sizeof(SmallDev)));
-    M3D_CUDA(ctx, ctx->h_small.reserve(sizeof(SmallDev)));
-    SmallDev *ds = ctx->d_small.as<SmallDev>();
-    SmallDev *hs = ctx->h_small.as<SmallDev>();
+/* ---- the sample table of rows [0, rows) of the stream (seed, n), k indices per row, drawn ON THE DEVICE
+ * into `d_table` (loop_kernels.cuh).  *d_status receives the outcome asynchronously (status != 0: the draw
+ * gave up -- too many duplicates -- and the caller has to fall back to the host draw). */
+bool device_draw_eligible(uint32_t n, int k, uint64_t rows) {
+    if (sampler_on_host() || n < 2 || k < 2 || k > 4) return false;
+    const double len = (double)rows * k + 4096.0;
+    if (len >= 2.0e9) return false;
+    return len * (0.5 * k * (k - 1)) / (double)n <= 0.25 * kDupCap; /* expected rows with a duplicate */
+}
+int draw_table_device(m3d_ctx *ctx, uint32_t seed, uint32_t n, int k, uint32_t rows, uint32_t *d_table,
+                      RowBreaks *d_status) {
+    const uint32_t nblocks = (uint32_t)(((uint64_t)rows * k + 4096 + 623) / 624);
+    const uint32_t len = nblocks * 624;
+    M3D_CUDA(ctx, ctx->d_draw.reserve(sizeof(uint32_t) * ((size_t)len + kDupCap) + sizeof(uint2) * (kDupCap + 2)));
+    uint32_t *stream = ctx->d_draw.as<uint32_t>();
+    uint32_t *list = stream + len;
+    uint2 *brk = reinterpret_cast<uint2 *>(list + kDupCap + ((len + kDupCap) & 1));
+    MtInit init;
+    init.mt[0] = seed;
+    for (uint32_t i = 1; i < 624; ++i) init.mt[i] = 1812433253u * (init.mt[i - 1] ^ (init.mt[i - 1] >> 30)) + i;
+    const uint64_t magic = UINT64_MAX / n + 1;
+    M3D_CUDA(ctx, cudaMemsetAsync(d_status, 0, sizeof(RowBreaks), ctx->stream));
+    mt_stream_kernel<<<1, 256, 0, ctx->stream>>>(init, n, magic, nblocks, stream);
+    M3D_LAUNCHED(ctx);
+    const int nb = std::max(1, std::min<int>(ctx->sm_count * 4, (int)((len + 255) / 256)));
+    dup_positions_kernel<<<nb, 256, 0, ctx->stream>>>(stream, len, k, d_status, list);
+    M3D_LAUNCHED(ctx);
+    row_breaks_kernel<<<1, 1024, 0, ctx->stream>>>(stream, len, k, rows, d_status, list, brk);
+    M3D_LAUNCHED(ctx);
+    build_rows_kernel<<<std::max(1, std::min<int>(ctx->sm_count * 4, (int)((rows + 255) / 256))), 256, 0, ctx->stream>>>(
+        stream, len, k, rows, d_status, brk, d_table);
+    M3D_LAUNCHED(ctx);
+    return M3D_OK;
+}
+
+constexpr int kRetryOnHost = 1000; /* internal: the device-side loop gave up, run the host loop */
+
+struct Fit {
+    m3d_ctx *ctx;
+    int kind, k;
+    const m3d_cloud *cloud_for_flags;
+    const CloudView &v;
+    const m3d_ransac_params &p;
+    SegArgs *seg;
+    FitResult *res;
+    uint32_t n;
+    uint64_t H;
+    bool exact_only, host_nrm;
+    SmallDev *ds, *hs;
     RefineBufs rb;
-    if (int rc = refine_bufs(ctx, n, &rb)) return rc;
-    M3D_CUDA(ctx, ctx->d_inl.reserve(sizeof(unsigned long long) * (size_t)std::max<uint32_t>(n, 1)));
-    M3D_CUDA(ctx, cudaMemsetAsync(&ds->resolves, 0, sizeof(unsigned long long), ctx->stream));
-
-    cudaEvent_t ev_a = ctx->ev[0], ev_b = ctx->ev[1], ev_s0 = ctx->ev[2], ev_s1 = ctx->ev[3];
-    M3D_CUDA(ctx, cudaEventRecord(ev_a, ctx->stream));
-
-    SampleStream stream(p.seed, n);
-    std::vector<uint32_t> table; /* all rows drawn so far (draw order) */
-    OrderedScan scan(n, k, p.probability, H);
+    const double *one_row_nrm;
+    cudaEvent_t ev_a, ev_b, ev_s0, ev_s1;
     float score_ms = 0;
     uint64_t evaluated = 0;
+    int R, rank;
 
-    /* host-normals mode: only the cylinder reads normals, and only those of its sample points */
-    const bool host_nrm = (kind == kCylinder) && v.nrm == nullptr && v.h_nrm != nullptr;
-    const double *one_row_nrm = host_nrm ? ds->row_nrm : nullptr;
-    /* sample row `row` (+ its normals) -> ds->sample / ds->row_nrm; pageable 48-byte copies are staged by the
-     * driver before cudaMemcpyAsync returns, so the stack buffer may go out of scope */
-    auto stage_row = [&](uint64_t row) -> int {
-        M3D_CUDA(ctx, cudaMemcpyAsync(ds->sample, &table[(size_t)row * k], sizeof(uint32_t) * k,
-                                      cudaMemcpyHostToDevice, ctx->stream));
-        if (host_nrm) {
-            double tmp[12];
+    /* where sample rows live: the current wave [wave_base, wave_base + wave_rows) in ctx->d_samples (and the
+     * normals of its sample points in ctx->d_rownrm in host-normals mode) + a host copy of the best row */
+    uint64_t wave_base = 0, wave_rows = 0;
+    bool have_saved = false;
+    uint64_t saved_idx = 0;
+    uint32_t saved_sample[4] = {0, 0, 0, 0};
+    double saved_nrm[12];
+
+    Fit(m3d_ctx *c, int kd, const m3d_cloud *cf, const CloudView &vv, const m3d_ransac_params &pp, SegArgs *sg, FitResult *r)
+        : ctx(c), kind(kd), k(sample_size(kd)), cloud_for_flags(cf), v(vv), p(pp), seg(sg), res(r) {}
+
+    int setup() {
+        H = p.max_iteration;
+        n = v.n;
+        exact_only = (p.flags & M3D_FLAG_EXACT_ONLY) != 0 || v.nonfinite;
+        memset(res, 0, sizeof *res);
+        res->st.stop_index = H;
+        M3D_CUDA(ctx, ctx->d_small.reserve(sizeof(SmallDev)));
+        M3D_CUDA(ctx, ctx->h_small.reserve(sizeof(SmallDev)));
+        ds = ctx->d_small.as<SmallDev>();
+        hs = ctx->h_small.as<SmallDev>();
+        if (int rc = refine_bufs(ctx, n, &rb)) return rc;
+        M3D_CUDA(ctx, ctx->d_inl.reserve(sizeof(unsigned long long) * (size_t)std::max<uint32_t>(n, 1)));
+        M3D_CUDA(ctx, cudaMemsetAsync(&ds->resolves, 0, sizeof(unsigned long long), ctx->stream));
+        ev_a = ctx->ev[0], ev_b = ctx->ev[1], ev_s0 = ctx->ev[2], ev_s1 = ctx->ev[3];
+        M3D_CUDA(ctx, cudaEventRecord(ev_a, ctx->stream));
+        /* host-normals mode: only the cylinder reads normals, and only those of its sample points */
+        host_nrm = (kind == kCylinder) && v.nrm == nullptr && v.h_nrm != nullptr;
+        one_row_nrm = host_nrm ? ds->row_nrm : nullptr;
+        R = ctx->world, rank = ctx->rank;
+        return M3D_OK;
+    }
+
+    void save_best(uint64_t idx, const uint32_t *row) {
+        have_saved = true;
+        saved_idx = idx;
+        for (int j = 0; j < k; ++j) saved_sample[j] = row[j];
+        if (host_nrm)
             for (int j = 0; j < k; ++j)
-                for (int c = 0; c < 3; ++c) tmp[3 * j + c] = v.h_nrm[3 * (size_t)table[(size_t)row * k + j] + c];
-            M3D_CUDA(ctx, cudaMemcpyAsync(ds->row_nrm, tmp, sizeof(double) * 3 * k, cudaMemcpyHostToDevice, ctx->stream));
+                for (int c = 0; c < 3; ++c) saved_nrm[3 * j + c] = v.h_nrm[3 * (size_t)row[j] + c];
+    }
+    /* sample row `row` (+ its normals) -> ds->sample / ds->row_nrm.  Pageable copies of a few bytes are staged
+     * by the driver before cudaMemcpyAsync returns */
+    int stage_row(uint64_t row) {
+        if (row >= wave_base && row < wave_base + wave_rows) {
+            const size_t off = (size_t)(row - wave_base) * k;
+            M3D_CUDA(ctx, cudaMemcpyAsync(ds->sample, ctx->d_samples.as<uint32_t>() + off, sizeof(uint32_t) * k,
+                                          cudaMemcpyDeviceToDevice, ctx->stream));
+            if (host_nrm)
+                M3D_CUDA(ctx, cudaMemcpyAsync(ds->row_nrm, ctx->d_rownrm.as<double>() + 3 * off, sizeof(double) * 3 * k,
+                                              cudaMemcpyDeviceToDevice, ctx->stream));
+            return 0;
         }
+        if (!have_saved || saved_idx != row) return ctx->fail(M3D_ERR_INTERNAL, "sample row %llu is not available", (unsigned long long)row);
+        M3D_CUDA(ctx, cudaMemcpyAsync(ds->sample, saved_sample, sizeof(uint32_t) * k, cudaMemcpyHostToDevice, ctx->stream));
+        if (host_nrm)
+            M3D_CUDA(ctx, cudaMemcpyAsync(ds->row_nrm, saved_nrm, sizeof(double) * 3 * k, cudaMemcpyHostToDevice, ctx->stream));
         return 0;
-    };
-    /* evaluates hypothesis `row` alone (tie-breaks, final best): model -> ds->model, then
-     * pass 1+2 -> ds->mid; optionally the index-order error */
-    auto eval_row = [&](uint64_t row, bool exact, uint64_t expect_cnt, double *rmse) -> int {
+    }
+    /* evaluates hypothesis `row` alone (tie-breaks): model -> ds->model, then pass 1+2 -> ds->mid;
+     * optionally the index-order error */
+    int eval_row(uint64_t row, bool exact, uint64_t expect_cnt, double *rmse) {
         if (int rc = stage_row(row)) return rc;
         if (int rc = fit_rows_kind(ctx, kind, v.xyz, v.nrm, ds->sample, 1, ds->model, ds->valid, one_row_nrm)) return rc;
         if (int rc = count_pass_kind(ctx, kind, v.xyz, n, ds->model, p.threshold, rb, &ds->mid)) return rc;
         if (exact) {
-            RefineOut *scratch_out = &ds->out;
             if (int rc = write_pass_kind(ctx, kind, v.xyz, n, ds->model, p.threshold, rb, &ds->mid,
-                                         ctx->d_inl.as<unsigned long long>(), scratch_out))
+                                         ctx->d_inl.as<unsigned long long>(), &ds->out))
                 return rc;
-            if (int rc = seq_err_kind(ctx, kind, v.xyz, ctx->d_inl.as<unsigned long long>(), expect_cnt,
-                                      ds->model, &ds->seq_err))
+            if (int rc = seq_err_kind(ctx, kind, v.xyz, ctx->d_inl.as<unsigned long long>(), expect_cnt, ds->model, &ds->seq_err))
                 return rc;
         }
         M3D_CUDA(ctx, cudaMemcpyAsync(hs, ds, sizeof(SmallDev), cudaMemcpyDeviceToHost, ctx->stream));
         M3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         if (hs->mid.n_inl != expect_cnt)
             return ctx->fail(M3D_ERR_INTERNAL, "hypothesis %llu: scoring kernel counted %llu inliers, fp64 pass %llu",
-                             (unsigned long long)row, (unsigned long long)expect_cnt,
-                             (unsigned long long)hs->mid.n_inl);
+                             (unsigned long long)row, (unsigned long long)expect_cnt, (unsigned long long)hs->mid.n_inl);
         const double e = exact ? hs->seq_err : hs->mid.err;
         *rmse = expect_cnt ? e / std::sqrt((double)expect_cnt) : 1e10;
         return 0;
-    };
+    }
 
-    const int R = ctx->world, rank = ctx->rank;
-    uint64_t done = 0;
-    /* a wave is at most kMaxWave rows PER RANK: one exchange + one host replay per wave, whatever the number of ranks */
-    const uint32_t wave_cap = (uint32_t)std::min<uint64_t>((uint64_t)kMaxWave * (uint64_t)std::max(ctx->world, 1), 1u << 22);
-    uint32_t wave = (p.probability >= 1.0) ? wave_cap : 256;
-    int rc_scan = 0;
-    while (done < H && !scan.stopped) {
-        const uint32_t rows = (uint32_t)std::min<uint64_t>(wave, H - done);
-        /* The sample rows come from one sequential mt19937 stream drawn on the host, and every rank needs the
-         * whole table (its own rows for the GPU, any row for the replay's tie-breaks and the final refit).
-         * Rows are dealt to the ranks in cyclic blocks (ShardMap), so a rank can launch the first part of its
-         * shard after drawing a fraction of the table and draws the rest while its GPU works. */
-        const ShardMap sm{rows, (uint32_t)R, (uint32_t)rank};
-        const uint32_t S = sm.padded(), mine = sm.local_rows();
-        table.resize((size_t)(done + rows) * k);
-        M3D_CUDA(ctx, ctx->h_samples.reserve(sizeof(uint32_t) * (size_t)rows * k));
-        M3D_CUDA(ctx, ctx->d_samples.reserve(sizeof(uint32_t) * (size_t)rows * k));
-        if (host_nrm) { /* normals of this wave's sample points only: rows x k x 3 doubles */
-            M3D_CUDA(ctx, ctx->h_rownrm.reserve(sizeof(double) * (size_t)rows * k * 3));
-            M3D_CUDA(ctx, ctx->d_rownrm.reserve(sizeof(double) * (size_t)rows * k * 3));
-        }
-        uint32_t drawn = 0; /* rows of this wave drawn and uploaded so far */
-        auto draw_to = [&](uint32_t upto) -> int {
-            if (upto <= drawn) return 0;
-            uint32_t *tab = &table[(size_t)(done + drawn) * k];
-            stream.draw_rows(k, upto - drawn, tab);
-            const size_t off = (size_t)drawn * k, cnt = (size_t)(upto - drawn) * k;
-            memcpy(ctx->h_samples.as<uint32_t>() + off, tab, sizeof(uint32_t) * cnt);
-            M3D_CUDA(ctx, cudaMemcpyAsync(ctx->d_samples.as<uint32_t>() + off, ctx->h_samples.as<uint32_t>() + off,
-                                          sizeof(uint32_t) * cnt, cudaMemcpyHostToDevice, ctx->stream));
-            if (host_nrm) {
-                double *dst = ctx->h_rownrm.as<double>() + 3 * off;
-                for (size_t e = 0; e < cnt; ++e) {
-                    const double *src = v.h_nrm + 3 * (size_t)tab[e];
-                    dst[3 * e] = src[0], dst[3 * e + 1] = src[1], dst[3 * e + 2] = src[2];
-                }
-                M3D_CUDA(ctx, cudaMemcpyAsync(ctx->d_rownrm.as<double>() + 3 * off, dst, sizeof(double) * 3 * cnt,
-                                              cudaMemcpyHostToDevice, ctx->stream));
-            }
-            drawn = upto;
-            return 0;
-        };
-        M3D_CUDA(ctx, ctx->d_counts.reserve(sizeof(uint32_t) * (size_t)std::max<uint32_t>(S, 1)));
-        M3D_CUDA(ctx, ctx->d_counts_all.reserve(sizeof(uint32_t) * (size_t)std::max<uint32_t>(S, 1) * R));
-        M3D_CUDA(ctx, cudaMemsetAsync(ctx->d_counts.p, 0, sizeof(uint32_t) * (size_t)std::max<uint32_t>(S, 1), ctx->stream));
-        bool s0_recorded = false;
-        /* one launch on a single GPU (the draw of a 10k-row table is ~50 us there); with R ranks the table is R
-         * times longer, so the shard is issued in up to four parts -- of at least classify_min_rows() rows each
-         * when the shard is that large (so that every part is still pre-sorted into culled / dense hypotheses),
-         * else in two halves */
-        uint32_t parts = 1;
-        if (R > 1) parts = (mine >= 2 * classify_min_rows()) ? std::min<uint32_t>(4, mine / classify_min_rows())
-                                                              : (mine >= 8192 ? 2 : 1);
-        for (uint32_t part = 0; part < parts && mine; ++part) {
-            const uint32_t l0 = (uint32_t)((uint64_t)mine * part / parts) / kShardBlock * kShardBlock;
-            const uint32_t l1 = (part + 1 == parts) ? mine : (uint32_t)((uint64_t)mine * (part + 1) / parts) / kShardBlock * kShardBlock;
-            if (l1 <= l0) continue;
-            if (int rc = draw_to(std::min<uint32_t>(rows, sm.wave_row(l1 - 1) + 1))) return rc;
-            if (!s0_recorded) { /* score_ms = the launches of the wave (the first part's table draw is not GPU time) */
-                M3D_CUDA(ctx, cudaEventRecord(ev_s0, ctx->stream));
-                s0_recorded = true;
-            }
-            ScoreArgs a{};
-            a.pts32 = v.pts32;
-            a.blob = (p.flags & M3D_FLAG_DENSE) ? nullptr : v.blob;
-            a.perm = v.perm;
-            a.flags = p.flags;
-            a.xyz = v.xyz;
-            a.nrm = v.nrm;
-            a.row_nrm = host_nrm ? ctx->d_rownrm.as<double>() : nullptr;
-            a.meta = v.meta;
-            a.samples = ctx->d_samples.as<uint32_t>();
-            a.counts = ctx->d_counts.as<uint32_t>() + l0;
-            a.resolves = &ds->resolves;
-            a.thr = p.threshold;
-            a.n = n;
-            a.row_begin = l0; /* shard-local */
-            a.rows = l1 - l0;
-            a.shard_world = (uint32_t)R;
-            a.shard_rank = (uint32_t)rank;
-            if (int rc = launch_score_kind(ctx, kind, cloud_for_flags, a, exact_only)) return rc;
-        }
-        if (!s0_recorded) M3D_CUDA(ctx, cudaEventRecord(ev_s0, ctx->stream)); /* a rank without rows in this wave */
-        M3D_CUDA(ctx, cudaEventRecord(ev_s1, ctx->stream));
-        if (int rc = draw_to(rows)) return rc; /* the rest of the table (host side), while the GPU works */
-        const uint32_t *d_all = ctx->d_counts.as<uint32_t>();
-        if (R > 1) {
-            if (int rc = exchange_allgather(ctx, ctx->d_counts.p, ctx->d_counts_all.p, sizeof(uint32_t) * (size_t)S))
-                return rc;
-            d_all = ctx->d_counts_all.as<uint32_t>();
-        }
-        M3D_CUDA(ctx, ctx->h_counts.reserve(sizeof(uint32_t) * (size_t)S * R));
-        M3D_CUDA(ctx, cudaMemcpyAsync(ctx->h_counts.p, d_all, sizeof(uint32_t) * (size_t)S * R,
-                                      cudaMemcpyDeviceToHost, ctx->stream));
-        M3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        float ms = 0;
-        cudaEventElapsedTime(&ms, ev_s0, ev_s1);
-        score_ms += ms;
-        evaluated += rows;
+    ScoreArgs score_args(uint32_t l0, uint32_t l1) const {
+        ScoreArgs a{};
+        a.pts32 = v.pts32;
+        a.blob = (p.flags & M3D_FLAG_DENSE) ? nullptr : v.blob;
+        a.perm = v.perm;
+        a.flags = p.flags;
+        a.xyz = v.xyz;
+        a.nrm = v.nrm;
+        a.row_nrm = host_nrm ? ctx->d_rownrm.as<double>() : nullptr;
+        a.meta = v.meta;
+        a.samples = ctx->d_samples.as<uint32_t>();
+        a.counts = ctx->d_counts.as<uint32_t>() + l0;
+        a.resolves = &ds->resolves;
+        a.thr = p.threshold;
+        a.n = n;
+        a.row_begin = l0; /* shard-local */
+        a.rows = l1 - l0;
+        a.shard_world = (uint32_t)R;
+        a.shard_rank = (uint32_t)rank;
+        return a;
+    }
 
-        const uint32_t *hc = ctx->h_counts.as<uint32_t>();
+    /* RefineModel (ransac.h:534-549) on the minimal model of the sample row staged in ds->sample */
+    int enqueue_refine() {
+        if (int rc = fit_rows_kind(ctx, kind, v.xyz, v.nrm, ds->sample, 1, ds->model, ds->valid, one_row_nrm)) return rc;
+        if (int rc = count_pass_kind(ctx, kind, v.xyz, n, ds->model, p.threshold, rb, &ds->mid)) return rc;
+        if (seg) return write_pass<kPlane, true>(ctx, v.xyz, n, ds->model, p.threshold, rb, &ds->mid,
+                                                 ctx->d_inl.as<unsigned long long>(), &ds->out, *seg);
+        return write_pass_kind(ctx, kind, v.xyz, n, ds->model, p.threshold, rb, &ds->mid,
+                               ctx->d_inl.as<unsigned long long>(), &ds->out);
+    }
+
+    /* host replay of ransac.h:572-613 over the wave's counts (rank-major gathered buffer `hc`) */
+    int replay_wave(OrderedScan &scan, const ShardMap &sm, const uint32_t *hc, uint64_t done, uint32_t rows,
+                    const uint32_t *h_table) {
+        int rc_scan = 0;
         for (uint32_t r = 0; r < rows && !scan.stopped; ++r) {
             const uint32_t raw = hc[sm.gathered_index(r)]; /* rank-major buffer -> wave row */
             const bool valid = (raw & kInvalidBit) == 0;
             const uint64_t cnt = raw & ~kInvalidBit;
+            const uint64_t before = scan.found ? scan.best_index : UINT64_MAX;
             scan.step(done + r, valid, cnt, [&](uint64_t j, bool exact, double *rmse) {
                 const uint32_t rawj = (j >= done) ? hc[sm.gathered_index((uint32_t)(j - done))] : 0;
                 const uint64_t cj = (j == scan.best_index && scan.found) ? scan.best_count : (uint64_t)(rawj & ~kInvalidBit);
@@ -600,62 +623,275 @@ int fit_view(m3d_ctx *ctx, int kind, const m3d_cloud *cloud_for_flags, const Clo
                 return rc;
             });
             if (rc_scan) return rc_scan;
+            if (h_table && scan.found && scan.best_index != before) save_best(scan.best_index, h_table + (size_t)r * k);
         }
-        done += rows;
-        if (wave < wave_cap) wave = std::min<uint32_t>(wave_cap, wave * 4);
+        return 0;
     }
-    if (!scan.stopped && done >= H) {
-        /* the loop ran to max_iteration; the reference checks `count > current_iteration` only at
-         * the top of an iteration, so nothing more to do */
-    }
-    scan.fill(&res->st);
-    res->st.evaluated = evaluated;
-    res->st.score_ms = score_ms;
 
-    int ret = 0;
-    if (scan.found) {
-        /* RefineModel (ransac.h:534-549) on the winning minimal model */
-        const uint64_t bi = scan.best_index;
-        if (int rc = stage_row(bi)) return rc;
-        if (int rc = fit_rows_kind(ctx, kind, v.xyz, v.nrm, ds->sample, 1, ds->model, ds->valid, one_row_nrm)) return rc;
-        if (int rc = count_pass_kind(ctx, kind, v.xyz, n, ds->model, p.threshold, rb, &ds->mid)) return rc;
-        if (seg) {
-            if (int rc = write_pass<kPlane, true>(ctx, v.xyz, n, ds->model, p.threshold, rb, &ds->mid,
-                                                  ctx->d_inl.as<unsigned long long>(), &ds->out, *seg))
-                return rc;
-        } else {
-            if (int rc = write_pass_kind(ctx, kind, v.xyz, n, ds->model, p.threshold, rb, &ds->mid,
-                                         ctx->d_inl.as<unsigned long long>(), &ds->out))
-                return rc;
+    /* the wave's counts of all ranks -> ctx->h_counts (rank-major), synchronised */
+    int fetch_counts(uint32_t S) {
+        const uint32_t *d_all = ctx->d_counts.as<uint32_t>();
+        if (R > 1) {
+            M3D_CUDA(ctx, ctx->d_counts_all.reserve(sizeof(uint32_t) * (size_t)std::max<uint32_t>(S, 1) * R));
+            if (int rc = exchange_allgather(ctx, ctx->d_counts.p, ctx->d_counts_all.p, sizeof(uint32_t) * (size_t)S)) return rc;
+            d_all = ctx->d_counts_all.as<uint32_t>();
         }
-        M3D_CUDA(ctx, cudaMemcpyAsync(hs, ds, sizeof(SmallDev), cudaMemcpyDeviceToHost, ctx->stream));
-        M3D_CUDA(ctx, cudaEventRecord(ev_b, ctx->stream));
+        M3D_CUDA(ctx, ctx->h_counts.reserve(sizeof(uint32_t) * (size_t)std::max<uint32_t>(S, 1) * R));
+        M3D_CUDA(ctx, cudaMemcpyAsync(ctx->h_counts.p, d_all, sizeof(uint32_t) * (size_t)S * R, cudaMemcpyDeviceToHost, ctx->stream));
         M3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        if (hs->mid.n_inl != scan.best_count)
-            return ctx->fail(M3D_ERR_INTERNAL, "best hypothesis %llu: scoring kernel counted %llu inliers, fp64 pass %llu",
-                             (unsigned long long)bi, (unsigned long long)scan.best_count,
-                             (unsigned long long)hs->mid.n_inl);
-        res->n_inl = hs->mid.n_inl;
-        memcpy(res->minimal, hs->model, sizeof res->minimal);
-        const bool refit = (p.flags & M3D_FLAG_NO_REFIT) == 0;
-        memcpy(res->refined, refit ? hs->out.model : hs->model, sizeof res->refined);
-        res->st.refit_ok = refit ? hs->out.ok : 1;
-        if (!(scan.best_rmse_known && scan.best_rmse_exact && scan.best_index == bi && scan.best_rmse != 0))
-            res->st.best_rmse = hs->mid.err / std::sqrt((double)hs->mid.n_inl);
-        res->st.exact_resolves = hs->resolves;
-        ret = res->st.refit_ok;
-    } else {
-        M3D_CUDA(ctx, cudaMemcpyAsync(&hs->resolves, &ds->resolves, sizeof(unsigned long long),
-                                      cudaMemcpyDeviceToHost, ctx->stream));
-        M3D_CUDA(ctx, cudaEventRecord(ev_b, ctx->stream));
-        M3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        res->st.exact_resolves = hs->resolves;
+        return 0;
     }
-    float ms = 0;
-    cudaEventElapsedTime(&ms, ev_a, ev_b);
-    res->st.device_ms = ms;
-    res->ret = ret;
-    return M3D_OK;
+
+    int finish(OrderedScan &scan, bool refined_already) {
+        scan.fill(&res->st);
+        res->st.evaluated = evaluated;
+        res->st.score_ms = score_ms;
+        int ret = 0;
+        if (scan.found) {
+            const uint64_t bi = scan.best_index;
+            if (!refined_already) {
+                if (int rc = stage_row(bi)) return rc;
+                if (int rc = enqueue_refine()) return rc;
+                M3D_CUDA(ctx, cudaMemcpyAsync(hs, ds, sizeof(SmallDev), cudaMemcpyDeviceToHost, ctx->stream));
+                M3D_CUDA(ctx, cudaEventRecord(ev_b, ctx->stream));
+                M3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            }
+            if (hs->mid.n_inl != scan.best_count)
+                return ctx->fail(M3D_ERR_INTERNAL, "best hypothesis %llu: scoring kernel counted %llu inliers, fp64 pass %llu",
+                                 (unsigned long long)bi, (unsigned long long)scan.best_count, (unsigned long long)hs->mid.n_inl);
+            res->n_inl = hs->mid.n_inl;
+            memcpy(res->minimal, hs->model, sizeof res->minimal);
+            const bool refit = (p.flags & M3D_FLAG_NO_REFIT) == 0;
+            memcpy(res->refined, refit ? hs->out.model : hs->model, sizeof res->refined);
+            res->st.refit_ok = refit ? hs->out.ok : 1;
+            if (!(scan.best_rmse_known && scan.best_rmse_exact && scan.best_index == bi && scan.best_rmse != 0))
+                res->st.best_rmse = hs->mid.err / std::sqrt((double)hs->mid.n_inl);
+            res->st.exact_resolves = hs->resolves;
+            ret = res->st.refit_ok;
+        } else {
+            if (!refined_already) {
+                M3D_CUDA(ctx, cudaMemcpyAsync(&hs->resolves, &ds->resolves, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+                M3D_CUDA(ctx, cudaEventRecord(ev_b, ctx->stream));
+                M3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            }
+            res->st.exact_resolves = hs->resolves;
+        }
+        float ms = 0;
+        cudaEventElapsedTime(&ms, ev_a, ev_b);
+        res->st.device_ms = ms;
+        res->ret = ret;
+        return M3D_OK;
+    }
+
+    /* ---- probability == 1 (no adaptive exit, ransac.h:601-606): the whole loop stays on the device.
+     * Sample table drawn on the device (or on the host when the cylinder's normals live there), ONE scoring
+     * launch per wave, wave_best_kernel + (R > 1) an all-gather of one 64-byte record per rank +
+     * best_merge_kernel, and -- for a single wave -- RefineModel of the provisional winner enqueued behind
+     * them, so that a fit costs one stream synchronisation.  Ties in the inlier count (the reference breaks
+     * them with inlier_rmse) and a hypothesis with fitness 1 (which stops the reference's loop) are detected
+     * in the record and replayed on the host exactly as before. */
+    int run_on_device() {
+        constexpr uint64_t kFastMaxRows = 1u << 22;
+        if (H == 0 || H > kFastMaxRows || (host_nrm && H > (1u << 20))) return kRetryOnHost;
+        const uint32_t rows_all = (uint32_t)H;
+        OrderedScan scan(n, k, p.probability, H);
+        M3D_CUDA(ctx, ctx->d_samples.reserve(sizeof(uint32_t) * (size_t)rows_all * k));
+        const bool dev_draw = !host_nrm && device_draw_eligible(n, k, rows_all);
+        std::vector<uint32_t> h_table;
+        if (dev_draw) {
+            if (int rc = draw_table_device(ctx, p.seed, n, k, rows_all, ctx->d_samples.as<uint32_t>(), &ds->draw)) return rc;
+        } else {
+            M3D_CUDA(ctx, cudaMemsetAsync(&ds->draw, 0, sizeof(RowBreaks), ctx->stream));
+            M3D_CUDA(ctx, ctx->h_samples.reserve(sizeof(uint32_t) * (size_t)rows_all * k));
+            uint32_t *tab = ctx->h_samples.as<uint32_t>();
+            SampleStream stream(p.seed, n);
+            stream.draw_rows(k, rows_all, tab);
+            M3D_CUDA(ctx, cudaMemcpyAsync(ctx->d_samples.p, tab, sizeof(uint32_t) * (size_t)rows_all * k,
+                                          cudaMemcpyHostToDevice, ctx->stream));
+            if (host_nrm) { /* normals of the sample points only: rows x k x 3 doubles */
+                const size_t cnt = (size_t)rows_all * k;
+                M3D_CUDA(ctx, ctx->h_rownrm.reserve(sizeof(double) * cnt * 3));
+                M3D_CUDA(ctx, ctx->d_rownrm.reserve(sizeof(double) * cnt * 3));
+                double *dst = ctx->h_rownrm.as<double>();
+                for (size_t e = 0; e < cnt; ++e) {
+                    const double *src = v.h_nrm + 3 * (size_t)tab[e];
+                    dst[3 * e] = src[0], dst[3 * e + 1] = src[1], dst[3 * e + 2] = src[2];
+                }
+                M3D_CUDA(ctx, cudaMemcpyAsync(ctx->d_rownrm.p, dst, sizeof(double) * 3 * cnt, cudaMemcpyHostToDevice, ctx->stream));
+            }
+        }
+        wave_base = 0, wave_rows = rows_all; /* the whole table is resident: stage_row never needs the host */
+        M3D_CUDA(ctx, ctx->d_recs.reserve(sizeof(BestRec) * (size_t)(R + 1)));
+        BestRec *d_local = ctx->d_recs.as<BestRec>(), *d_all = d_local + 1;
+
+        const uint32_t cap = (uint32_t)std::min<uint64_t>((uint64_t)(1u << 18) * (uint64_t)std::max(R, 1), kFastMaxRows);
+        uint64_t done = 0;
+        bool refined = false;
+        while (done < H && !scan.stopped) {
+            const uint32_t rows = (uint32_t)std::min<uint64_t>(cap, H - done);
+            const ShardMap sm{rows, (uint32_t)R, (uint32_t)rank};
+            const uint32_t S = sm.padded(), mine = sm.local_rows();
+            M3D_CUDA(ctx, ctx->d_counts.reserve(sizeof(uint32_t) * (size_t)std::max<uint32_t>(S, 1)));
+            M3D_CUDA(ctx, cudaMemsetAsync(ctx->d_counts.p, 0, sizeof(uint32_t) * (size_t)std::max<uint32_t>(S, 1), ctx->stream));
+            M3D_CUDA(ctx, cudaEventRecord(ev_s0, ctx->stream));
+            if (mine) {
+                ScoreArgs a = score_args(0, mine);
+                a.samples = ctx->d_samples.as<uint32_t>() + (size_t)done * k;
+                if (host_nrm) a.row_nrm = ctx->d_rownrm.as<double>() + (size_t)done * k * 3;
+                if (int rc = launch_score_kind(ctx, kind, cloud_for_flags, a, exact_only)) return rc;
+            }
+            M3D_CUDA(ctx, cudaEventRecord(ev_s1, ctx->stream));
+            wave_best_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->d_counts.as<uint32_t>(), mine, (uint32_t)R, (uint32_t)rank, n,
+                                                          &ds->draw, d_local);
+            M3D_LAUNCHED(ctx);
+            if (int rc = exchange_allgather(ctx, d_local, d_all, sizeof(BestRec))) return rc;
+            best_merge_kernel<<<1, 32, 0, ctx->stream>>>(d_all, (uint32_t)R, ctx->d_samples.as<uint32_t>() + (size_t)done * k, k,
+                                                         host_nrm ? ctx->d_rownrm.as<double>() + (size_t)done * k * 3 : nullptr,
+                                                         &ds->best, ds->sample, ds->row_nrm);
+            M3D_LAUNCHED(ctx);
+            const bool speculate = (rows == H) && !seg;
+            if (speculate)
+                if (int rc = enqueue_refine()) return rc;
+            M3D_CUDA(ctx, cudaMemcpyAsync(hs, ds, sizeof(SmallDev), cudaMemcpyDeviceToHost, ctx->stream));
+            if (speculate) M3D_CUDA(ctx, cudaEventRecord(ev_b, ctx->stream));
+            M3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            float ms = 0;
+            cudaEventElapsedTime(&ms, ev_s0, ev_s1);
+            score_ms += ms;
+            const BestRec rec = hs->best;
+            if (rec.status) return kRetryOnHost; /* the device draw gave up: nothing of this fit is kept */
+            evaluated += rows;
+            bool clobbered = false;
+            if (rec.first_full != kNoRow || rec.n_tied > (uint32_t)kTiedCap) {
+                /* fitness 1 (the loop stops behind it) or more ties than the record lists: sequential replay */
+                if (int rc = fetch_counts(S)) return rc;
+                if (int rc = replay_wave(scan, sm, ctx->h_counts.as<uint32_t>(), done, rows, nullptr)) return rc;
+                clobbered = true;
+            } else if (rec.max_count == 0) {
+                scan.count += rec.n_valid;
+            } else {
+                /* only rows that reach the wave's maximum can end up as the best (ransac.h:592-613); they are
+                 * stepped in loop order, which breaks count ties with inlier_rmse exactly like the full replay */
+                uint32_t fed = 0;
+                int rc_scan = 0;
+                for (uint32_t t = 0; t < rec.n_tied; ++t) {
+                    scan.step(done + rec.tied[t], true, rec.max_count, [&](uint64_t j, bool exact, double *rmse) {
+                        const uint64_t cj = (j == scan.best_index && scan.found) ? scan.best_count : (uint64_t)rec.max_count;
+                        const int rc = eval_row(j, exact, cj, rmse);
+                        clobbered = true;
+                        if (rc) rc_scan = rc;
+                        return rc;
+                    });
+                    if (rc_scan) return rc_scan;
+                    ++fed;
+                }
+                scan.count += rec.n_valid - fed;
+            }
+            refined = speculate && !clobbered && scan.found && scan.best_index == done + rec.first_row;
+            if (speculate && !scan.found && !clobbered) refined = true; /* nothing to refine; hs->resolves is current */
+            done += rows;
+        }
+        return finish(scan, refined);
+    }
+
+    /* ---- probability < 1: hypotheses are scored in growing waves and the host replays the loop's
+     * bookkeeping after each (adaptive early exit, ransac.h:601-610) */
+    int run_on_host() {
+        SampleStream stream(p.seed, n);
+        std::vector<uint32_t> table; /* the current wave's rows (draw order) */
+        OrderedScan scan(n, k, p.probability, H);
+        uint64_t done = 0;
+        /* a wave is at most kMaxWave rows PER RANK: one exchange + one host replay per wave, whatever the number of ranks */
+        const uint32_t wave_cap = (uint32_t)std::min<uint64_t>((uint64_t)kMaxWave * (uint64_t)std::max(R, 1), 1u << 22);
+        uint32_t wave = (p.probability >= 1.0) ? wave_cap : 256;
+        while (done < H && !scan.stopped) {
+            const uint32_t rows = (uint32_t)std::min<uint64_t>(wave, H - done);
+            /* The sample rows come from one sequential mt19937 stream drawn on the host, and every rank needs the
+             * whole table (its own rows for the GPU, any row for the replay's tie-breaks and the final refit).
+             * Rows are dealt to the ranks in cyclic blocks (ShardMap), so a rank can launch the first part of its
+             * shard after drawing a fraction of the table and draws the rest while its GPU works. */
+            const ShardMap sm{rows, (uint32_t)R, (uint32_t)rank};
+            const uint32_t S = sm.padded(), mine = sm.local_rows();
+            table.resize((size_t)rows * k);
+            wave_base = done, wave_rows = rows;
+            M3D_CUDA(ctx, ctx->h_samples.reserve(sizeof(uint32_t) * (size_t)rows * k));
+            M3D_CUDA(ctx, ctx->d_samples.reserve(sizeof(uint32_t) * (size_t)rows * k));
+            if (host_nrm) { /* normals of this wave's sample points only: rows x k x 3 doubles */
+                M3D_CUDA(ctx, ctx->h_rownrm.reserve(sizeof(double) * (size_t)rows * k * 3));
+                M3D_CUDA(ctx, ctx->d_rownrm.reserve(sizeof(double) * (size_t)rows * k * 3));
+            }
+            uint32_t drawn = 0; /* rows of this wave drawn and uploaded so far */
+            auto draw_to = [&](uint32_t upto) -> int {
+                if (upto <= drawn) return 0;
+                uint32_t *tab = &table[(size_t)drawn * k];
+                stream.draw_rows(k, upto - drawn, tab);
+                const size_t off = (size_t)drawn * k, cnt = (size_t)(upto - drawn) * k;
+                memcpy(ctx->h_samples.as<uint32_t>() + off, tab, sizeof(uint32_t) * cnt);
+                M3D_CUDA(ctx, cudaMemcpyAsync(ctx->d_samples.as<uint32_t>() + off, ctx->h_samples.as<uint32_t>() + off,
+                                              sizeof(uint32_t) * cnt, cudaMemcpyHostToDevice, ctx->stream));
+                if (host_nrm) {
+                    double *dst = ctx->h_rownrm.as<double>() + 3 * off;
+                    for (size_t e = 0; e < cnt; ++e) {
+                        const double *src = v.h_nrm + 3 * (size_t)tab[e];
+                        dst[3 * e] = src[0], dst[3 * e + 1] = src[1], dst[3 * e + 2] = src[2];
+                    }
+                    M3D_CUDA(ctx, cudaMemcpyAsync(ctx->d_rownrm.as<double>() + 3 * off, dst, sizeof(double) * 3 * cnt,
+                                                  cudaMemcpyHostToDevice, ctx->stream));
+                }
+                drawn = upto;
+                return 0;
+            };
+            M3D_CUDA(ctx, ctx->d_counts.reserve(sizeof(uint32_t) * (size_t)std::max<uint32_t>(S, 1)));
+            M3D_CUDA(ctx, cudaMemsetAsync(ctx->d_counts.p, 0, sizeof(uint32_t) * (size_t)std::max<uint32_t>(S, 1), ctx->stream));
+            bool s0_recorded = false;
+            /* one launch on a single GPU (the draw of a 10k-row table is ~50 us there); with R ranks the table is R
+             * times longer, so the shard is issued in up to four parts -- of at least classify_min_rows() rows each
+             * when the shard is that large (so that every part is still pre-sorted into culled / dense hypotheses),
+             * else in two halves */
+            uint32_t parts = 1;
+            if (R > 1) parts = (mine >= 2 * classify_min_rows()) ? std::min<uint32_t>(4, mine / classify_min_rows())
+                                                                  : (mine >= 8192 ? 2 : 1);
+            for (uint32_t part = 0; part < parts && mine; ++part) {
+                const uint32_t l0 = (uint32_t)((uint64_t)mine * part / parts) / kShardBlock * kShardBlock;
+                const uint32_t l1 = (part + 1 == parts) ? mine : (uint32_t)((uint64_t)mine * (part + 1) / parts) / kShardBlock * kShardBlock;
+                if (l1 <= l0) continue;
+                if (int rc = draw_to(std::min<uint32_t>(rows, sm.wave_row(l1 - 1) + 1))) return rc;
+                if (!s0_recorded) { /* score_ms = the launches of the wave (the first part's table draw is not GPU time) */
+                    M3D_CUDA(ctx, cudaEventRecord(ev_s0, ctx->stream));
+                    s0_recorded = true;
+                }
+                if (int rc = launch_score_kind(ctx, kind, cloud_for_flags, score_args(l0, l1), exact_only)) return rc;
+            }
+            if (!s0_recorded) M3D_CUDA(ctx, cudaEventRecord(ev_s0, ctx->stream)); /* a rank without rows in this wave */
+            M3D_CUDA(ctx, cudaEventRecord(ev_s1, ctx->stream));
+            if (int rc = draw_to(rows)) return rc; /* the rest of the table (host side), while the GPU works */
+            if (int rc = fetch_counts(S)) return rc;
+            float ms = 0;
+            cudaEventElapsedTime(&ms, ev_s0, ev_s1);
+            score_ms += ms;
+            evaluated += rows;
+            if (int rc = replay_wave(scan, sm, ctx->h_counts.as<uint32_t>(), done, rows, table.data())) return rc;
+            done += rows;
+            if (wave < wave_cap) wave = std::min<uint32_t>(wave_cap, wave * 4);
+        }
+        /* (when the loop ran to max_iteration: the reference checks `count > current_iteration` only at the
+         * top of an iteration, so nothing more to do) */
+        return finish(scan, false);
+    }
+};
+
+int fit_view(m3d_ctx *ctx, int kind, const m3d_cloud *cloud_for_flags, const CloudView &v,
+             const m3d_ransac_params &p, SegArgs *seg, FitResult *res) {
+    Fit f(ctx, kind, cloud_for_flags, v, p, seg, res);
+    if (int rc = f.setup()) return rc;
+    if (p.probability >= 1.0 && !loop_on_host()) {
+        const int rc = f.run_on_device();
+        if (rc != kRetryOnHost) return rc;
+        Fit g(ctx, kind, cloud_for_flags, v, p, seg, res); /* fresh state */
+        if (int rc2 = g.setup()) return rc2;
+        return g.run_on_host();
+    }
+    return f.run_on_host();
 }
 
 int check_params(m3d_ctx *ctx, int kind, size_t n, bool has_normals, const m3d_ransac_params *p) {
@@ -750,6 +986,25 @@ int m3d_ransac_fit(m3d_ctx *ctx, int kind, const double *xyz, const double *nrm,
     ctx->scratch_cloud->h_nrm = nullptr; /* borrowed for this call only */
     ctx->scratch_cloud->has_normals = false;
     return rc;
+}
+
+/* utils.h:81-97 drawn on the device (loop_kernels.cuh): rows x k indices, bit-identical to m3d_sample_table.
+ * returns 1 = drawn on the device, 0 = not eligible / gave up (too many duplicate draws: tiny clouds) */
+int m3d_sample_table_device(m3d_ctx *ctx, uint32_t seed, size_t n, int k, size_t rows, uint32_t *out) {
+    if (!ctx || !out || k < 1) return M3D_ERR_INVALID_ARG;
+    if (rows == 0) return 1;
+    if (n >= (size_t)kInvalidBit || rows > (1u << 22) || !device_draw_eligible((uint32_t)n, k, rows)) return 0;
+    M3D_CUDA(ctx, cudaSetDevice(ctx->device));
+    M3D_CUDA(ctx, ctx->d_small.reserve(sizeof(SmallDev)));
+    M3D_CUDA(ctx, ctx->h_small.reserve(sizeof(SmallDev)));
+    SmallDev *ds = ctx->d_small.as<SmallDev>();
+    SmallDev *hs = ctx->h_small.as<SmallDev>();
+    M3D_CUDA(ctx, ctx->d_samples.reserve(sizeof(uint32_t) * rows * k));
+    if (int rc = draw_table_device(ctx, seed, (uint32_t)n, k, (uint32_t)rows, ctx->d_samples.as<uint32_t>(), &ds->draw)) return rc;
+    M3D_CUDA(ctx, cudaMemcpyAsync(&hs->draw, &ds->draw, sizeof(RowBreaks), cudaMemcpyDeviceToHost, ctx->stream));
+    M3D_CUDA(ctx, cudaMemcpyAsync(out, ctx->d_samples.p, sizeof(uint32_t) * rows * k, cudaMemcpyDeviceToHost, ctx->stream));
+    M3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return hs->draw.status ? 0 : 1;
 }
 
 #ifdef M3D_CULL_STATS

@@ -42,6 +42,54 @@ def gather_counts(packed, world, all_gather):
     return torch.cat(outs).numpy().astype(np.uint32)
 
 
+NO_ROW = 0xFFFFFFFF
+TIED_CAP = 8  # csrc/loop_kernels.cuh kTiedCap
+REC_WORDS = 16  # BestRec = 64 bytes
+
+
+def best_record(packed, rows_of_rank, n_points):
+    """csrc/loop_kernels.cuh wave_best_kernel restated: the 16-word record one rank derives from its shard's packed
+    counts (bit31 = MinimalFit failed) -- max count, first row reaching it, number of ties, valid rows, first row
+    with fitness 1, the first TIED_CAP tied rows (wave row numbers, ascending)."""
+    packed = np.asarray(packed, dtype=np.uint32)[: len(rows_of_rank)]
+    rows_of_rank = np.asarray(rows_of_rank, dtype=np.uint32)
+    valid = (packed >> 31) == 0
+    cnt = np.where(valid, packed, 0).astype(np.uint32)
+    rec = np.full(REC_WORDS, NO_ROW, dtype=np.uint32)
+    rec[[0, 2, 3, 5, 6, 7]] = 0
+    rec[3] = int(valid.sum())
+    full = rows_of_rank[valid & (cnt == n_points) & (cnt > 0)]
+    if len(full):
+        rec[4] = full.min()
+    best = int(cnt.max()) if len(cnt) else 0
+    if best:
+        tied = np.sort(rows_of_rank[cnt == best])
+        rec[0], rec[1], rec[2] = best, tied[0], len(tied)
+        rec[8: 8 + min(len(tied), TIED_CAP)] = tied[:TIED_CAP]
+    return rec
+
+
+def merge_records(recs):
+    """best_merge_kernel restated: the record of the whole wave from the ranks' records (rank-major (world, 16))"""
+    recs = np.asarray(recs, dtype=np.uint32).reshape(-1, REC_WORDS)
+    m = np.full(REC_WORDS, NO_ROW, dtype=np.uint32)
+    m[[0, 2, 3, 5, 6, 7]] = 0
+    m[0] = recs[:, 0].max()
+    m[3] = recs[:, 3].sum()
+    m[4] = recs[:, 4].min()
+    m[5] = np.bitwise_or.reduce(recs[:, 5])
+    if m[0]:
+        top = recs[recs[:, 0] == m[0]]
+        m[1] = top[:, 1].min()
+        m[2] = top[:, 2].sum()
+        tied = np.sort(top[:, 8:].ravel())
+        tied = tied[tied != NO_ROW][:TIED_CAP]
+        m[8: 8 + len(tied)] = tied
+        if (top[:, 2] > TIED_CAP).any() and m[2] <= TIED_CAP:
+            m[2] = TIED_CAP + 1
+    return m
+
+
 def torch_exchange(group=None, device=None):
     """Exchange callback for Context.set_exchange: all-gathers `nbytes` per rank through
     torch.distributed (NCCL on CUDA tensors when on_device, gloo on host memory otherwise)."""

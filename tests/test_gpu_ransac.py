@@ -440,3 +440,48 @@ def test_full_size_properties_c5(ctx, capi):
     np.testing.assert_array_equal(np.nonzero(d < 0.01)[0], inl)
     assert np.all(np.diff(inl.astype(np.int64)) > 0) and len(inl) > 0.69 * len(xyz)
     cloud.free()
+
+
+# ---------------------------------------------------------------------------------------------------
+# the device-side loop (probability == 1): sample table drawn on the GPU, arg-best record instead of the
+# host replay (csrc/loop_kernels.cuh)
+@pytest.mark.parametrize("seed,n,k,rows", [(1, 1_000_000, 3, 10_000), (2, 1_000_000, 4, 10_000), (3, 1_000_000, 2, 80_000),
+                                           (4, 5000, 4, 20_000), (5, 700, 3, 3000), (6, 40, 3, 400), (7, 2, 2, 100),
+                                           (8, 4_000_000, 3, 100_000), (9, 65536, 3, 1), (10, 123457, 2, 624 * 5)])
+def test_sample_table_device_equals_host(ctx, capi, seed, n, k, rows):
+    """utils.h:81-97 (mt19937, % size, duplicate rejection) drawn on the GPU == the host stream, bit for bit;
+    small clouds have many rejected draws (row boundaries shift), tiny ones make the device give up (None)"""
+    dev = ctx.sample_table_device(seed, n, k, rows)
+    host = capi.sample_table(seed, n, k, rows)
+    if dev is None:
+        assert n < 200  # gave up: duplicate-heavy stream, the host draw is used
+    else:
+        np.testing.assert_array_equal(dev, host)
+
+
+def test_device_loop_many_ties_and_perfect_fit(ctx, capi, orc):
+    """probability 1: (a) more count ties than the 8 a record lists -> host replay of the wave; (b) a hypothesis
+    with fitness 1 stops the reference's loop (ransac.h:607-609) even without the adaptive exit"""
+    rng = np.random.default_rng(11)
+    xyz = np.round(rng.uniform(-1, 1, (30, 3)), 0)  # 27 lattice sites: massive ties
+    _check_fit(ctx, capi, orc, capi.PLANE, xyz, None, 0.3, 600, 1.0, seed=2)
+    plane = np.c_[rng.uniform(-1, 1, (3000, 2)), np.zeros(3000)]
+    st, ost = _check_fit(ctx, capi, orc, capi.PLANE, plane, None, 0.01, 300, 1.0, seed=3)
+    assert ost["stop_index"] < 300
+    # resident cloud with device normals: the cylinder's table is drawn on the device too
+    xyz, nrm = synth.make_c2(n=30000, seed=12)
+    cloud = ctx.upload(xyz, nrm)
+    for kind in KINDS:
+        rc, model, inl, st = ctx.ransac_fit_cloud(kind, cloud, 0.01, 900, 1.0, seed=21 + kind)
+        orc_rc, omodel, oinl, ost = orc.ransac_fit(kind, xyz, nrm if kind == 2 else None, thr=0.01, max_it=900, prob=1.0,
+                                                   seed=21 + kind)
+        assert rc == orc_rc and np.array_equal(inl, oinl)
+        for key in ("best_index", "best_count", "iterations_run", "stop_index", "found"):
+            assert st[key] == ost[key], (key, st, ost)
+    cloud.free()
+
+
+def test_device_loop_several_waves(ctx, capi, orc):
+    """more hypotheses than one device-side wave holds (2^18 per rank): the best is carried across waves"""
+    xyz = synth.make_c1(n=2500, seed=13)
+    _check_fit(ctx, capi, orc, capi.PLANE, xyz, None, 0.01, 300_000, 1.0, seed=5)

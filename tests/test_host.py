@@ -150,6 +150,77 @@ def test_sharded_counts_over_gloo_match_single_process(capi, orc):
         assert r[1:] == (ost["best_index"], ost["best_count"], ost["iterations_run"], ost["stop_index"])
 
 
+def _record_worker(rank, world, port, q):
+    """probability == 1: every rank reduces its shard to one 64-byte record (sharding.best_record = the device's
+    wave_best_kernel), the records are all-gathered (gloo) and merged (best_merge_kernel)"""
+    import torch
+    import torch.distributed as dist
+    import orc
+    from misc3d_b200 import capi, synth as sy
+    from misc3d_b200.sharding import shard_rows, best_record, merge_records, REC_WORDS
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    xyz = sy.make_c1(n=2000, seed=8)
+    H, thr, seed = 701, 0.01, 3
+    table = capi.sample_table(seed, len(xyz), 3, H)
+    mine, S = shard_rows(H, rank, world)
+    valid, counts, _ = _oracle_counts(orc, orc.PLANE, xyz, None, table[mine], thr)
+    packed = counts.astype(np.uint32) | ((1 - valid).astype(np.uint32) << 31)
+    rec = torch.from_numpy(best_record(packed, mine, len(xyz)).astype(np.int32))
+    outs = [torch.empty_like(rec) for _ in range(world)]
+    dist.all_gather(outs, rec)
+    m = merge_records(torch.stack(outs).numpy().astype(np.uint32).reshape(world, REC_WORDS))
+    q.put((rank, int(m[0]), int(m[1]), int(m[2]), int(m[3]), int(m[4])))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_best_record_exchange_over_gloo_matches_sequential_loop(capi, orc):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_record_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    xyz = synth.make_c1(n=2000, seed=8)
+    rc, model, inl, ost = orc.ransac_fit(orc.PLANE, xyz, thr=0.01, max_it=701, prob=1.0, seed=3)
+    for r in res:
+        max_count, first_row, n_tied, n_valid, first_full = r[1:]
+        assert max_count == ost["best_count"] and n_valid == ost["iterations_run"] and first_full == 0xFFFFFFFF
+        if n_tied == 1:
+            assert first_row == ost["best_index"]
+
+
+def test_best_record_restatement_properties():
+    """the record keeps exactly what the sequential best-update can end on: rows at the maximum count"""
+    from misc3d_b200.sharding import shard_rows, best_record, merge_records, NO_ROW, TIED_CAP
+    rng = np.random.default_rng(5)
+    for world in (1, 2, 3, 8):
+        rows = 3000
+        counts = rng.integers(0, 50, rows).astype(np.uint32)
+        counts[rng.integers(0, rows, 40)] = 49            # ties at the maximum
+        invalid = rng.random(rows) < 0.1
+        packed = counts | (invalid.astype(np.uint32) << 31)
+        recs = []
+        for r in range(world):
+            mine, S = shard_rows(rows, r, world)
+            recs.append(best_record(packed[mine], mine, 10**6))
+        m = merge_records(np.stack(recs))
+        ok = ~invalid
+        best = counts[ok].max()
+        tied = np.flatnonzero(ok & (counts == best))
+        assert m[0] == best and m[1] == tied[0] and m[3] == ok.sum() and m[4] == NO_ROW
+        assert m[2] == len(tied) or (m[2] > TIED_CAP and len(tied) > TIED_CAP)
+        if len(tied) <= TIED_CAP:
+            assert list(m[8: 8 + len(tied)]) == list(tied)
+
+
 @pytest.mark.parametrize("rows,world", [(1, 1), (101, 2), (256, 2), (257, 3), (10000, 8), (80000, 8), (65536, 4),
                                         (12345, 5), (511, 8)])
 def test_shard_map_is_a_partition(capi, rows, world):
