@@ -81,6 +81,13 @@ uint64_t m3d_ctx_launch_count(const m3d_ctx *ctx);
  * denominator bench.py reports beside the HBM one */
 int m3d_probe_fp32_ffma(m3d_ctx *ctx, double *ffma_per_s);
 
+/* work counters of the scoring launches run with M3D_FLAG_STATS since the last call (read and cleared):
+ * out[0] (hypothesis, tile) bounding-sphere tests, [1] survivors, [2] surviving (hypothesis, cell) pairs
+ * (x32 = point-hypothesis pairs evaluated point by point), [3] / [4] evaluation passes with one / two
+ * hypotheses per lane, [5] guard-band re-scans.  bench.py derives the kernel's binding-resource figure
+ * from these. */
+int m3d_score_stats(m3d_ctx *ctx, uint64_t out[8]);
+
 /* -------- multi-GPU: hypothesis sharding.  rank r scores hypotheses
  * [r*ceil(H/R), (r+1)*ceil(H/R)) of the SAME global sample table; one all-gather of the per-
  * hypothesis inlier counts; then every rank replays the identical ordered scan, so results do
@@ -110,7 +117,9 @@ typedef struct m3d_ransac_params {
 #define M3D_FLAG_EXACT_ONLY 1u /* score with the fp64 reference-order kernel only (slow; debug) */
 #define M3D_FLAG_NO_REFIT 2u   /* skip RefineModel's GeneralFit (model_out = minimal model)     */
 #define M3D_FLAG_DENSE 4u      /* score every point-hypothesis pair (no bounding-sphere culling) */
-#define M3D_FLAG_CLASSIFY 8u   /* always pre-sort the hypotheses into culled / dense ones (default: waves >= 16384 rows) */
+#define M3D_FLAG_CLASSIFY 8u   /* round-1 culling kernel (M3D_SCORE_PATH=cull) only: always pre-sort the hypotheses into
+                                  culled / dense ones (default there: launches of >= 12288 rows) */
+#define M3D_FLAG_STATS 16u     /* run the counting build of the scoring kernel (slower); read with m3d_score_stats */
 
 typedef struct m3d_ransac_stats {
     uint64_t best_index;     /* loop index i of the winning minimal model                      */

@@ -17,7 +17,7 @@ PLANE, SPHERE, CYLINDER = 0, 1, 2
 KSAMPLE = {PLANE: 3, SPHERE: 4, CYLINDER: 2}
 NPARAM = {PLANE: 4, SPHERE: 4, CYLINDER: 7}
 MATCH_FLANN, MATCH_ANNOY = 0, 1
-FLAG_EXACT_ONLY, FLAG_NO_REFIT, FLAG_DENSE, FLAG_CLASSIFY = 1, 2, 4, 8
+FLAG_EXACT_ONLY, FLAG_NO_REFIT, FLAG_DENSE, FLAG_CLASSIFY, FLAG_STATS = 1, 2, 4, 8, 16
 
 OK = 0
 ERR_INVALID_ARG, ERR_TOO_FEW_POINTS, ERR_PROBABILITY, ERR_NO_NORMALS = -1, -2, -3, -4
@@ -30,7 +30,7 @@ EXPORTS = [
     "m3d_cloud_upload", "m3d_cloud_from_device", "m3d_cloud_free", "m3d_cloud_size",
     "m3d_ransac_fit_cloud", "m3d_score_samples", "m3d_evaluate_model", "m3d_sample_table",
     "m3d_ordered_scan", "m3d_segment_plane_iterative", "m3d_match_correspondence", "m3d_nearest",
-    "m3d_ransac_registration", "m3d_least_squares_transform", "m3d_shard_rows", "m3d_sample_table_device",
+    "m3d_ransac_registration", "m3d_least_squares_transform", "m3d_shard_rows", "m3d_sample_table_device", "m3d_score_stats",
 ]
 
 
@@ -227,6 +227,13 @@ class Context:
         v = C.c_double(0)
         self._check(lib().m3d_probe_fp32_ffma(self.h, C.byref(v)))
         return float(v.value)
+
+    def score_stats(self):
+        """work counters of the launches run with FLAG_STATS since the last call (m3d_score_stats)"""
+        out = np.zeros(8, dtype=np.uint64)
+        self._check(lib().m3d_score_stats(self.h, _p(out, C.c_uint64)))
+        return {"tile_tests": int(out[0]), "tile_survivors": int(out[1]), "cell_pairs": int(out[2]),
+                "passes_1": int(out[3]), "passes_2": int(out[4]), "rescans": int(out[5])}
 
     def sample_table_device(self, seed, n, k, rows):
         """the sample table drawn on the GPU (m3d_sample_table_device): (rows, k) uint32, or None when the

@@ -16,6 +16,7 @@
 #include "loop_kernels.cuh"
 #include "ransac_kernels.cuh"
 #include "score_cull.cuh"
+#include "score_cell.cuh"
 #include "scan.h"
 
 using namespace m3d;
@@ -94,14 +95,15 @@ int cloud_create(m3d_ctx *ctx, const double *xyz, const double *nrm, size_t n, c
 /* scoring path: M3D_SCORE_PATH=dense keeps every point-hypothesis pair (score_kernel); default
  * (cull) uses the Morton-ordered copy for clouds of >= kCullMinPoints finite points */
 constexpr size_t kCullMinPoints = 2048;
-bool cull_enabled() {
+int score_path() { /* 0 dense (score_kernel), 1 score_cull_kernel (round 1), 2 score_cell_kernel (default) */
     static int v = -1;
     if (v < 0) {
         const char *e = getenv("M3D_SCORE_PATH");
-        v = (e && strcmp(e, "dense") == 0) ? 0 : 1;
+        v = (e && strcmp(e, "dense") == 0) ? 0 : ((e && strcmp(e, "cull") == 0) ? 1 : 2);
     }
-    return v != 0;
+    return v;
 }
+bool cull_enabled() { return score_path() != 0; }
 
 /* builds (once per upload) the Morton-ordered tile blob of score_cull.cuh: counting sort over a
  * 128^3 grid (histogram, 3-kernel scan, scatter) + bounding spheres */
@@ -160,6 +162,28 @@ int launch_cull_t(m3d_ctx *ctx, const ScoreArgs &a, uint32_t ntiles) {
     return M3D_OK;
 }
 
+template <int KIND, int THREADS, int HPT, bool STATS>
+int launch_cell_t(m3d_ctx *ctx, const ScoreArgs &a, uint32_t ntiles) {
+    const size_t smem = CellSmem<KIND, THREADS * HPT>::bytes(THREADS / 32);
+    M3D_CUDA(ctx, cudaFuncSetAttribute(score_cell_kernel<KIND, THREADS, HPT, STATS>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const uint32_t hb = (a.rows + THREADS * HPT - 1) / (THREADS * HPT);
+    int per_sm = 0;
+    M3D_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, score_cell_kernel<KIND, THREADS, HPT, STATS>,
+                                                                 THREADS + 32, smem));
+    const uint32_t slots = (uint32_t)ctx->sm_count * (uint32_t)std::max(per_sm, 1);
+    uint32_t per_hb = std::max<uint32_t>(1, (slots + hb - 1) / hb);
+    per_hb = std::min(per_hb, ntiles);
+    M3D_CUDA(ctx, ctx->d_tiles.reserve(sizeof(uint32_t) * (size_t)hb));
+    M3D_CUDA(ctx, cudaMemsetAsync(ctx->d_tiles.p, 0, sizeof(uint32_t) * (size_t)hb, ctx->stream));
+    ScoreArgs b = a;
+    b.tile_counter = ctx->d_tiles.as<uint32_t>();
+    dim3 grid(hb, per_hb);
+    score_cell_kernel<KIND, THREADS, HPT, STATS><<<grid, THREADS + 32, smem, ctx->stream>>>(b);
+    M3D_LAUNCHED(ctx);
+    return M3D_OK;
+}
+
 /* ---- launch of the hot kernel for one (wave, kind) */
 template <int KIND, int THREADS, int HPT>
 int launch_score_t(m3d_ctx *ctx, const ScoreArgs &a, uint32_t ntiles) {
@@ -206,7 +230,13 @@ int launch_one(m3d_ctx *ctx, ScoreArgs a, uint32_t ntiles, bool cull) {
     M3D_CUDA(ctx, cudaMemsetAsync(a.queue_count, 0, sizeof(uint32_t), ctx->stream));
     int rc;
     const int var = score_variant_override();
-    if (cull) {
+    if (cull && score_path() == 2) {
+        if (a.flags & M3D_FLAG_STATS)
+            rc = launch_cell_t<KIND, 256, 2, true>(ctx, a, ntiles);
+        else
+            rc = (a.rows >= 2048) ? launch_cell_t<KIND, 256, 2, false>(ctx, a, ntiles)
+                                  : launch_cell_t<KIND, 128, 1, false>(ctx, a, ntiles);
+    } else if (cull) {
         switch (var) {
             case 128 * 16 + 1: rc = launch_cull_t<KIND, 128, 1>(ctx, a, ntiles); break;
             case 128 * 16 + 2: rc = launch_cull_t<KIND, 128, 2>(ctx, a, ntiles); break;
@@ -270,7 +300,10 @@ int launch_score(m3d_ctx *ctx, const m3d_cloud *c, ScoreArgs a, bool exact_only)
         return M3D_OK;
     }
     const bool cull = a.blob && cull_enabled();
-    if (cull && (a.rows >= classify_min_rows() || (a.flags & M3D_FLAG_CLASSIFY))) {
+    /* score_cell_kernel evaluates a hypothesis that crosses most of the cloud at dense-kernel cost: only the
+     * round-1 culling kernel needs the pre-sort into culled / dense hypotheses */
+    if (cull && (score_path() == 1 || (a.flags & M3D_FLAG_CLASSIFY)) &&
+        (a.rows >= classify_min_rows() || (a.flags & M3D_FLAG_CLASSIFY))) {
         /* row_map: [rows for the culling kernel ...   ... rows for the dense kernel], part = the two sizes */
         M3D_CUDA(ctx, ctx->d_rowmap.reserve(sizeof(uint32_t) * ((size_t)a.rows + 2)));
         uint32_t *map = ctx->d_rowmap.as<uint32_t>() + 2, *part = ctx->d_rowmap.as<uint32_t>();
@@ -1005,6 +1038,19 @@ int m3d_sample_table_device(m3d_ctx *ctx, uint32_t seed, size_t n, int k, size_t
     M3D_CUDA(ctx, cudaMemcpyAsync(out, ctx->d_samples.p, sizeof(uint32_t) * rows * k, cudaMemcpyDeviceToHost, ctx->stream));
     M3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return hs->draw.status ? 0 : 1;
+}
+
+/* counters of the statistics build of score_cell_kernel (M3D_FLAG_STATS), read and cleared:
+ * [0] (hypothesis, tile) tests, [1] survivors, [2] (hypothesis, cell) list entries (x32 = point-hypothesis
+ * pairs evaluated), [3] one-per-lane passes, [4] two-per-lane passes, [5] guard-band re-scans */
+int m3d_score_stats(m3d_ctx *ctx, uint64_t out[8]) {
+    if (!ctx || !out) return M3D_ERR_INVALID_ARG;
+    unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0}, v[8];
+    M3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    M3D_CUDA(ctx, cudaMemcpyFromSymbol(v, g_cell_stats, sizeof v));
+    M3D_CUDA(ctx, cudaMemcpyToSymbol(g_cell_stats, z, sizeof z));
+    for (int i = 0; i < 8; ++i) out[i] = v[i];
+    return M3D_OK;
 }
 
 #ifdef M3D_CULL_STATS
