@@ -164,7 +164,7 @@ int launch_cull_t(m3d_ctx *ctx, const ScoreArgs &a, uint32_t ntiles) {
 
 template <int KIND, int THREADS, int HPT, bool STATS>
 int launch_cell_t(m3d_ctx *ctx, const ScoreArgs &a, uint32_t ntiles) {
-    const size_t smem = CellSmem<KIND, THREADS * HPT>::bytes(THREADS / 32);
+    const size_t smem = CellSmem<KIND, THREADS, THREADS * HPT>::bytes();
     M3D_CUDA(ctx, cudaFuncSetAttribute(score_cell_kernel<KIND, THREADS, HPT, STATS>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const uint32_t hb = (a.rows + THREADS * HPT - 1) / (THREADS * HPT);
@@ -231,11 +231,17 @@ int launch_one(m3d_ctx *ctx, ScoreArgs a, uint32_t ntiles, bool cull) {
     int rc;
     const int var = score_variant_override();
     if (cull && score_path() == 2) {
+        /* 1024 hypotheses per CTA (one CTA of 16 consumer warps per SM) once the launch fills the machine that
+         * way: longer per-cell lists (fewer half-empty passes), half the tile tests and barriers per pair */
+        static const int cell_var = getenv("M3D_CELL_VARIANT") ? atoi(getenv("M3D_CELL_VARIANT")) : 0;
         if (a.flags & M3D_FLAG_STATS)
-            rc = launch_cell_t<KIND, 256, 2, true>(ctx, a, ntiles);
+            rc = (cell_var == 256) ? launch_cell_t<KIND, 256, 2, true>(ctx, a, ntiles) : launch_cell_t<KIND, 512, 2, true>(ctx, a, ntiles);
+        else if (cell_var == 512 || (cell_var == 0 && a.rows >= 4096))
+            rc = launch_cell_t<KIND, 512, 2, false>(ctx, a, ntiles);
+        else if (cell_var == 256 || (cell_var == 0 && a.rows >= 1024))
+            rc = launch_cell_t<KIND, 256, 2, false>(ctx, a, ntiles);
         else
-            rc = (a.rows >= 2048) ? launch_cell_t<KIND, 256, 2, false>(ctx, a, ntiles)
-                                  : launch_cell_t<KIND, 128, 1, false>(ctx, a, ntiles);
+            rc = launch_cell_t<KIND, 128, 1, false>(ctx, a, ntiles);
     } else if (cull) {
         switch (var) {
             case 128 * 16 + 1: rc = launch_cull_t<KIND, 128, 1>(ctx, a, ntiles); break;

@@ -21,36 +21,43 @@
  *
  * A hypothesis that passes through most of the cloud simply sits in most lists and is evaluated at
  * dense-kernel cost, so no pre-classification of the hypotheses (cull_classify_kernel) is needed.
- * Two consumer-only named barriers per tile separate the phases; the producer warp keeps a 2-stage
- * TMA ring filled (a tile takes ~10 us of CTA time, far above the copy latency).
+ * Two consumer-only named barriers per tile separate the phases (see the pipeline at the end of the kernel);
+ * the producer warp keeps a 2-3 stage TMA ring filled (a tile takes ~10 us of CTA time, far above the copy
+ * latency) and parks on its mbarrier with a suspend-time hint instead of spinning.
  */
 #pragma once
 #include "score_cull.cuh"
 
 namespace m3d {
 
-#ifndef M3D_CELL_STAGES
-#define M3D_CELL_STAGES 2
-#endif
-constexpr int kCellStages = M3D_CELL_STAGES;
-
 /* counters of the statistics build of the kernel (STATS = true): what the bench reports as the work the
- * kernel actually did.  [0] (group, tile) tests x32, [1] (hypothesis, tile) survivors, [2] (hypothesis,
+ * kernel actually did.  [0] (hypothesis, tile) tests, [1] (hypothesis, tile) survivors, [2] (hypothesis,
  * cell) list entries, [3] one-per-lane passes, [4] two-per-lane passes, [5] guard-band re-scans */
 __device__ unsigned long long g_cell_stats[8];
 
-template <int KIND, int NH>
+template <int THREADS>
+struct CellCfg {
+    static constexpr int kStages = THREADS >= 512 ? 3 : 2;     /* TMA ring depth                              */
+    static constexpr int kMinBlocks = THREADS >= 512 ? 1 : (THREADS >= 256 ? 2 : 4);
+};
+
+template <int KIND, int THREADS, int NH>
 struct CellSmem {
+    static constexpr int kStages = CellCfg<THREADS>::kStages;
     static constexpr int kPlanes = KIND == kPlane ? 2 : (KIND == kSphere ? 3 : 4); /* float4 planes of hypothesis parameters */
     static constexpr int kListStride = NH + 2; /* u16 entries per cell list; +2 shifts consecutive cells by one bank */
-    static constexpr size_t bytes(int warps) {
-        return (size_t)kCellStages * kBlobF4 * sizeof(float4)          /* tile ring                    */
-               + (size_t)kPlanes * (NH + 1) * sizeof(float4)           /* parameters (+ one dummy row) */
-               + (size_t)kTileCells * kListStride * sizeof(uint16_t)   /* per-cell hypothesis lists    */
-               + (size_t)warps * kQBuf * sizeof(uint2)                 /* guard-band staging           */
-               + (size_t)NH * sizeof(uint32_t)                         /* per-hypothesis counts        */
-               + (2 * kTileCells + 2 + kCellStages) * sizeof(uint32_t) /* list lengths x2, unit cursors x2, group cursors */
-               + 2 * kCellStages * sizeof(uint64_t) + kCellStages * sizeof(uint32_t) + 32;
+    static constexpr size_t kListBytes = ((size_t)kTileCells * kListStride * sizeof(uint16_t) + 15) & ~(size_t)15;
+    static constexpr size_t kSurvBytes = ((size_t)NH * sizeof(uint16_t) + 15) & ~(size_t)15;
+    static constexpr size_t bytes() {
+        return (size_t)kStages * kBlobF4 * sizeof(float4)             /* tile ring                    */
+               + (size_t)kPlanes * (NH + 1) * sizeof(float4)          /* parameters (+ one dummy row) */
+               + kListBytes                                            /* per-cell hypothesis lists    */
+               + kSurvBytes                                            /* hypotheses surviving the tile test */
+               + (size_t)(THREADS / 32) * kQBuf * sizeof(uint2)       /* guard-band staging           */
+               + 2 * kStages * sizeof(uint64_t)                       /* full / empty barriers        */
+               + (size_t)NH * sizeof(uint32_t)                        /* per-hypothesis counts        */
+               + (kStages + 2 * kTileCells + 6) * sizeof(uint32_t)    /* tile ids, list lengths x2, cursors */
+               + 32;
     }
 };
 
@@ -85,46 +92,47 @@ __device__ __forceinline__ void load_fast_cull(const float4 *hyp, uint32_t h, Fa
 }
 
 template <int KIND, int THREADS, int HPT, bool STATS>
-__global__ void __launch_bounds__(THREADS + 32, (THREADS >= 256 ? 2 : 4)) score_cell_kernel(const ScoreArgs a) {
+__global__ void __launch_bounds__(THREADS + 32, CellCfg<THREADS>::kMinBlocks) score_cell_kernel(const ScoreArgs a) {
     constexpr int NH = THREADS * HPT; /* hypotheses of the CTA */
     constexpr int NC = KIND == kCylinder ? 8 : 4;
     constexpr int PB = KIND == kCylinder ? 2 : 1;
     constexpr int WARPS = THREADS / 32;
-    using L = CellSmem<KIND, NH>;
+    constexpr int S = CellCfg<THREADS>::kStages;
+    using L = CellSmem<KIND, THREADS, NH>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float4 *tiles = reinterpret_cast<float4 *>(smem_raw);
-    float4 *hyp = tiles + (size_t)kCellStages * kBlobF4;
+    float4 *hyp = tiles + (size_t)S * kBlobF4;
     uint16_t *lists = reinterpret_cast<uint16_t *>(hyp + (size_t)L::kPlanes * (NH + 1));
-    uint2 *qbufs = reinterpret_cast<uint2 *>(reinterpret_cast<unsigned char *>(lists) +
-                                             (((size_t)kTileCells * L::kListStride * sizeof(uint16_t) + 15) & ~(size_t)15));
+    uint16_t *surv = reinterpret_cast<uint16_t *>(reinterpret_cast<unsigned char *>(lists) + L::kListBytes);
+    uint2 *qbufs = reinterpret_cast<uint2 *>(reinterpret_cast<unsigned char *>(surv) + L::kSurvBytes);
     uint64_t *full = reinterpret_cast<uint64_t *>(qbufs + WARPS * kQBuf);
-    uint64_t *empty = full + kCellStages;
-    volatile uint32_t *tile_id = reinterpret_cast<volatile uint32_t *>(empty + kCellStages);
-    uint32_t *scnt = const_cast<uint32_t *>(tile_id) + kCellStages; /* inlier counts of the CTA's hypotheses            */
-    uint32_t *grp_next = scnt + NH;                                 /* next unclaimed hypothesis group of a stage's tile */
-    uint32_t *ccnt = grp_next + kCellStages;                        /* [2][32] list lengths, by tile parity              */
-    uint32_t *unit_next = ccnt + 2 * kTileCells;                    /* [2] next unclaimed (cell, pass) unit              */
+    uint64_t *empty = full + S;
+    uint32_t *scnt = reinterpret_cast<uint32_t *>(empty + S);  /* inlier counts of the CTA's hypotheses      */
+    volatile uint32_t *tile_id = scnt + NH;                    /* [S] tile in each stage                     */
+    uint32_t *ccnt = const_cast<uint32_t *>(tile_id) + S;      /* [2][32] list lengths, by tile parity       */
+    uint32_t *unit_next = ccnt + 2 * kTileCells;               /* [2] next unclaimed evaluation unit         */
+    uint32_t *surv_cnt = unit_next + 2;                        /* [2] survivors of the tile test             */
+    uint32_t *surv_next = surv_cnt + 2;                        /* [2] next unclaimed survivor                */
 
     const int tid = threadIdx.x;
     const uint32_t ntiles = (a.n + kTile - 1) / kTile;
 
     if (tid == THREADS) {
 #pragma unroll
-        for (int s = 0; s < kCellStages; ++s) {
+        for (int s = 0; s < S; ++s) {
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], 1);
         }
         mbar_fence_init();
     }
-    if (tid < 2 * kTileCells) ccnt[tid] = 0;
-    if (tid < 2) unit_next[tid] = 0;
+    if (tid < 2 * kTileCells + 6) ccnt[tid] = 0; /* list lengths and all cursors */
     __syncthreads();
 
     if (tid >= THREADS) { /* ---------------- producer: claims tiles, one bulk copy per tile */
         if (tid == THREADS) {
             for (uint32_t k = 0;; ++k) {
-                const int st = k % kCellStages;
-                if (k >= kCellStages) mbar_wait_relaxed(&empty[st], ((k / kCellStages) - 1) & 1);
+                const int st = k % S;
+                if (k >= (uint32_t)S) mbar_wait_relaxed(&empty[st], ((k / S) - 1) & 1);
                 const uint32_t t = atomicAdd(&a.tile_counter[blockIdx.x], 1u);
                 if (t >= ntiles) {
                     tile_id[st] = kNoTile;
@@ -132,7 +140,6 @@ __global__ void __launch_bounds__(THREADS + 32, (THREADS >= 256 ? 2 : 4)) score_
                     break;
                 }
                 tile_id[st] = t;
-                grp_next[st] = 0; /* published with tile_id by the barrier's release/acquire */
                 tma_load_1d(tiles + (size_t)st * kBlobF4, a.blob + (size_t)t * kBlobF4,
                             (uint32_t)(kBlobF4 * sizeof(float4)), &full[st]);
             }
@@ -144,6 +151,7 @@ __global__ void __launch_bounds__(THREADS + 32, (THREADS >= 256 ? 2 : 4)) score_
     const CloudMeta M = *a.meta;
     const unsigned fullmask = 0xffffffffu;
     const int lane = tid & 31, warp = tid >> 5;
+    const unsigned ltmask = (1u << lane) - 1;
     uint2 *qbuf = qbufs + warp * kQBuf;
     uint32_t qn = 0; /* entries staged in qbuf (warp-uniform) */
     unsigned long long st_tests = 0, st_tiles = 0, st_cells = 0, st_p1 = 0, st_p2 = 0, st_rescan = 0;
@@ -201,11 +209,12 @@ __global__ void __launch_bounds__(THREADS + 32, (THREADS >= 256 ? 2 : 4)) score_
         if (KIND != kPlane) hyp[(PB + 1) * (NH + 1) + hl] = make_float4(ck.c, ck.d, 0.f, 0.f);
         scnt[hl] = 0;
     }
-    if (tid == 0) { /* the dummy hypothesis (index NH) pads incomplete passes: never an inlier, never in the band */
+    if (tid == 0) { /* the dummy hypothesis (index NH) pads incomplete passes / chunks: never an inlier, never in the
+                     * band, culled by every sphere test (the encoding make_cull uses for a failed MinimalFit) */
         hyp[NH] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (KIND == kCylinder) hyp[(NH + 1) + NH] = make_float4(0.f, 0.f, 0.f, 0.f);
-        hyp[PB * (NH + 1) + NH] = make_float4(-1.f, 0.f, 0.f, 0.f);
-        if (KIND != kPlane) hyp[(PB + 1) * (NH + 1) + NH] = make_float4(0.f, 0.f, 0.f, 0.f);
+        hyp[PB * (NH + 1) + NH] = KIND == kPlane ? make_float4(-1.f, 0.f, -1.f, 0.f) : make_float4(-1.f, 0.f, 0.f, 0.f);
+        if (KIND != kPlane) hyp[(PB + 1) * (NH + 1) + NH] = make_float4(-INFINITY, -1.f, 0.f, 0.f);
     }
     asm volatile("bar.sync 1, %0;" ::"n"(THREADS) : "memory");
 
@@ -213,7 +222,7 @@ __global__ void __launch_bounds__(THREADS + 32, (THREADS >= 256 ? 2 : 4)) score_
     const uint32_t cta_row0 = blockIdx.x * HPT * THREADS; /* local index + cta_row0 = row of the launch */
     uint32_t nres = 0;
 
-    /* the rare path: lane's hypothesis `hown` saw a point of cell `c` inside its guard band.  The whole warp
+    /* the rare path: lane's hypothesis `hown` saw a point of the cell inside its guard band.  The whole warp
      * re-examines the cell for every flagged hypothesis (lane = point) and stages (row, sorted position,
      * provisional decision) for resolve_queue_kernel. */
     auto rescan = [&](unsigned need, uint32_t hown, const float4 *cell, uint32_t gbase) {
@@ -233,121 +242,173 @@ __global__ void __launch_bounds__(THREADS + 32, (THREADS >= 256 ? 2 : 4)) score_
             if (qn + na > (uint32_t)kQBuf) flush_queue();
             if (amb) {
                 const uint32_t prov = __float_as_uint(v) >> 31;
-                qbuf[qn + __popc(am & ((1u << lane) - 1))] = make_uint2(cta_row0 + h, (gbase + lane) | (prov << 31));
+                qbuf[qn + __popc(am & ltmask)] = make_uint2(cta_row0 + h, (gbase + lane) | (prov << 31));
             }
             qn += na;
             nres += (lane == 0) ? na : 0u;
         }
     };
 
-    for (uint32_t k = 0;; ++k) {
-        const int st = k % kCellStages;
-        mbar_wait(&full[st], (k / kCellStages) & 1);
-        const uint32_t t = tile_id[st];
-        if (t == kNoTile) break;
-        const float4 *sp = tiles + (size_t)st * kBlobF4;
-        const uint32_t base = t * kTile;
+    /* step A of tile k: lane = hypothesis against the tile's bounding sphere; the survivors go to `surv`.
+     * Groups are dealt to the warps statically (HPT each): the step is short and perfectly balanced. */
+    auto tile_tests = [&](uint32_t k) -> bool {
+        const int st = k % S;
+        mbar_wait(&full[st], (k / S) & 1);
+        if (tile_id[st] == kNoTile) return false;
+        const float4 tb = tiles[(size_t)st * kBlobF4 + kTile + kTileCells];
+        for (uint32_t grp = warp; grp < kGroups; grp += WARPS) {
+            Fast<KIND> g;
+            CullP gk;
+            load_fast_cull<KIND, NH>(hyp, grp * 32 + lane, g, gk);
+            const bool alive = !cull_test<KIND>(g.c, gk, tb);
+            const unsigned live = __ballot_sync(fullmask, alive);
+            if (STATS) st_tests += 32, st_tiles += __popc(live);
+            if (live) {
+                uint32_t pos = 0;
+                if (lane == 0) pos = atomicAdd(&surv_cnt[k & 1], (uint32_t)__popc(live));
+                pos = __shfl_sync(fullmask, pos, 0);
+                if (alive) surv[pos + __popc(live & ltmask)] = (uint16_t)(grp * 32 + lane);
+            }
+        }
+        return true;
+    };
+    /* step B of tile k: lane = cell; every surviving hypothesis is tested against the 32 cell spheres and the
+     * lane whose cell survives appends it to that cell's list.  Survivors are claimed four at a time. */
+    auto cell_tests = [&](uint32_t k) {
+        const float4 *sp = tiles + (size_t)(k % S) * kBlobF4;
+        const float4 cb = sp[kTile + lane];
         uint32_t *cc = ccnt + (k & 1) * kTileCells;
-        /* ---------------------------------------------------------------- phase 1: who survives where */
-        {
-            const float4 tb = sp[kTile + kTileCells]; /* tile sphere (broadcast) */
-            const float4 cb = sp[kTile + lane];       /* this lane's cell sphere */
-            uint16_t *mylist = lists + lane * L::kListStride;
-            for (;;) {
-                uint32_t grp = 0;
-                if (lane == 0) grp = atomicAdd(&grp_next[st], 1u);
-                grp = __shfl_sync(fullmask, grp, 0);
-                if (grp >= kGroups) break;
-                const uint32_t hbase = grp * 32;
-                Fast<KIND> g;
-                CullP gk;
-                load_fast_cull<KIND, NH>(hyp, hbase + lane, g, gk); /* lane = hypothesis */
-                unsigned live = __ballot_sync(fullmask, !cull_test<KIND>(g.c, gk, tb));
-                if (STATS) st_tests += 32, st_tiles += __popc(live);
-                while (live) { /* lane = cell; two hypotheses per trip for instruction-level parallelism */
-                    const int s0 = __ffs(live) - 1;
-                    live &= live - 1;
-                    const bool two = live != 0;
-                    const int s1 = two ? __ffs(live) - 1 : s0;
-                    live &= live - 1; /* no-op when live == 0 */
-                    Fast<KIND> g0, g1;
-                    CullP k0, k1;
-                    load_fast_cull<KIND, NH>(hyp, hbase + s0, g0, k0);
-                    load_fast_cull<KIND, NH>(hyp, hbase + s1, g1, k1);
-                    const bool keep0 = !cull_test<KIND>(g0.c, k0, cb);
-                    const bool keep1 = two && !cull_test<KIND>(g1.c, k1, cb);
-                    if (keep0 || keep1) {
-                        const uint32_t pos = atomicAdd(&cc[lane], (keep0 ? 1u : 0u) + (keep1 ? 1u : 0u));
-                        if (keep0) mylist[pos] = (uint16_t)(hbase + s0);
-                        if (keep1) mylist[pos + (keep0 ? 1u : 0u)] = (uint16_t)(hbase + s1);
-                    }
-                    if (STATS) st_cells += __popc(__ballot_sync(fullmask, keep0)) + __popc(__ballot_sync(fullmask, keep1));
+        uint16_t *mylist = lists + lane * L::kListStride;
+        const uint32_t total = surv_cnt[k & 1];
+        if (warp == 0 && lane < 2) { /* the other parity's survivor cursors: idle until the next tile's step A */
+            if (lane == 0) surv_cnt[(k + 1) & 1] = 0;
+            else surv_next[(k + 1) & 1] = 0;
+        }
+        for (;;) {
+            uint32_t i0 = 0;
+            if (lane == 0) i0 = atomicAdd(&surv_next[k & 1], 4u);
+            i0 = __shfl_sync(fullmask, i0, 0);
+            if (i0 >= total) break;
+#pragma unroll
+            for (int half = 0; half < 2; ++half) { /* two hypotheses per trip for instruction-level parallelism */
+                const uint32_t i = i0 + 2 * half;
+                if (i >= total) break;
+                const uint32_t h0 = surv[i];
+                const uint32_t h1 = (i + 1 < total) ? (uint32_t)surv[i + 1] : (uint32_t)NH;
+                Fast<KIND> g0, g1;
+                CullP k0, k1;
+                load_fast_cull<KIND, NH>(hyp, h0, g0, k0);
+                load_fast_cull<KIND, NH>(hyp, h1, g1, k1);
+                const bool keep0 = !cull_test<KIND>(g0.c, k0, cb);
+                const bool keep1 = !cull_test<KIND>(g1.c, k1, cb); /* the dummy is culled everywhere */
+                if (keep0 || keep1) {
+                    const uint32_t pos = atomicAdd(&cc[lane], (keep0 ? 1u : 0u) + (keep1 ? 1u : 0u));
+                    if (keep0) mylist[pos] = (uint16_t)h0;
+                    if (keep1) mylist[pos + (keep0 ? 1u : 0u)] = (uint16_t)h1;
                 }
+                if (STATS) st_cells += __popc(__ballot_sync(fullmask, keep0)) + __popc(__ballot_sync(fullmask, keep1));
             }
         }
-        asm volatile("bar.sync 1, %0;" ::"n"(THREADS) : "memory"); /* the lists of this tile are complete */
-        /* ---------------------------------------------------------------- phase 2: evaluate per cell */
-        {
-            uint32_t maxc = cc[lane];
-            maxc = __reduce_max_sync(fullmask, maxc);
-            const uint32_t units = ((maxc + 63) >> 6) * kTileCells; /* unit u = (cell u % 32, entries [64 (u / 32), +64)) */
-            if (warp == 0) { /* reset the other parity's cursors for the next tile (nobody touches them in this phase) */
-                ccnt[((k + 1) & 1) * kTileCells + lane] = 0;
-                if (lane == 0) unit_next[(k + 1) & 1] = 0;
-            }
-            for (;;) {
-                uint32_t u = 0;
-                if (lane == 0) u = atomicAdd(&unit_next[k & 1], 1u);
-                u = __shfl_sync(fullmask, u, 0);
-                if (u >= units) break;
-                const uint32_t c = u & (kTileCells - 1), off = (u / kTileCells) * 64;
-                const uint32_t cnt = cc[c];
-                if (off >= cnt) continue;
-                const uint32_t rem = cnt - off;
-                const uint16_t *lst = lists + c * L::kListStride + off;
-                const float4 *cell = sp + c * kCellPts;
-                if (rem > 32) { /* two hypotheses per lane: packed fp32x2 arithmetic, bit-identical halves */
-                    const uint32_t h0 = lst[lane];
-                    const uint32_t h1 = (32u + lane < rem) ? (uint32_t)lst[32 + lane] : (uint32_t)NH;
-                    Fast<KIND> f0, f1;
-                    load_fast<KIND, NH>(hyp, h0, f0);
-                    load_fast<KIND, NH>(hyp, h1, f1);
-                    Fast2<KIND> f2;
-                    pack_fast<KIND>(f0, f1, f2);
-                    uint32_t c0 = 0, c1 = 0;
-                    float m0 = INFINITY, m1 = INFINITY;
+    };
+    /* phase 2 of tile k: lane = hypothesis.  A unit = up to 64 entries of one cell's list; the warp gathers their
+     * coefficients once and streams the cell's 32 points as broadcast loads (the dense kernel's inner loop). */
+    auto evaluate = [&](uint32_t k) {
+        const float4 *sp = tiles + (size_t)(k % S) * kBlobF4;
+        const uint32_t base = tile_id[k % S] * kTile;
+        const uint32_t *cc = ccnt + (k & 1) * kTileCells;
+        /* units are numbered cell by cell (inclusive scan of the cells' pass counts, in registers): no claim is empty */
+        const uint32_t mycnt = cc[lane];
+        const uint32_t mypass = (mycnt + 63) >> 6;
+        uint32_t inc = mypass;
 #pragma unroll
-                    for (int j = 0; j < kCellPts; ++j) {
-                        float t0, t1;
-                        fast_eval2<KIND>(f2, cell[j], t0, t1);
-                        accumulate_v(__fsub_rn(fabsf(t0), f0.T), c0, m0);
-                        accumulate_v(__fsub_rn(fabsf(t1), f1.T), c1, m1);
-                    }
-                    const bool fl0 = m0 < f0.band, fl1 = m1 < f1.band;
-                    if (__any_sync(fullmask, fl0 || fl1)) {
-                        rescan(__ballot_sync(fullmask, fl0), h0, cell, base + c * kCellPts);
-                        rescan(__ballot_sync(fullmask, fl1), h1, cell, base + c * kCellPts);
-                    }
-                    if (c0) atomicAdd(&scnt[h0], c0);
-                    if (c1) atomicAdd(&scnt[h1], c1); /* h1 == NH (dummy) never counts */
-                    if (STATS) st_p2++;
-                } else {
-                    const uint32_t h0 = (lane < rem) ? (uint32_t)lst[lane] : (uint32_t)NH;
-                    Fast<KIND> f0;
-                    load_fast<KIND, NH>(hyp, h0, f0);
-                    uint32_t c0 = 0;
-                    float m0 = INFINITY;
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t tt = __shfl_up_sync(fullmask, inc, o);
+            if (lane >= o) inc += tt;
+        }
+        const uint32_t units = __shfl_sync(fullmask, inc, 31);
+        if (warp == 0) { /* reset the other parity's list lengths / unit cursor for the next tile (idle in this phase) */
+            ccnt[((k + 1) & 1) * kTileCells + lane] = 0;
+            if (lane == 0) unit_next[(k + 1) & 1] = 0;
+        }
+        for (;;) {
+            uint32_t u = 0;
+            if (lane == 0) u = atomicAdd(&unit_next[k & 1], 1u);
+            u = __shfl_sync(fullmask, u, 0);
+            if (u >= units) break;
+            const uint32_t c = __popc(__ballot_sync(fullmask, inc <= u)); /* first cell whose units reach past u */
+            const uint32_t off = (u - __shfl_sync(fullmask, inc - mypass, c)) * 64;
+            const uint32_t rem = __shfl_sync(fullmask, mycnt, c) - off;
+            const uint16_t *lst = lists + c * L::kListStride + off;
+            const float4 *cell = sp + c * kCellPts;
+            if (rem > 32) { /* two hypotheses per lane: packed fp32x2 arithmetic, bit-identical halves */
+                const uint32_t h0 = lst[lane];
+                const uint32_t h1 = (32u + lane < rem) ? (uint32_t)lst[32 + lane] : (uint32_t)NH;
+                Fast<KIND> f0, f1;
+                load_fast<KIND, NH>(hyp, h0, f0);
+                load_fast<KIND, NH>(hyp, h1, f1);
+                /* packed ONCE per pass.  The halves arrive in LDS.128 register quads, so ptxas has to move them
+                 * into aligned pairs -- and, left alone, re-materialises those moves in front of every FFMA2 of the
+                 * point loop (6 MOV per point).  Routing each pair through x * 1 + (-0) (exact for every x, -0
+                 * included) makes the pair the result of a real instruction: it is built once and stays. */
+                Fast2<KIND> f2;
+                {
+                    const f32x2_t one2 = pack2(1.f, 1.f), nz2 = pack2(-0.f, -0.f);
 #pragma unroll
-                    for (int j = 0; j < kCellPts; ++j) accumulate_v(fast_v<KIND>(f0, cell[j]), c0, m0);
-                    const bool fl0 = m0 < f0.band;
-                    if (__any_sync(fullmask, fl0)) rescan(__ballot_sync(fullmask, fl0), h0, cell, base + c * kCellPts);
-                    if (c0) atomicAdd(&scnt[h0], c0);
-                    if (STATS) st_p1++;
+                    for (int i = 0; i < NC; ++i)
+                        asm volatile("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(f2.c[i]) : "l"(pack2(f0.c[i], f1.c[i])), "l"(one2), "l"(nz2));
                 }
+                uint32_t c0 = 0, c1 = 0;
+                float m0 = INFINITY, m1 = INFINITY;
+#pragma unroll
+                for (int j = 0; j < kCellPts; ++j) {
+                    float t0, t1;
+                    fast_eval2<KIND>(f2, cell[j], t0, t1);
+                    accumulate_v(__fsub_rn(fabsf(t0), f0.T), c0, m0);
+                    accumulate_v(__fsub_rn(fabsf(t1), f1.T), c1, m1);
+                }
+                const bool fl0 = m0 < f0.band, fl1 = m1 < f1.band;
+                if (__any_sync(fullmask, fl0 || fl1)) {
+                    rescan(__ballot_sync(fullmask, fl0), h0, cell, base + c * kCellPts);
+                    rescan(__ballot_sync(fullmask, fl1), h1, cell, base + c * kCellPts);
+                }
+                if (c0) atomicAdd(&scnt[h0], c0);
+                if (c1) atomicAdd(&scnt[h1], c1); /* h1 == NH (dummy) never counts */
+                if (STATS) st_p2++;
+            } else {
+                const uint32_t h0 = (lane < rem) ? (uint32_t)lst[lane] : (uint32_t)NH;
+                Fast<KIND> f0;
+                load_fast<KIND, NH>(hyp, h0, f0);
+                uint32_t c0 = 0;
+                float m0 = INFINITY;
+#pragma unroll
+                for (int j = 0; j < kCellPts; ++j) accumulate_v(fast_v<KIND>(f0, cell[j]), c0, m0);
+                const bool fl0 = m0 < f0.band;
+                if (__any_sync(fullmask, fl0)) rescan(__ballot_sync(fullmask, fl0), h0, cell, base + c * kCellPts);
+                if (c0) atomicAdd(&scnt[h0], c0);
+                if (STATS) st_p1++;
             }
         }
-        asm volatile("bar.sync 1, %0;" ::"n"(THREADS) : "memory"); /* lists and tile consumed */
-        if (tid == 0) mbar_arrive(&empty[st]);
+    };
+
+    /* Software pipeline over the tiles, two consumer-only barriers per tile:
+     *     [evaluate(k) ; tile_tests(k+1)]  X  [cell_tests(k+1)]  Y  [evaluate(k+1) ; tile_tests(k+2)]  X ...
+     * X: every warp is done with tile k (its stage goes back to the producer) and the survivor list of tile k+1
+     * is complete; Y: the cell lists of tile k+1 are complete.  The short, statically balanced tile_tests step
+     * rides on the long evaluate phase instead of needing a barrier of its own. */
+    bool more = tile_tests(0);
+    asm volatile("bar.sync 1, %0;" ::"n"(THREADS) : "memory");
+    if (more) {
+        cell_tests(0);
+        asm volatile("bar.sync 1, %0;" ::"n"(THREADS) : "memory");
+        for (uint32_t k = 0;; ++k) {
+            evaluate(k);
+            more = tile_tests(k + 1);
+            asm volatile("bar.sync 1, %0;" ::"n"(THREADS) : "memory"); /* X */
+            if (tid == 0) mbar_arrive(&empty[k % S]);
+            if (!more) break;
+            cell_tests(k + 1);
+            asm volatile("bar.sync 1, %0;" ::"n"(THREADS) : "memory"); /* Y */
+        }
     }
 
     flush_queue();

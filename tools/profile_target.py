@@ -16,6 +16,17 @@ if what == "ransac":
         for rep in range(2):
             rc, model, inl, st = ctx.ransac_fit_cloud(kind, cloud, 0.01, 10000, 1.0, seed=rep)
             print(kind, rep, st["score_ms"], st["device_ms"], st["exact_resolves"])
+elif what == "stats":  # work counters of the scoring kernel (statistics build, M3D_FLAG_STATS)
+    import json
+    xyz, nrm = synth.make_c2()
+    cloud = ctx.upload(xyz, nrm)
+    for kind in (0, 1, 2):
+        rc, model, inl, st = ctx.ransac_fit_cloud(kind, cloud, 0.01, 10000, 1.0, seed=1, flags=capi.FLAG_STATS)
+        s = ctx.score_stats()
+        s["pairs_evaluated_frac"] = s["cell_pairs"] * 32 / (1e6 * 1e4)
+        s["lane_slots"] = 32 * s["passes_1"] + 64 * s["passes_2"]
+        s["lane_efficiency"] = s["cell_pairs"] / max(s["lane_slots"], 1)
+        print(kind, st["score_ms"], json.dumps(s))
 else:
     d = synth.make_c4()
     i0, i1, ms = ctx.match_correspondence(d["src_feat"], d["dst_feat"])
