@@ -222,6 +222,54 @@ def cpu_baseline(xyz, nrm, budget_s=12.0):
     return out
 
 
+def kernel_profile():
+    """ncu figures of the dominant kernel kept under profiles/ (written by tools/ncu_summary.py from an ncu --set full
+    capture of THIS kernel build: the file records the sha of the kernel source, so a stale profile is visible)."""
+    import hashlib
+    p = os.path.join(ROOT, "profiles", "score_kernel_ncu.json")
+    src = os.path.join(ROOT, "misc3d_b200", "csrc", "score_cell.cuh")
+    if not os.path.exists(p):
+        return None
+    try:
+        d = json.load(open(p))
+        d["stale"] = d.get("kernel_source_sha16") != hashlib.sha256(open(src, "rb").read()).hexdigest()[:16]
+        return d
+    except Exception:
+        return None
+
+
+def c5_leg(ctx, capi, synth, dist, dev, rank, world, reps=3):
+    """BASELINE config C5 -- fit_plane, 4M points x 100k hypotheses, STRONG scaling: the 100k hypotheses are sharded
+    over the ranks (one 64-byte best record per rank is exchanged).  Returns ms per fit (max over ranks)."""
+    import torch
+    n, H = 4_000_000, 100_000
+    xyz = synth.make_c1(n=n, seed=SEED)
+    cloud = ctx.upload(xyz)
+    res = None
+    for _ in range(2):
+        res = ctx.ransac_fit_cloud(0, cloud, THR, H, 1.0, seed=7, want_inliers=False)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    score = []
+    for r in range(reps):
+        res = ctx.ransac_fit_cloud(0, cloud, THR, H, 1.0, seed=7, want_inliers=False)
+        score.append(res[3]["score_ms"])
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / reps
+    t = torch.tensor([dt], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = 1e3 * float(t.item())
+    cloud.free()
+    st = res[3]
+    return {"workload": "C5: fit_plane, 4M points x 100k hypotheses, probability 1.0; hypotheses sharded over the ranks "
+                        "(strong scaling), cloud resident", "ms_per_fit": ms, "hypotheses_per_sec": H / (ms * 1e-3),
+            "point_hypotheses_per_sec": float(n) * H / (ms * 1e-3), "score_ms_rank0": float(np.mean(score)),
+            "best_index": int(st["best_index"]), "best_count": int(st["best_count"]), "n_gpus": world}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -229,6 +277,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-extras", action="store_true", help="skip the pageable / pybind / C5 legs")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -281,13 +330,28 @@ def main():
             out.append((rc, len(inl), st))
         return out
 
-    def step_e2e(seed):
+    def step_e2e(seed, pts, nrms, buf):
         d2h = 0
         for kind in KINDS:
-            rc, model, inl, st = ctx.ransac_fit(kind, np_xyz, np_nrm if kind == 2 else None, THR, H, 1.0,
-                                                seed=seed + kind, inl_buf=inl_buf)
-            d2h += inl.nbytes + 4 * H
+            rc, model, inl, st = ctx.ransac_fit(kind, pts, nrms if kind == 2 else None, THR, H, 1.0,
+                                                seed=seed + kind, inl_buf=buf)
+            d2h += inl.nbytes + 64 * world
         return d2h
+
+    def timed_e2e(step, n_warm=2):
+        for w in range(n_warm):
+            step(3000 + w)
+        barrier()
+        t0 = time.perf_counter()
+        out = None
+        for s in range(args.steps):
+            out = step(4000 + 3 * s)
+        barrier()
+        dt = time.perf_counter() - t0
+        t = torch.tensor([dt], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return 3.0 * H * args.steps / float(t.item()), out
 
     # ---------------------------------------------------------------- value: resident cloud
     for w in range(args.warmup):
@@ -298,6 +362,9 @@ def main():
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     score_ms = {k: [] for k in KINDS}
     fit_ms = {k: [] for k in KINDS}
+    refine_ms = {k: [] for k in KINDS}
+    draw_ms = {k: [] for k in KINDS}
+    n_inl_k = {k: 0 for k in KINDS}
     resolves = 0
     launches0 = ctx.launches
     barrier()
@@ -310,6 +377,9 @@ def main():
         for kind, (rc, n_inl, st) in zip(KINDS, res):
             score_ms[kind].append(st["score_ms"])
             fit_ms[kind].append(st["device_ms"])
+            refine_ms[kind].append(st["refine_ms"])
+            draw_ms[kind].append(st["draw_ms"])
+            n_inl_k[kind] = n_inl
             resolves += st["exact_resolves"]
     barrier()
     launches = ctx.launches - launches0
@@ -322,22 +392,46 @@ def main():
     value = 3.0 * H * args.steps / (total_ms * 1e-3)
 
     # ---------------------------------------------------------------- e2e: host buffers through the C-ABI
-    for w in range(2):
-        step_e2e(3000 + w)
-    barrier()
-    e2e_t0 = time.perf_counter()
-    d2h = 0
-    for s in range(args.steps):
-        d2h = step_e2e(4000 + 3 * s)
-    barrier()
-    e2e_s = time.perf_counter() - e2e_t0
-    t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = 3.0 * H * args.steps / float(t.item())
-    # three cloud uploads + the sample tables + the normals of the cylinder's sample points (2 per hypothesis; the
-    # caller's normal array itself stays on the host)
-    h2d = 3 * xyz.nbytes + (3 + 4 + 2) * 4 * H + 2 * 24 * H
+    e2e_value, d2h = timed_e2e(lambda seed: step_e2e(seed, np_xyz, np_nrm, inl_buf))
+    # three cloud uploads + the normals of the cylinder's sample points (2 per hypothesis; the caller's normal array
+    # itself stays on the host) + the cylinder's host-drawn sample table (plane / sphere tables are drawn on the device)
+    h2d = 3 * xyz.nbytes + 2 * 24 * H + 2 * 4 * H
+    extras = {}
+    if not args.no_extras:
+        # the same call with what an Open3D / numpy caller actually holds: pageable arrays, pageable result buffer
+        pg_xyz, pg_nrm = xyz.copy(), nrm.copy()
+        pg_buf = np.empty(N_POINTS, dtype=np.uint64)
+        v, _ = timed_e2e(lambda seed: step_e2e(seed, pg_xyz, pg_nrm, pg_buf), n_warm=1)
+        extras["e2e_pageable"] = {"value": v, "unit": "hypotheses/s", "api": "m3d_ransac_fit (host buffers, pageable numpy arrays)"}
+        if world == 1:
+            try:   # the reference-facing python call: misc3d.common.fit_* (pybind11 shim over the C++ facade)
+                sys.path.insert(0, os.path.join(ROOT, "python"))
+                import misc3d
+
+                class _PC:   # duck-typed open3d.geometry.PointCloud
+                    def __init__(self, p, n):
+                        self.points, self.normals = p, n
+                pc = _PC(pg_xyz, pg_nrm)
+                fits = (misc3d.common.fit_plane, misc3d.common.fit_sphere, misc3d.common.fit_cylinder)
+
+                def step_py(seed):
+                    for kind, f in zip(KINDS, fits):
+                        f(pc, THR, H, 1.0, seed=seed + kind)
+                    return 0
+                v, _ = timed_e2e(step_py, n_warm=1)
+                extras["e2e_pybind"] = {"value": v, "unit": "hypotheses/s",
+                                        "api": "misc3d.common.fit_plane/fit_sphere/fit_cylinder (pybind11 shim; returns the "
+                                               "inlier indices as a python list like the reference: O(n_inl) boxing included)"}
+            except Exception as e:  # the shim is optional on the bench box
+                extras["e2e_pybind"] = {"value": None, "error": str(e)[:200]}
+        extras["c5"] = c5_leg(ctx, capi, synth, dist, dev, rank, world)
+
+    # work counters of the kernel (statistics build, one sharded launch per primitive, outside the timed region;
+    # every rank takes part in the fit's exchange, rank 0 reports its shard)
+    stats = {}
+    for k in KINDS:
+        ctx.ransac_fit_cloud(k, cloud, THR, H, 1.0, seed=2000 + k, flags=capi.FLAG_STATS, want_inliers=False)
+        stats[k] = ctx.score_stats()
 
     if rank != 0:
         if world > 1:
@@ -347,57 +441,78 @@ def main():
     # ---------------------------------------------------------------- roofline of the dominant kernel
     hbm_peak, which, pk = peaks()
     ffma_peak = ctx.probe_fp32_ffma()  # FFMA lane-ops/s measured on this device
+    dfma_peak = ctx.probe_fp64_dfma()  # DFMA lane-ops/s (resolve / refine kernels)
     h_local = H // world  # hypotheses one launch scores on this rank
     per_kind = {}
     tot_score = sum(np.mean(score_ms[k]) for k in KINDS)
+    useful_ops = 0.0
     for k, name in zip(KINDS, ("plane", "sphere", "cylinder")):
         ms = float(np.mean(score_ms[k]))
         units = float(N_POINTS) * h_local
+        pairs = 32.0 * stats[k]["cell_pairs"]
+        slots = 32.0 * (32 * stats[k]["passes_1"] + 64 * stats[k]["passes_2"])
+        # fp32 FMA-pipe lane-ops the kernel executed for point tests: per evaluated pair FAST_FFMA_PER_UNIT FFMA + 1 FADD
+        ops = (FAST_FFMA_PER_UNIT[k] + 1) * slots
+        useful_ops += ops
+        rbytes = 48.0 * N_POINTS + 8.0 * n_inl_k[k]
+        rms = float(np.mean(refine_ms[k]))
         per_kind[name] = {"score_kernel_ms": ms, "fit_ms": float(np.mean(fit_ms[k])),
+                          "refine_ms": rms, "draw_ms": float(np.mean(draw_ms[k])),
+                          "refine_GBps": rbytes / (rms * 1e-3) / 1e9 if rms > 0 else None,
+                          "refine_frac_of_hbm_peak": rbytes / (rms * 1e-3) / 1e9 / hbm_peak if rms > 0 else None,
                           "point_hypotheses_per_sec": units / (ms * 1e-3),
-                          "stream_equiv_GBps": 24.0 * units / (ms * 1e-3) / 1e9,
-                          "ref_fp64_flops_per_sec": FLOPS_PER_UNIT[k] * units / (ms * 1e-3),
-                          "ffma_frac_of_measured": FAST_FFMA_PER_UNIT[k] * units / (ms * 1e-3) / ffma_peak}
+                          "pairs_evaluated_frac": pairs / units, "tile_survivor_frac": stats[k]["tile_survivors"] / max(stats[k]["tile_tests"], 1),
+                          "lane_efficiency": pairs / max(slots, 1.0), "guard_band_rescans": stats[k]["rescans"],
+                          "fp32_pipe_frac": ops / (ms * 1e-3) / ffma_peak,
+                          "dense_equiv_ffma_frac": FAST_FFMA_PER_UNIT[k] * units / (ms * 1e-3) / ffma_peak}
     # ALGORITHMIC bytes per launch: 24 B per point-hypothesis unit (one Vector3d streamed per
     # evaluation, what the reference's loop moves) x N*H units.  `traffic` is what ncu measured at the DRAM
-    # (one read of the cloud): achieved / peak is >> 1 because every point fetched is re-used by all
-    # hypotheses from shared memory / L2 -- the kernel is FP32-issue bound (roofline_alu), not HBM bound.
+    # (one read of the cloud): achieved / peak is >> 1 because every point fetched is re-used on chip and ~90 % of
+    # the pairs are decided per cell / tile -- the contract figure is not a utilisation; `binding` is.
     launch_ms = tot_score / 3.0
     algo_bytes = 24.0 * N_POINTS * h_local
     ach = algo_bytes / (launch_ms * 1e-3) / 1e9
     compulsory = 24.0 * N_POINTS + 64.0 * h_local
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "score_kernel_traffic.json")
-    if os.path.exists(tp):
-        try:
-            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
-        except Exception:
-            traffic = None
-    roofline = {"bound": "hbm", "kernel": "score_cull_kernel<KIND,256,2> (average of the plane, sphere and cylinder launches)",
+    prof = kernel_profile()
+    traffic = prof.get("dram_bytes_per_launch") if prof else None
+    binding = {"resource": "warp-instruction issue slots (the kernel is instruction-issue / latency bound; HBM idle)",
+               "frac": prof.get("issue_slots_busy_frac") if prof else None,
+               "frac_source": ("ncu smsp__issue_active of this kernel build, profiles/score_kernel_ncu.json"
+                               + (" [STALE: kernel source changed since the capture]" if prof and prof.get("stale") else ""))
+               if prof else "no ncu capture in profiles/",
+               "ncu": {k: prof.get(k) for k in ("issue_slots_busy_frac", "fma_pipe_frac", "smem_wavefront_frac", "warps_active_frac",
+                                                "warp_instructions_per_launch", "duration_ms", "capture")} if prof else None,
+               # measured in THIS run from the kernel's own counters: fp32 lane-operations issued for point tests
+               # (evaluated lane slots x (FFMA + FADD per pair)) over the FFMA rate measured by m3d_probe_fp32_ffma
+               "fp32_pipe_frac_live": useful_ops / (tot_score * 1e-3) / ffma_peak,
+               "pairs_evaluated_frac_live": {n: per_kind[n]["pairs_evaluated_frac"] for n in per_kind},
+               "lane_efficiency_live": {n: per_kind[n]["lane_efficiency"] for n in per_kind}}
+    roofline = {"bound": "hbm", "kernel": "score_cell_kernel<KIND,512,1024> (average of the plane, sphere and cylinder launches)",
                 "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": traffic,
                 "peak_source": f"{which} (MEASURED_PEAKS.json hbm_gbs)" if which == "measured" else "fallback",
                 "algorithmic_bytes_per_launch": algo_bytes, "launch_ms": launch_ms,
-                "note": "24 B x N x H streaming-equivalent bytes (SURVEY.md 8d); frac > 1 = every point fetched from "
-                        "HBM once per launch is re-used on chip by the whole hypothesis batch, and whole cells / tiles "
-                        "of point-hypothesis pairs are decided by one bounding-sphere test; DRAM traffic (ncu) ~ one "
-                        "read of the Morton-ordered cloud",
-                "binding_resource": {"what": "shared-memory bandwidth (one LDS.128 per lane per surviving hypothesis-cell pair)",
-                                     "pct_of_peak_wavefronts": {"plane": 71.2, "sphere": 60.6, "cylinder": 51.1},
-                                     "issue_slots_busy_pct": {"plane": 57.3, "sphere": 59.3, "cylinder": 59.2},
-                                     "pairs_evaluated_pct": {"plane": 10.8, "sphere": 10.6, "cylinder": 6.9},
-                                     "source": "profiles/r01_ncu_score_cull_run14.md, profiles/r01_cull_stats_run14.json "
-                                               "(ncu --set full; not measured in this run)"},
+                "note": "24 B x N x H streaming-equivalent bytes (SURVEY.md 8d); frac >> 1 is NOT a utilisation: every point "
+                        "fetched from HBM once per launch is re-used on chip by the whole hypothesis batch and ~90 % of the "
+                        "pairs are decided by one bounding-sphere test per cell / tile; see `binding`",
+                "binding": binding,
                 "compulsory_bytes_per_launch": compulsory,
                 "compulsory_GBps": compulsory / (launch_ms * 1e-3) / 1e9,
                 "compulsory_frac": compulsory / (launch_ms * 1e-3) / 1e9 / hbm_peak}
     ffma_ops = sum(FAST_FFMA_PER_UNIT[k] * float(N_POINTS) * h_local for k in KINDS)
     roofline_alu = {"bound": "fp32-fma-pipe (dense-equivalent)", "achieved": ffma_ops / (tot_score * 1e-3) / 1e12,
                     "peak": ffma_peak / 1e12, "unit": "TFFMA/s",
-                    "frac": ffma_ops / (tot_score * 1e-3) / ffma_peak,
+                    "frac": ffma_ops / (tot_score * 1e-3) / ffma_peak, "fp64_dfma_peak_T": dfma_peak / 1e12,
                     "note": "FFMA lane-ops a dense evaluation of all N x H pairs would need (3/4/8 per pair) over the "
-                            "FFMA rate measured by m3d_probe_fp32_ffma on this device; the culling kernel evaluates only "
-                            "the ~7-11 % of the pairs whose cell survives the bounding-sphere tests (profiles/), so this "
-                            "is a speed-up measure against the dense kernel's binding roofline, not a utilisation"}
+                            "FFMA rate measured by m3d_probe_fp32_ffma on this device: a speed-up measure against the dense "
+                            "kernel's binding roofline, not a utilisation (the kernel evaluates ~7-11 % of the pairs)"}
+    rb = sum(48.0 * N_POINTS + 8.0 * n_inl_k[k] for k in KINDS)
+    rt = sum(float(np.mean(refine_ms[k])) for k in KINDS)
+    roofline_refine = {"bound": "hbm", "kernels": "refine_count / refine_scan / refine_write / refine_final (RefineModel, ransac.h:534-549)",
+                       "achieved": rb / (rt * 1e-3) / 1e9 if rt > 0 else None, "peak": hbm_peak, "unit": "GB/s",
+                       "frac": rb / (rt * 1e-3) / 1e9 / hbm_peak if rt > 0 else None,
+                       "algorithmic_bytes_per_fit": "2 x 24 N read + 8 n_inl written",
+                       "note": "timed with CUDA events around the four passes of one fit (the 24 MB cloud is L2-resident after the "
+                               "scoring kernel; launch gaps of the four short kernels are inside the interval)"}
 
     cpu = None if args.no_cpu else cpu_baseline(xyz, nrm)
     line = {
@@ -408,16 +523,18 @@ def main():
         "config": {"workload": "C2: fit_plane+fit_sphere+fit_cylinder on one 1M-point synthetic cloud, "
                                f"{H_PER_PRIM} hypotheses per primitive per GPU, probability 1.0 (no early exit)",
                    "n_points": N_POINTS, "hypotheses_per_primitive": H, "threshold": THR,
-                   "l2": "512 MiB flush write between timed steps", "sharding": f"hypotheses over {world} rank(s)"},
+                   "l2": "512 MiB flush write between timed steps", "sharding": f"hypotheses over {world} rank(s)",
+                   "seeds": "a different sample-table seed every step and primitive (no table re-use)"},
         "point_hypotheses_per_sec": value * N_POINTS,
         "e2e": {"value": e2e_value, "unit": "hypotheses/s", "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": int(d2h), "api": "m3d_ransac_fit (host buffers, pinned)"},
         "gpu_launches": int(launches),
         "clocks": clk,
-        "roofline": roofline, "roofline_alu": roofline_alu, "per_primitive": per_kind,
+        "roofline": roofline, "roofline_alu": roofline_alu, "roofline_refine": roofline_refine, "per_primitive": per_kind,
         "exact_resolves_per_step": resolves / args.steps,
         "cpu_baseline": cpu,
     }
+    line.update(extras)
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

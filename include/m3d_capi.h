@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define M3D_ABI_VERSION 1
+#define M3D_ABI_VERSION 2
 
 typedef enum m3d_status {
     M3D_OK = 0,
@@ -80,6 +80,8 @@ uint64_t m3d_ctx_launch_count(const m3d_ctx *ctx);
 /* measured fp32 FFMA issue rate of the device (FFMA lane-operations per second): the ALU roofline
  * denominator bench.py reports beside the HBM one */
 int m3d_probe_fp32_ffma(m3d_ctx *ctx, double *ffma_per_s);
+/* the same for fp64 (DFMA lane-operations per second): the resolve / refine kernels' ALU roofline */
+int m3d_probe_fp64_dfma(m3d_ctx *ctx, double *dfma_per_s);
 
 /* work counters of the scoring launches run with M3D_FLAG_STATS since the last call (read and cleared):
  * out[0] (hypothesis, tile) bounding-sphere tests, [1] survivors, [2] surviving (hypothesis, cell) pairs
@@ -133,6 +135,9 @@ typedef struct m3d_ransac_stats {
     int32_t refit_ok;        /* GeneralFit's return value (ransac.h:548)                       */
     float device_ms;         /* CUDA-event time of the whole fit on the ctx stream             */
     float score_ms;          /* CUDA-event time of the scoring kernel(s) alone                 */
+    float refine_ms;         /* CUDA-event time of the RefineModel passes (ransac.h:534-549):
+                                2 x 24 N bytes read + 8 n_inl written -- the HBM-bound part        */
+    float draw_ms;           /* CUDA-event time of the device-side sample draw (0: host draw)  */
 } m3d_ransac_stats;
 
 /* Replaces RANSAC<Estimator,Model,Sampler>::{SetPointCloud, SetProbability, SetMaxIteration,

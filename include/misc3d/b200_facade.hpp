@@ -21,6 +21,7 @@
 #include <array>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <functional>
 #include <memory>
 #include <random>
@@ -144,6 +145,7 @@ class RANSAC {
 public:
     RANSAC() = default;
     void SetPointCloud(const PointCloud &pc) { pc_ = pc; }       /* deep copy, ransac.h:469-475 */
+    void SetPointCloud(PointCloud &&pc) { pc_ = std::move(pc); } /* not in the reference: callers that own a temporary */
     void SetProbability(double probability) {                     /* ransac.h:482-487 */
         if (probability <= 0 || probability > 1) LogError("Probability must be > 0 or <= 1.0");
         probability_ = probability;

@@ -25,7 +25,7 @@ ERR_CUDA, ERR_NCCL, ERR_NO_INLIERS, ERR_CAPACITY, ERR_INTERNAL = -5, -6, -7, -8,
 
 EXPORTS = [
     "m3d_abi_version", "m3d_device_count", "m3d_ctx_create", "m3d_ctx_create_on_stream",
-    "m3d_ctx_destroy", "m3d_last_error", "m3d_ctx_stream", "m3d_ctx_launch_count", "m3d_probe_fp32_ffma",
+    "m3d_ctx_destroy", "m3d_last_error", "m3d_ctx_stream", "m3d_ctx_launch_count", "m3d_probe_fp32_ffma", "m3d_probe_fp64_dfma",
     "m3d_nccl_unique_id", "m3d_ctx_init_nccl", "m3d_ctx_set_exchange", "m3d_ransac_fit",
     "m3d_cloud_upload", "m3d_cloud_from_device", "m3d_cloud_free", "m3d_cloud_size",
     "m3d_ransac_fit_cloud", "m3d_score_samples", "m3d_evaluate_model", "m3d_sample_table",
@@ -48,7 +48,7 @@ class RansacStats(_Dictable):
     _fields_ = [("best_index", C.c_uint64), ("best_count", C.c_uint64), ("best_rmse", C.c_double),
                 ("iterations_run", C.c_uint64), ("stop_index", C.c_uint64), ("evaluated", C.c_uint64),
                 ("exact_resolves", C.c_uint64), ("found", C.c_int32), ("refit_ok", C.c_int32),
-                ("device_ms", C.c_float), ("score_ms", C.c_float)]
+                ("device_ms", C.c_float), ("score_ms", C.c_float), ("refine_ms", C.c_float), ("draw_ms", C.c_float)]
 
 
 class RegStats(_Dictable):
@@ -226,6 +226,11 @@ class Context:
     def probe_fp32_ffma(self):
         v = C.c_double(0)
         self._check(lib().m3d_probe_fp32_ffma(self.h, C.byref(v)))
+        return float(v.value)
+
+    def probe_fp64_dfma(self):
+        v = C.c_double(0)
+        self._check(lib().m3d_probe_fp64_dfma(self.h, C.byref(v)))
         return float(v.value)
 
     def score_stats(self):

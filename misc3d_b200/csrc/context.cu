@@ -117,7 +117,46 @@ __global__ void __launch_bounds__(256) ffma_probe_kernel(float *out, int iters, 
     out[blockIdx.x * blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
 }
 
+__global__ void __launch_bounds__(256) dfma_probe_kernel(double *out, int iters, double a, double b) {
+    double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            x0 = fma(x0, a, b);
+            x1 = fma(x1, a, b);
+            x2 = fma(x2, a, b);
+            x3 = fma(x3, a, b);
+            x4 = fma(x4, a, b);
+            x5 = fma(x5, a, b);
+            x6 = fma(x6, a, b);
+            x7 = fma(x7, a, b);
+        }
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+}
+
 extern "C" {
+
+int m3d_probe_fp64_dfma(m3d_ctx *c, double *dfma_per_s) {
+    if (!c || !dfma_per_s) return M3D_ERR_INVALID_ARG;
+    M3D_CUDA(c, cudaSetDevice(c->device));
+    const int blocks = c->sm_count * 8, threads = 256, iters = 256;
+    M3D_CUDA(c, c->d_tmp5.reserve(sizeof(double) * (size_t)blocks * threads));
+    double best = 0;
+    for (int rep = 0; rep < 4; ++rep) {
+        M3D_CUDA(c, cudaEventRecord(c->ev[0], c->stream));
+        dfma_probe_kernel<<<blocks, threads, 0, c->stream>>>(c->d_tmp5.as<double>(), iters, 0.999, 0.001);
+        M3D_LAUNCHED(c);
+        M3D_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
+        M3D_CUDA(c, cudaStreamSynchronize(c->stream));
+        float ms = 0;
+        cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]);
+        const double r = (double)blocks * threads * (double)iters * 64.0 / (ms * 1e-3);
+        if (rep > 0 && r > best) best = r;
+    }
+    *dfma_per_s = best;
+    return M3D_OK;
+}
 
 int m3d_probe_fp32_ffma(m3d_ctx *c, double *ffma_per_s) {
     if (!c || !ffma_per_s) return M3D_ERR_INVALID_ARG;

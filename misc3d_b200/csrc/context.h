@@ -90,7 +90,7 @@ struct m3d_ctx {
     int sm_count = 148;
     uint64_t launches = 0;
     std::string err;
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 
     /* scratch (grow-only) */
     m3d::DevBuf d_samples, d_counts, d_counts_all, d_blk, d_part, d_small, d_inl, d_models, d_valid;

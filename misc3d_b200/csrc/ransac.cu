@@ -162,14 +162,14 @@ int launch_cull_t(m3d_ctx *ctx, const ScoreArgs &a, uint32_t ntiles) {
     return M3D_OK;
 }
 
-template <int KIND, int THREADS, int HPT, bool STATS>
+template <int KIND, int THREADS, int NH, bool STATS>
 int launch_cell_t(m3d_ctx *ctx, const ScoreArgs &a, uint32_t ntiles) {
-    const size_t smem = CellSmem<KIND, THREADS, THREADS * HPT>::bytes();
-    M3D_CUDA(ctx, cudaFuncSetAttribute(score_cell_kernel<KIND, THREADS, HPT, STATS>,
+    const size_t smem = CellSmem<KIND, THREADS, NH>::bytes();
+    M3D_CUDA(ctx, cudaFuncSetAttribute(score_cell_kernel<KIND, THREADS, NH, STATS>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const uint32_t hb = (a.rows + THREADS * HPT - 1) / (THREADS * HPT);
+    const uint32_t hb = (a.rows + NH - 1) / NH;
     int per_sm = 0;
-    M3D_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, score_cell_kernel<KIND, THREADS, HPT, STATS>,
+    M3D_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, score_cell_kernel<KIND, THREADS, NH, STATS>,
                                                                  THREADS + 32, smem));
     const uint32_t slots = (uint32_t)ctx->sm_count * (uint32_t)std::max(per_sm, 1);
     uint32_t per_hb = std::max<uint32_t>(1, (slots + hb - 1) / hb);
@@ -179,7 +179,7 @@ int launch_cell_t(m3d_ctx *ctx, const ScoreArgs &a, uint32_t ntiles) {
     ScoreArgs b = a;
     b.tile_counter = ctx->d_tiles.as<uint32_t>();
     dim3 grid(hb, per_hb);
-    score_cell_kernel<KIND, THREADS, HPT, STATS><<<grid, THREADS + 32, smem, ctx->stream>>>(b);
+    score_cell_kernel<KIND, THREADS, NH, STATS><<<grid, THREADS + 32, smem, ctx->stream>>>(b);
     M3D_LAUNCHED(ctx);
     return M3D_OK;
 }
@@ -235,13 +235,13 @@ int launch_one(m3d_ctx *ctx, ScoreArgs a, uint32_t ntiles, bool cull) {
          * way: longer per-cell lists (fewer half-empty passes), half the tile tests and barriers per pair */
         static const int cell_var = getenv("M3D_CELL_VARIANT") ? atoi(getenv("M3D_CELL_VARIANT")) : 0;
         if (a.flags & M3D_FLAG_STATS)
-            rc = (cell_var == 256) ? launch_cell_t<KIND, 256, 2, true>(ctx, a, ntiles) : launch_cell_t<KIND, 512, 2, true>(ctx, a, ntiles);
+            rc = (cell_var == 256) ? launch_cell_t<KIND, 256, 512, true>(ctx, a, ntiles) : launch_cell_t<KIND, 512, 1024, true>(ctx, a, ntiles);
         else if (cell_var == 512 || (cell_var == 0 && a.rows >= 4096))
-            rc = launch_cell_t<KIND, 512, 2, false>(ctx, a, ntiles);
+            rc = launch_cell_t<KIND, 512, 1024, false>(ctx, a, ntiles);
         else if (cell_var == 256 || (cell_var == 0 && a.rows >= 1024))
-            rc = launch_cell_t<KIND, 256, 2, false>(ctx, a, ntiles);
+            rc = launch_cell_t<KIND, 256, 512, false>(ctx, a, ntiles);
         else
-            rc = launch_cell_t<KIND, 128, 1, false>(ctx, a, ntiles);
+            rc = launch_cell_t<KIND, 128, 128, false>(ctx, a, ntiles);
     } else if (cull) {
         switch (var) {
             case 128 * 16 + 1: rc = launch_cull_t<KIND, 128, 1>(ctx, a, ntiles); break;
@@ -526,8 +526,9 @@ struct Fit {
     SmallDev *ds, *hs;
     RefineBufs rb;
     const double *one_row_nrm;
-    cudaEvent_t ev_a, ev_b, ev_s0, ev_s1;
+    cudaEvent_t ev_a, ev_b, ev_s0, ev_s1, ev_r0, ev_r1, ev_d0, ev_d1;
     float score_ms = 0;
+    bool drew_on_device = false;
     uint64_t evaluated = 0;
     int R, rank;
 
@@ -556,6 +557,7 @@ struct Fit {
         M3D_CUDA(ctx, ctx->d_inl.reserve(sizeof(unsigned long long) * (size_t)std::max<uint32_t>(n, 1)));
         M3D_CUDA(ctx, cudaMemsetAsync(&ds->resolves, 0, sizeof(unsigned long long), ctx->stream));
         ev_a = ctx->ev[0], ev_b = ctx->ev[1], ev_s0 = ctx->ev[2], ev_s1 = ctx->ev[3];
+        ev_r0 = ctx->ev[4], ev_r1 = ctx->ev[5], ev_d0 = ctx->ev[6], ev_d1 = ctx->ev[7];
         M3D_CUDA(ctx, cudaEventRecord(ev_a, ctx->stream));
         /* host-normals mode: only the cylinder reads normals, and only those of its sample points */
         host_nrm = (kind == kCylinder) && v.nrm == nullptr && v.h_nrm != nullptr;
@@ -637,6 +639,13 @@ struct Fit {
 
     /* RefineModel (ransac.h:534-549) on the minimal model of the sample row staged in ds->sample */
     int enqueue_refine() {
+        M3D_CUDA(ctx, cudaEventRecord(ev_r0, ctx->stream));
+        const int rc = enqueue_refine_passes();
+        if (rc) return rc;
+        M3D_CUDA(ctx, cudaEventRecord(ev_r1, ctx->stream));
+        return M3D_OK;
+    }
+    int enqueue_refine_passes() {
         if (int rc = fit_rows_kind(ctx, kind, v.xyz, v.nrm, ds->sample, 1, ds->model, ds->valid, one_row_nrm)) return rc;
         if (int rc = count_pass_kind(ctx, kind, v.xyz, n, ds->model, p.threshold, rb, &ds->mid)) return rc;
         if (seg) return write_pass<kPlane, true>(ctx, v.xyz, n, ds->model, p.threshold, rb, &ds->mid,
@@ -718,6 +727,14 @@ struct Fit {
         float ms = 0;
         cudaEventElapsedTime(&ms, ev_a, ev_b);
         res->st.device_ms = ms;
+        if (scan.found) {
+            if (cudaEventElapsedTime(&ms, ev_r0, ev_r1) == cudaSuccess) res->st.refine_ms = ms;
+            else cudaGetLastError();
+        }
+        if (drew_on_device) {
+            if (cudaEventElapsedTime(&ms, ev_d0, ev_d1) == cudaSuccess) res->st.draw_ms = ms;
+            else cudaGetLastError();
+        }
         res->ret = ret;
         return M3D_OK;
     }
@@ -738,7 +755,10 @@ struct Fit {
         const bool dev_draw = !host_nrm && device_draw_eligible(n, k, rows_all);
         std::vector<uint32_t> h_table;
         if (dev_draw) {
+            M3D_CUDA(ctx, cudaEventRecord(ev_d0, ctx->stream));
             if (int rc = draw_table_device(ctx, p.seed, n, k, rows_all, ctx->d_samples.as<uint32_t>(), &ds->draw)) return rc;
+            M3D_CUDA(ctx, cudaEventRecord(ev_d1, ctx->stream));
+            drew_on_device = true;
         } else {
             M3D_CUDA(ctx, cudaMemsetAsync(&ds->draw, 0, sizeof(RowBreaks), ctx->stream));
             M3D_CUDA(ctx, ctx->h_samples.reserve(sizeof(uint32_t) * (size_t)rows_all * k));

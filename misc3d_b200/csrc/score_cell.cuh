@@ -37,8 +37,8 @@ __device__ unsigned long long g_cell_stats[8];
 
 template <int THREADS>
 struct CellCfg {
-    static constexpr int kStages = THREADS >= 512 ? 3 : 2;     /* TMA ring depth                              */
-    static constexpr int kMinBlocks = THREADS >= 512 ? 1 : (THREADS >= 256 ? 2 : 4);
+    static constexpr int kStages = THREADS >= 384 ? 3 : 2;     /* TMA ring depth                              */
+    static constexpr int kMinBlocks = THREADS >= 384 ? 1 : (THREADS >= 256 ? 2 : 4);
 };
 
 template <int KIND, int THREADS, int NH>
@@ -91,9 +91,9 @@ __device__ __forceinline__ void load_fast_cull(const float4 *hyp, uint32_t h, Fa
     }
 }
 
-template <int KIND, int THREADS, int HPT, bool STATS>
+template <int KIND, int THREADS, int NH, bool STATS>
 __global__ void __launch_bounds__(THREADS + 32, CellCfg<THREADS>::kMinBlocks) score_cell_kernel(const ScoreArgs a) {
-    constexpr int NH = THREADS * HPT; /* hypotheses of the CTA */
+    constexpr int HPT = (NH + THREADS - 1) / THREADS; /* hypotheses a consumer thread prepares in the prologue */
     constexpr int NC = KIND == kCylinder ? 8 : 4;
     constexpr int PB = KIND == kCylinder ? 2 : 1;
     constexpr int WARPS = THREADS / 32;
@@ -188,7 +188,9 @@ __global__ void __launch_bounds__(THREADS + 32, CellCfg<THREADS>::kMinBlocks) sc
     bool invalid[HPT];
 #pragma unroll
     for (int h = 0; h < HPT; ++h) { /* parameters go to shared memory; nothing of them stays in registers */
-        row[h] = (blockIdx.x * HPT + h) * THREADS + tid;
+        const uint32_t hl = h * THREADS + tid; /* CTA-local hypothesis index */
+        const bool mine = hl < (uint32_t)NH;
+        row[h] = mine ? blockIdx.x * NH + hl : 0xffffffffu;
         double m[8];
         bool ok = false;
         if (row[h] < a.rows) ok = fit_row<KIND>(a.xyz, a.nrm, a.samples, a.src_row(row[h]), m, a.row_nrm);
@@ -198,11 +200,11 @@ __global__ void __launch_bounds__(THREADS + 32, CellCfg<THREADS>::kMinBlocks) sc
             for (int i = 0; i < 8; ++i)
                 a.models[(size_t)row[h] * 8 + i] = (ok && i < param_count(KIND)) ? m[i] : 0.0;
         }
+        if (!mine) continue;
         Fast<KIND> f;
         CullP ck;
         make_fast<KIND>(m, ok, M, a.thr, f);
         make_cull<KIND>(f, m, M, a.thr, ck);
-        const uint32_t hl = h * THREADS + tid;
         hyp[hl] = make_float4(f.c[0], f.c[1], f.c[2], f.c[3]);
         if (KIND == kCylinder) hyp[(NH + 1) + hl] = make_float4(f.c[4], f.c[5], f.c[6], f.c[7]);
         hyp[PB * (NH + 1) + hl] = make_float4(f.T, f.band, ck.a, ck.b);
@@ -219,7 +221,7 @@ __global__ void __launch_bounds__(THREADS + 32, CellCfg<THREADS>::kMinBlocks) sc
     asm volatile("bar.sync 1, %0;" ::"n"(THREADS) : "memory");
 
     constexpr uint32_t kGroups = NH / 32;
-    const uint32_t cta_row0 = blockIdx.x * HPT * THREADS; /* local index + cta_row0 = row of the launch */
+    const uint32_t cta_row0 = blockIdx.x * NH; /* local index + cta_row0 = row of the launch */
     uint32_t nres = 0;
 
     /* the rare path: lane's hypothesis `hown` saw a point of the cell inside its guard band.  The whole warp
@@ -250,13 +252,13 @@ __global__ void __launch_bounds__(THREADS + 32, CellCfg<THREADS>::kMinBlocks) sc
     };
 
     /* step A of tile k: lane = hypothesis against the tile's bounding sphere; the survivors go to `surv`.
-     * Groups are dealt to the warps statically (HPT each): the step is short and perfectly balanced. */
+     * Groups are dealt to the warps statically: the step is short and balanced. */
     auto tile_tests = [&](uint32_t k) -> bool {
         const int st = k % S;
         mbar_wait(&full[st], (k / S) & 1);
         if (tile_id[st] == kNoTile) return false;
         const float4 tb = tiles[(size_t)st * kBlobF4 + kTile + kTileCells];
-        for (uint32_t grp = warp; grp < kGroups; grp += WARPS) {
+        for (uint32_t grp = warp; grp < kGroups; grp += WARPS) { /* kGroups / WARPS groups per warp (+-1) */
             Fast<KIND> g;
             CullP gk;
             load_fast_cull<KIND, NH>(hyp, grp * 32 + lane, g, gk);
@@ -416,7 +418,7 @@ __global__ void __launch_bounds__(THREADS + 32, CellCfg<THREADS>::kMinBlocks) sc
 #pragma unroll
     for (int h = 0; h < HPT; ++h) {
         if (row[h] < a.rows) {
-            const uint32_t c = scnt[h * THREADS + tid];
+            const uint32_t c = scnt[h * THREADS + tid]; /* row[h] < a.rows implies a CTA-local index < NH */
             const uint32_t ci = a.cnt_row(row[h]);
             if (c) atomicAdd(&a.counts[ci], c);
             if (invalid[h] && blockIdx.y == 0) atomicOr(&a.counts[ci], kInvalidBit);

@@ -82,7 +82,7 @@ std::tuple<py::array_t<double>, std::vector<size_t>> fit_primitive(const py::obj
     if (!seed.is_none()) fit.SetSeed(seed.cast<uint32_t>());
     ModelT model;
     std::vector<size_t> inliers;
-    fit.SetPointCloud(pc);
+    fit.SetPointCloud(std::move(pc)); /* the converted cloud is ours: no second copy */
     bool ret;
     {
         py::gil_scoped_release nogil;

@@ -186,10 +186,34 @@ def test_segmentation_parity(ctx, capi, orc):
     assert rc == 0 and len(planes) == 0
 
 
+def _full_size_rows_vs_cpu(orc, kind, xyz, nrm, table, counts, models, valid, thr, inl_of_best=None, best=None):
+    """32 rows of a full-size launch (8 with the largest counts, the first 8, 16 random) against the CPU side on the
+    SAME full-size cloud: MinimalFit models bit for bit and EvaluateModel counts from the oracle, and -- when the
+    reference's own sources were compiled (oracle/_ref) -- the per-point distances of ransac.h itself for the winner,
+    i.e. the identical inlier list."""
+    rng = np.random.default_rng(99)
+    sub = np.unique(np.r_[np.argsort(counts)[-8:], np.arange(8), rng.choice(len(table), 16, replace=False)])
+    ovalid, ocounts, omodels = _oracle_rows(orc, kind, xyz, nrm, table[sub], thr)
+    np.testing.assert_array_equal(valid[sub], ovalid)
+    np.testing.assert_array_equal(models[sub].view(np.uint64), omodels.view(np.uint64))
+    np.testing.assert_array_equal(counts[sub], ocounts)
+    if inl_of_best is not None:
+        import refc
+        m = models[best, :{0: 4, 1: 4, 2: 7}[kind]]
+        if refc.available():
+            d = refc.distances(kind, m, xyz)        # the reference's CalcPointToModelDistance, point by point
+        else:
+            d = np.array([orc.distance(kind, m, q) for q in xyz[inl_of_best]])  # oracle: at least no false inlier
+            assert np.all(d < thr)
+            return
+        np.testing.assert_array_equal(np.nonzero(d < thr)[0], inl_of_best)
+
+
 @pytest.mark.parametrize("kind", KINDS)
-def test_full_size_properties_c2(ctx, capi, kind):
-    """BASELINE config C2 size (1M points): size-independent properties instead of the oracle --
-    fast counts == fp64 reference-order counts, inliers ascending and exactly {d < thr}."""
+def test_full_size_properties_c2(ctx, capi, orc, kind):
+    """BASELINE config C2 size (1M points): fast counts == fp64 reference-order counts, inliers ascending and exactly
+    {d < thr}; and, on the full 1M-point cloud, 32 hypotheses against the oracle + the winner's inlier list against
+    the compiled reference's distances."""
     xyz, nrm = synth.make_c2()
     cloud = ctx.upload(xyz, nrm if kind == 2 else None)
     table = capi.sample_table(3, len(xyz), capi.KSAMPLE[kind], 4096)
@@ -207,6 +231,8 @@ def test_full_size_properties_c2(ctx, capi, kind):
         m = models[st["best_index"]]
         d = np.abs((m[0] * xyz[:, 0] + m[2] * xyz[:, 2]) + (m[1] * xyz[:, 1] + m[3])) / np.sqrt(m[0] ** 2 + m[1] ** 2 + m[2] ** 2)
         np.testing.assert_array_equal(np.nonzero(d < 0.01)[0], inl)
+    _full_size_rows_vs_cpu(orc, kind, xyz, nrm if kind == 2 else None, table, counts, models, valid, 0.01,
+                           inl_of_best=inl, best=st["best_index"])
     cloud.free()
 
 
@@ -418,7 +444,7 @@ def test_full_size_properties_c3(ctx, capi, orc):
     np.testing.assert_allclose(planes, oplanes, rtol=1e-9, atol=1e-12)
 
 
-def test_full_size_properties_c5(ctx, capi):
+def test_full_size_properties_c5(ctx, capi, orc):
     """BASELINE config C5 size (4M points x 100k plane hypotheses, one GPU's view of it): the default path
     (waves pre-sorted into culled / dense hypotheses) and the dense kernel agree on the winner, the winner's
     count is the fp64 count of its minimal model, and the inlier list is exactly {d < thr} of that model."""
@@ -439,6 +465,14 @@ def test_full_size_properties_c5(ctx, capi):
     d = np.abs((m[0] * xyz[:, 0] + m[2] * xyz[:, 2]) + (m[1] * xyz[:, 1] + m[3])) / np.sqrt(m[0] ** 2 + m[1] ** 2 + m[2] ** 2)
     np.testing.assert_array_equal(np.nonzero(d < 0.01)[0], inl)
     assert np.all(np.diff(inl.astype(np.int64)) > 0) and len(inl) > 0.69 * len(xyz)
+    # the full 4M-point cloud against the CPU side: 32 rows of the launch + the winner's inlier list
+    table4k = capi.sample_table(1, len(xyz), 3, 4096)
+    c4k, m4k, v4k = ctx.score_samples(0, cloud, table4k, 0.01)
+    _full_size_rows_vs_cpu(orc, 0, xyz, None, table4k, c4k, m4k, v4k, 0.01)
+    import refc
+    if refc.available():
+        d = refc.distances(0, m[:4], xyz)
+        np.testing.assert_array_equal(np.nonzero(d < 0.01)[0], inl)
     cloud.free()
 
 

@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol(capi):
     missing = [s for s in declared if not hasattr(L, s)]
     assert not missing, missing
     assert sorted(capi.EXPORTS) == declared
-    assert L.m3d_abi_version() == 1
+    assert L.m3d_abi_version() == 2
 
 
 def test_no_cpu_fallback(capi):

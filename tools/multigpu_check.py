@@ -1,5 +1,6 @@
-"""torchrun target: hypothesis-sharded fits over R ranks (NCCL all-gather of the counts inside the
-library) must return exactly what a single-rank fit returns -- R-invariance incl. early exit.
+"""torchrun target: hypothesis-sharded fits over R ranks must return exactly what a single-rank fit returns --
+R-invariance incl. early exit (probability < 1: all-gather of the counts + host replay; probability == 1: one
+64-byte best record per rank, device-side arg-best, ties / fitness-1 replayed on the host).
   python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/multigpu_check.py
 """
 import os
@@ -37,6 +38,22 @@ for kind in (0, 1, 2):
             print(f"kind {kind} prob {prob}: sharded == single: {same}; best {b[3]['best_index']} count {b[3]['best_count']} "
                   f"stop {b[3]['stop_index']} evaluated {b[3]['evaluated']} score_ms single {a[3]['score_ms']:.3f} "
                   f"sharded {b[3]['score_ms']:.3f}", flush=True)
+# resident clouds (device normals: the cylinder's sample table is drawn on the device too), count ties, a perfect fit
+cs, cm = single.upload(xyz, nrm), sharded.upload(xyz, nrm)
+rng = np.random.default_rng(3)
+lattice = np.round(rng.uniform(-1, 1, (60, 3)), 0)
+flat = np.c_[rng.uniform(-1, 1, (5000, 2)), np.zeros(5000)]
+cases = [(kind, lambda c, kind=kind: c.ransac_fit_cloud(kind, cs if c is single else cm, 0.01, 12000, 1.0, seed=5), f"resident kind {kind}")
+         for kind in (0, 1, 2)]
+cases += [(0, lambda c: c.ransac_fit(0, lattice, None, 0.3, 3000, 1.0, seed=2), "ties (lattice cloud)"),
+          (0, lambda c: c.ransac_fit(0, flat, None, 0.01, 2000, 1.0, seed=4), "fitness 1 stops the loop")]
+for kind, run, name in cases:
+    a, b = run(single), run(sharded)
+    same = (a[0] == b[0] and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2]) and
+            all(a[3][k] == b[3][k] for k in ("best_index", "best_count", "iterations_run", "stop_index")))
+    ok = ok and same
+    if rank == 0:
+        print(f"{name}: sharded == single: {same}; best {b[3]['best_index']} count {b[3]['best_count']} stop {b[3]['stop_index']}", flush=True)
 t = torch.tensor([1 if ok else 0], device="cuda")
 dist.all_reduce(t, op=dist.ReduceOp.MIN)
 if rank == 0:
