@@ -62,6 +62,7 @@ typedef enum m3d_match_method { M3D_MATCH_FLANN = 0, M3D_MATCH_ANNOY = 1 } m3d_m
 
 typedef struct m3d_ctx m3d_ctx;     /* stream + scratch + (optional) communicator */
 typedef struct m3d_cloud m3d_cloud; /* a point cloud resident in HBM              */
+typedef struct m3d_knn m3d_knn;     /* an exact k-NN index resident in HBM        */
 
 /* ------------------------------------------------------------------ context */
 int m3d_abi_version(void);
@@ -211,6 +212,11 @@ int m3d_segment_plane_iterative(m3d_ctx *ctx, const double *xyz, size_t n, doubl
                                 int max_iteration, double min_ratio, uint32_t seed,
                                 double *planes, size_t cap_planes, uint64_t *labels,
                                 size_t *n_planes, float *device_ms);
+/* the same with 32-bit labels (0xFFFFFFFF = unassigned): half the device-to-host bytes of the call */
+int m3d_segment_plane_iterative_u32(m3d_ctx *ctx, const double *xyz, size_t n, double threshold,
+                                    int max_iteration, double min_ratio, uint32_t seed,
+                                    double *planes, size_t cap_planes, uint32_t *labels,
+                                    size_t *n_planes, float *device_ms);
 
 /* --------------------------------------------------- correspondence matching */
 /* Replaces ANNMatcher::Match (src/correspondence_matching.cpp:52-84) / NearestSearch (:13-44);
@@ -223,6 +229,17 @@ int m3d_match_correspondence(m3d_ctx *ctx, const double *src, size_t ns, const d
 /* one direction only: nn[i] = argmin_j |src_i - dst_j|^2 (ties -> lowest j) */
 int m3d_nearest(m3d_ctx *ctx, const double *src, size_t ns, const double *dst, size_t nd, int dim,
                 size_t *nn, float *device_ms);
+
+/* Replaces misc3d::common::KNearestSearch (include/misc3d/common/knn.h:24-73, src/knn.cpp:36-139; an
+ * approximate Annoy forest there).  data: dim x n float64 column-major (Eigen::MatrixXd; a point cloud is
+ * dim = 3).  m3d_knn_search answers nq queries (dim x nq column-major) with the EXACT k nearest items in
+ * ascending distance (ties: lower index): idx_out / dist_out are nq x k (row q holds count_out[q] valid
+ * entries), distances are Euclidean -- not squared -- as Annoy reports them (knn.cpp:103-113).  radius > 0
+ * keeps only items with distance <= radius (SearchHybrid, knn.cpp:115-139). */
+int m3d_knn_create(m3d_ctx *ctx, const double *data, int dim, size_t n, m3d_knn **out);
+void m3d_knn_free(m3d_knn *index);
+int m3d_knn_search(m3d_ctx *ctx, m3d_knn *index, const double *queries, size_t nq, int k, double radius,
+                   size_t *idx_out, double *dist_out, int *count_out);
 
 /* ------------------------------------------------------- RANSAC registration */
 typedef struct m3d_reg_stats {
@@ -249,7 +266,8 @@ int m3d_ransac_registration(m3d_ctx *ctx, const double *src_xyz, size_t ns, cons
                             uint32_t seed, double *T_out, m3d_reg_stats *stats);
 
 /* Replaces LeastSquareSolver::Solve = Eigen::umeyama over all pairs
- * (src/transform_estimation.cpp:49-66).  src/dst: n x 3 float64 host. */
+ * (src/transform_estimation.cpp:49-66).  src/dst: n x 3 float64 host.  n < 3 -> M3D_ERR_TOO_FEW_POINTS
+ * (the reference throws "The number of points pair is less than 3.", transform_estimation.cpp:29-31). */
 int m3d_least_squares_transform(m3d_ctx *ctx, const double *src_xyz, const double *dst_xyz,
                                 size_t n, int with_scaling, double *T_out);
 

@@ -18,6 +18,7 @@
  * back to what the reference does (LogError -> throws std::runtime_error; FitModel -> bool).
  */
 #pragma once
+#include <algorithm>
 #include <array>
 #include <cstdint>
 #include <cstdio>
@@ -196,6 +197,76 @@ using RANSACPlane = RANSAC<M3D_PLANE, Plane>;
 using RANSACShpere = RANSAC<M3D_SPHERE, Sphere>; /* (sic) ransac.h:667 */
 using RANSACCylinder = RANSAC<M3D_CYLINDER, Cylinder>;
 
+/* KNearestSearch (include/misc3d/common/knn.h:24-73, src/knn.cpp:36-139).  The reference wraps an approximate
+ * Annoy forest (n_trees, racy 4-thread build); here the same class answers with the EXACT neighbours from a data
+ * set resident in HBM (m3d_knn_*).  n_trees is kept for source compatibility and ignored.  Distances are what
+ * Annoy reports: Euclidean, not squared (the reference's parameter name `distance2` notwithstanding). */
+class KNearestSearch {
+public:
+    KNearestSearch() : n_trees_(4) {}
+    explicit KNearestSearch(int n_trees) : n_trees_(n_trees) {}
+    KNearestSearch(const FeatureMatrix &data, int n_trees = 4) : n_trees_(n_trees) { SetMatrixData(data); }
+    KNearestSearch(const PointCloud &geometry, int n_trees = 4) : n_trees_(n_trees) { SetGeometry(geometry); }
+    ~KNearestSearch() { m3d_knn_free(index_); }
+    KNearestSearch(const KNearestSearch &) = delete;
+    KNearestSearch &operator=(const KNearestSearch &) = delete;
+
+    bool SetMatrixData(const FeatureMatrix &data) { return SetRawData(data.data, (size_t)data.dim, data.count); }
+    bool SetGeometry(const PointCloud &geometry) { /* knn.cpp:57-77: the points as a 3 x n matrix */
+        return SetRawData(geometry.points_.empty() ? nullptr : geometry.points_[0].data(), 3, geometry.points_.size());
+    }
+    bool SetFeature(const FeatureMatrix &feature) { return SetMatrixData(feature); }
+
+    /* knn.cpp:103-113 */
+    int SearchKNN(const std::vector<double> &query, int knn, std::vector<size_t> &indices,
+                  std::vector<double> &distance2) const {
+        if (dataset_size_ == 0 || query.size() != dimension_ || knn < 0) return -1;
+        return Query(query, knn, 0.0, indices, distance2);
+    }
+    /* knn.cpp:115-139, including its off-by-one: of the neighbours within `radius` the LAST one is dropped
+     * (`num = i - 1`).  With no neighbour inside the radius the reference resizes to SIZE_MAX (i.e. crashes);
+     * here that case returns 0. */
+    int SearchHybrid(const std::vector<double> &query, double radius, int knn, std::vector<size_t> &indices,
+                     std::vector<double> &distance2) const {
+        if (dataset_size_ == 0 || query.size() != dimension_ || knn < 0) return -1;
+        Query(query, knn, 0.0, indices, distance2);
+        size_t i = 0;
+        for (; i < indices.size(); ++i)
+            if (distance2[i] > radius) break;
+        const size_t num = i == 0 ? 0 : i - 1;
+        indices.resize(num);
+        distance2.resize(num);
+        return (int)num;
+    }
+
+private:
+    bool SetRawData(const double *data, size_t dim, size_t count) { /* knn.cpp:36-50 */
+        dimension_ = dim;
+        dataset_size_ = count;
+        m3d_knn_free(index_);
+        index_ = nullptr;
+        if (dimension_ == 0 || dataset_size_ == 0) return false;
+        m3d_ctx *ctx = b200::DefaultContext();
+        if (m3d_knn_create(ctx, data, (int)dim, count, &index_) != M3D_OK) b200::Raise(ctx);
+        return true;
+    }
+    int Query(const std::vector<double> &query, int knn, double radius, std::vector<size_t> &indices,
+              std::vector<double> &distance) const {
+        m3d_ctx *ctx = b200::DefaultContext();
+        indices.assign((size_t)knn, 0);
+        distance.assign((size_t)knn, 0.0);
+        int count = 0;
+        if (m3d_knn_search(ctx, index_, query.data(), 1, knn, radius, indices.data(), distance.data(), &count) != M3D_OK)
+            b200::Raise(ctx);
+        indices.resize((size_t)count);
+        distance.resize((size_t)count);
+        return count;
+    }
+    int n_trees_;
+    m3d_knn *index_ = nullptr;
+    size_t dimension_ = 0, dataset_size_ = 0;
+};
+
 }  // namespace common
 
 /* ------------------------------------------------------------------ segmentation */
@@ -213,19 +284,29 @@ inline std::vector<std::pair<Vector4d, PointCloud>> SegmentPlaneIterative(const 
         return result;
     }
     m3d_ctx *ctx = b200::DefaultContext();
-    const size_t cap = 1024;
-    std::vector<double> planes(4 * cap);
-    std::vector<uint64_t> labels(n);
+    /* the reference has no limit on the number of planes: the plane buffer grows (the call is deterministic in
+     * `seed`, so a retry reproduces the rounds already done) */
+    const uint32_t the_seed = seed ? *seed : b200::RandomSeed();
+    size_t cap = 1024;
+    std::vector<double> planes;
+    std::vector<uint32_t> labels(n);
     size_t n_planes = 0;
-    const int rc = m3d_segment_plane_iterative(ctx, pcd.points_[0].data(), n, threshold, max_iteration, min_ratio,
-                                               seed ? *seed : b200::RandomSeed(), planes.data(), cap, labels.data(),
-                                               &n_planes, nullptr);
-    if (rc != M3D_OK) b200::Raise(ctx);
+    for (;;) {
+        planes.assign(4 * cap, 0.0);
+        const int rc = m3d_segment_plane_iterative_u32(ctx, pcd.points_[0].data(), n, threshold, max_iteration, min_ratio,
+                                                       the_seed, planes.data(), cap, labels.data(), &n_planes, nullptr);
+        if (rc == M3D_ERR_CAPACITY && cap < n / 3 + 1) {
+            cap = std::min(n / 3 + 1, cap * 16);
+            continue;
+        }
+        if (rc != M3D_OK) b200::Raise(ctx);
+        break;
+    }
     result.resize(n_planes);
     for (size_t k = 0; k < n_planes; ++k)
         for (int i = 0; i < 4; ++i) result[k].first[i] = planes[4 * k + i];
     for (size_t i = 0; i < n; ++i) /* clusters keep ascending original order (stable compaction) */
-        if (labels[i] != UINT64_MAX) result[labels[i]].second.points_.push_back(pcd.points_[i]);
+        if (labels[i] != UINT32_MAX) result[labels[i]].second.points_.push_back(pcd.points_[i]);
     return result;
 }
 }  // namespace segmentation
@@ -300,7 +381,9 @@ public:
     explicit LeastSquareSolver(bool scaling = false) : scaling_(scaling) {}
     /* src, dst: n corresponding points each */
     Matrix4d Solve(const std::vector<Vector3d> &src, const std::vector<Vector3d> &dst) const {
-        if (src.size() != dst.size()) LogError("Point lists differ in length");
+        /* CheckValid, transform_estimation.cpp:27-37: both conditions throw */
+        if (src.size() < 3 || dst.size() < 3) LogError("The number of points pair is less than 3.");
+        if (src.size() != dst.size()) LogError("The number of points pair is not equal.");
         m3d_ctx *ctx = b200::DefaultContext();
         Matrix4d T{};
         const int rc = m3d_least_squares_transform(ctx, src.empty() ? nullptr : src[0].data(),

@@ -31,6 +31,7 @@ EXPORTS = [
     "m3d_ransac_fit_cloud", "m3d_score_samples", "m3d_evaluate_model", "m3d_sample_table",
     "m3d_ordered_scan", "m3d_segment_plane_iterative", "m3d_match_correspondence", "m3d_nearest",
     "m3d_ransac_registration", "m3d_least_squares_transform", "m3d_shard_rows", "m3d_sample_table_device", "m3d_score_stats",
+    "m3d_knn_create", "m3d_knn_free", "m3d_knn_search", "m3d_segment_plane_iterative_u32",
 ]
 
 
@@ -86,6 +87,8 @@ def lib():
         L.m3d_sample_table.restype = None
         L.m3d_ctx_destroy.argtypes = [C.c_void_p]
         L.m3d_cloud_free.argtypes = [C.c_void_p]
+        L.m3d_knn_free.restype = None
+        L.m3d_knn_free.argtypes = [C.c_void_p]
         L.m3d_last_error.argtypes = [C.c_void_p]
         L.m3d_ctx_stream.argtypes = [C.c_void_p]
         L.m3d_ctx_launch_count.argtypes = [C.c_void_p]
@@ -333,18 +336,20 @@ class Context:
         return int(cnt.value), float(err.value)
 
     # ------------------------------------------------------------------ segmentation
-    def segment_plane_iterative(self, xyz, threshold, max_iteration=100, min_ratio=0.05, seed=0, cap_planes=256):
-        """Returns (status, planes (P,4), labels (n,) uint64 with UINT64_MAX = unassigned, device_ms)."""
+    def segment_plane_iterative(self, xyz, threshold, max_iteration=100, min_ratio=0.05, seed=0, cap_planes=256,
+                                labels32=False):
+        """Returns (status, planes (P,4), labels (n,) uint64 with UINT64_MAX = unassigned -- uint32 / 0xFFFFFFFF with
+        labels32 -- , device_ms)."""
         xyz = _f64(xyz).reshape(-1, 3)
         n = len(xyz)
         planes = np.zeros((cap_planes, 4))
-        labels = np.empty(max(n, 1), dtype=np.uint64)
+        labels = np.empty(max(n, 1), dtype=np.uint32 if labels32 else np.uint64)
         npl = C.c_size_t(0)
         ms = C.c_float(0)
-        rc = lib().m3d_segment_plane_iterative(self.h, _p(xyz), C.c_size_t(n), C.c_double(threshold),
-                                               C.c_int(max_iteration), C.c_double(min_ratio),
-                                               C.c_uint32(seed & 0xFFFFFFFF), _p(planes), C.c_size_t(cap_planes),
-                                               _p(labels, C.c_uint64), C.byref(npl), C.byref(ms))
+        fn = lib().m3d_segment_plane_iterative_u32 if labels32 else lib().m3d_segment_plane_iterative
+        rc = fn(self.h, _p(xyz), C.c_size_t(n), C.c_double(threshold), C.c_int(max_iteration), C.c_double(min_ratio),
+                C.c_uint32(seed & 0xFFFFFFFF), _p(planes), C.c_size_t(cap_planes),
+                _p(labels, C.c_uint32 if labels32 else C.c_uint64), C.byref(npl), C.byref(ms))
         if rc in (ERR_INVALID_ARG, ERR_CUDA, ERR_INTERNAL, ERR_NCCL):
             self._check(rc)
         return rc, planes[:npl.value].copy(), labels[:n], float(ms.value)
@@ -395,6 +400,24 @@ class Context:
                                                        C.c_double(edge_thr), C.c_double(confidence),
                                                        C.c_uint32(seed & 0xFFFFFFFF), _p(T), C.byref(st)))
         return rc, T.reshape(4, 4).copy(), st.as_dict()
+
+    def knn_search(self, data, queries, k, radius=0.0):
+        """exact k-NN (m3d_knn_*): data (dim, n), queries (dim, nq) float64 -> (idx (nq, k) uint64, dist (nq, k), counts (nq,))"""
+        data = np.asfortranarray(data, dtype=np.float64)
+        queries = np.asfortranarray(queries, dtype=np.float64)
+        dim, n = data.shape
+        nq = queries.shape[1]
+        h = C.c_void_p()
+        self._check(lib().m3d_knn_create(self.h, _p(data), C.c_int(dim), C.c_size_t(n), C.byref(h)))
+        try:
+            idx = np.zeros((max(nq, 1), max(k, 1)), dtype=np.uint64)
+            dist = np.zeros((max(nq, 1), max(k, 1)))
+            cnt = np.zeros(max(nq, 1), dtype=np.int32)
+            self._check(lib().m3d_knn_search(self.h, h, _p(queries), C.c_size_t(nq), C.c_int(k), C.c_double(radius),
+                                             _p(idx, C.c_size_t), _p(dist), _p(cnt, C.c_int)))
+        finally:
+            lib().m3d_knn_free(h)
+        return idx[:nq, :k], dist[:nq, :k], cnt[:nq]
 
     def least_squares_transform(self, src, dst, with_scaling=False):
         src = _f64(src).reshape(-1, 3)

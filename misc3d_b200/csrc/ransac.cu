@@ -1177,15 +1177,22 @@ int m3d_evaluate_model(m3d_ctx *ctx, int kind, const m3d_cloud *cloud, const dou
     return M3D_OK;
 }
 
-/* SegmentPlaneIterative, src/iterative_plane_segmentation.cpp:7-39 */
-int m3d_segment_plane_iterative(m3d_ctx *ctx, const double *xyz, size_t n, double threshold, int max_iteration,
-                                double min_ratio, uint32_t seed, double *planes, size_t cap_planes,
-                                uint64_t *labels, size_t *n_planes, float *device_ms) {
+} /* extern "C" */
+
+namespace {
+/* SegmentPlaneIterative, src/iterative_plane_segmentation.cpp:7-39.  Labels are 32-bit on the device; `wide`
+ * selects the size_t labels of the original entry point (widened on the device before the copy). */
+int segment_impl(m3d_ctx *ctx, const double *xyz, size_t n, double threshold, int max_iteration, double min_ratio,
+                 uint32_t seed, double *planes, size_t cap_planes, void *labels, bool wide, size_t *n_planes,
+                 float *device_ms) {
     if (!ctx || !n_planes || (n && (!xyz || !labels)) || (cap_planes && !planes)) return M3D_ERR_INVALID_ARG;
     *n_planes = 0;
     if (device_ms) *device_ms = 0;
     if (n < 3) { /* :14-17 warning + empty result */
-        for (size_t i = 0; i < n; ++i) labels[i] = UINT64_MAX;
+        for (size_t i = 0; i < n; ++i) {
+            if (wide) static_cast<uint64_t *>(labels)[i] = UINT64_MAX;
+            else static_cast<uint32_t *>(labels)[i] = UINT32_MAX;
+        }
         return M3D_OK;
     }
     if (n >= (size_t)kInvalidBit) return ctx->fail(M3D_ERR_INVALID_ARG, "clouds of >= 2^31 points are not supported");
@@ -1201,8 +1208,8 @@ int m3d_segment_plane_iterative(m3d_ctx *ctx, const double *xyz, size_t n, doubl
     M3D_CUDA(ctx, ctx->d_tmp1.reserve(sizeof(float4) * n));                  /* pts32 B    */
     M3D_CUDA(ctx, ctx->d_tmp2.reserve(sizeof(uint32_t) * n));                /* orig A     */
     M3D_CUDA(ctx, ctx->d_tmp3.reserve(sizeof(uint32_t) * n));                /* orig B     */
-    M3D_CUDA(ctx, ctx->d_tmp4.reserve(sizeof(unsigned long long) * n));      /* labels     */
-    M3D_CUDA(ctx, cudaMemsetAsync(ctx->d_tmp4.p, 0xff, sizeof(unsigned long long) * n, ctx->stream));
+    M3D_CUDA(ctx, ctx->d_tmp4.reserve(sizeof(uint32_t) * n));                /* labels     */
+    M3D_CUDA(ctx, cudaMemsetAsync(ctx->d_tmp4.p, 0xff, sizeof(uint32_t) * n, ctx->stream));
     iota_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(ctx->d_tmp2.as<uint32_t>(), (uint32_t)n);
     M3D_LAUNCHED(ctx);
     double *xyz_cur = c->xyz.as<double>(), *xyz_nxt = ctx->d_tmp0.as<double>();
@@ -1229,8 +1236,7 @@ int m3d_segment_plane_iterative(m3d_ctx *ctx, const double *xyz, size_t n, doubl
         p.probability = 0.9999; /* estimator default, ransac.h:462 (SetProbability is not called, :20-21) */
         p.seed = seed + round;
         CloudView v{xyz_cur, nullptr, p32_cur, c->meta.as<CloudMeta>(), (uint32_t)remaining, c->h_meta.nonfinite != 0};
-        SegArgs seg{p32_cur, org_cur, xyz_nxt, p32_nxt, org_nxt, ctx->d_tmp4.as<unsigned long long>(),
-                    (unsigned long long)*n_planes};
+        SegArgs seg{p32_cur, org_cur, xyz_nxt, p32_nxt, org_nxt, ctx->d_tmp4.as<uint32_t>(), (uint32_t)*n_planes};
         FitResult res;
         if (int rc = fit_view(ctx, kPlane, c, v, p, &seg, &res)) return rc;
         total_ms += res.st.device_ms;
@@ -1247,10 +1253,35 @@ int m3d_segment_plane_iterative(m3d_ctx *ctx, const double *xyz, size_t n, doubl
         std::swap(org_cur, org_nxt);
         round++;
     }
-    M3D_CUDA(ctx, cudaMemcpyAsync(labels, ctx->d_tmp4.p, sizeof(uint64_t) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (wide) {
+        M3D_CUDA(ctx, ctx->d_inl.reserve(sizeof(unsigned long long) * n));
+        widen_labels_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(ctx->d_tmp4.as<uint32_t>(),
+                                                                        ctx->d_inl.as<unsigned long long>(), (uint32_t)n);
+        M3D_LAUNCHED(ctx);
+        M3D_CUDA(ctx, cudaMemcpyAsync(labels, ctx->d_inl.p, sizeof(uint64_t) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    } else {
+        M3D_CUDA(ctx, cudaMemcpyAsync(labels, ctx->d_tmp4.p, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    }
     M3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     if (device_ms) *device_ms = total_ms;
     return status;
 }
+}  // namespace
+
+extern "C" {
+
+int m3d_segment_plane_iterative(m3d_ctx *ctx, const double *xyz, size_t n, double threshold, int max_iteration,
+                                double min_ratio, uint32_t seed, double *planes, size_t cap_planes,
+                                uint64_t *labels, size_t *n_planes, float *device_ms) {
+    return segment_impl(ctx, xyz, n, threshold, max_iteration, min_ratio, seed, planes, cap_planes, labels, true, n_planes,
+                        device_ms);
+}
+int m3d_segment_plane_iterative_u32(m3d_ctx *ctx, const double *xyz, size_t n, double threshold, int max_iteration,
+                                    double min_ratio, uint32_t seed, double *planes, size_t cap_planes,
+                                    uint32_t *labels, size_t *n_planes, float *device_ms) {
+    return segment_impl(ctx, xyz, n, threshold, max_iteration, min_ratio, seed, planes, cap_planes, labels, false, n_planes,
+                        device_ms);
+}
+
 
 } /* extern "C" */

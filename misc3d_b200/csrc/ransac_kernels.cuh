@@ -242,6 +242,14 @@ __global__ void __launch_bounds__(256) convert_final_kernel(const double *__rest
     }
 }
 
+/* 32-bit cluster labels -> the size_t labels of the 64-bit entry point (0xFFFFFFFF -> UINT64_MAX) */
+__global__ void widen_labels_kernel(const uint32_t *__restrict__ in, unsigned long long *__restrict__ out, uint32_t n) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t v = in[i];
+        out[i] = v == 0xffffffffu ? ~0ull : (unsigned long long)v;
+    }
+}
+
 __global__ void iota_kernel(uint32_t *out, uint32_t n) {
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = i;
 }
@@ -958,8 +966,8 @@ struct SegArgs {
     double *xyz_out;
     float4 *pts32_out;
     uint32_t *orig_out;
-    unsigned long long *labels; /* [n_original] */
-    unsigned long long plane_id;
+    uint32_t *labels; /* [n_original], 0xFFFFFFFF = unassigned */
+    uint32_t plane_id;
 };
 
 /* pass 3: ascending inlier indices (stable), centred moments for GeneralFit; with SEG also the
@@ -1127,9 +1135,53 @@ __global__ void __launch_bounds__(256) refine_final_kernel(const double *__restr
             const double c00 = A11 * A22 - A12 * A12, c01 = A02 * A12 - A01 * A22, c02 = A01 * A12 - A02 * A11;
             const double c11 = A00 * A22 - A02 * A02, c12 = A01 * A02 - A00 * A12, c22 = A00 * A11 - A01 * A01;
             const double det = A00 * c00 + A01 * c01 + A02 * c02;
-            const double x = (c00 * b0 + c01 * b1 + c02 * b2) / det;
-            const double y = (c01 * b0 + c11 * b1 + c12 * b2) / det;
-            const double z = (c02 * b0 + c12 * b1 + c22 * b2) / det;
+            double x, y, z;
+            const double tr = A00 + A11 + A22;
+            if (fabs(det) > 1e-12 * tr * tr * tr && isfinite(det)) {
+                x = (c00 * b0 + c01 * b1 + c02 * b2) / det;
+                y = (c01 * b0 + c11 * b1 + c12 * b2) / det;
+                z = (c02 * b0 + c12 * b1 + c22 * b2) / det;
+            } else {
+                /* coplanar / collinear inliers: the system is rank deficient.  The reference's bdcSvd().solve()
+                 * returns a finite minimum-norm solution; here the minimum-norm solution of the CENTRED system
+                 * (pseudo-inverse through a Jacobi eigen-decomposition, eigenvalues below 1e-12 of the largest
+                 * dropped) -- finite and on the same sphere family, not bit-comparable (documented deviation). */
+                double a[3][3] = {{A00, A01, A02}, {A01, A11, A12}, {A02, A12, A22}};
+                double v[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+                for (int sweep = 0; sweep < 12; ++sweep)
+                    for (int p = 0; p < 2; ++p)
+                        for (int q = p + 1; q < 3; ++q) {
+                            if (fabs(a[p][q]) < 1e-300) continue;
+                            const double th = (a[q][q] - a[p][p]) / (2.0 * a[p][q]);
+                            const double t = (th >= 0 ? 1.0 : -1.0) / (fabs(th) + sqrt(th * th + 1.0));
+                            const double c = 1.0 / sqrt(t * t + 1.0), sn = t * c;
+                            for (int k = 0; k < 3; ++k) { /* A <- A J */
+                                const double akp = a[k][p], akq = a[k][q];
+                                a[k][p] = c * akp - sn * akq;
+                                a[k][q] = sn * akp + c * akq;
+                            }
+                            for (int k = 0; k < 3; ++k) { /* A <- J^T A */
+                                const double apk = a[p][k], aqk = a[q][k];
+                                a[p][k] = c * apk - sn * aqk;
+                                a[q][k] = sn * apk + c * aqk;
+                            }
+                            for (int k = 0; k < 3; ++k) {
+                                const double vkp = v[k][p], vkq = v[k][q];
+                                v[k][p] = c * vkp - sn * vkq;
+                                v[k][q] = sn * vkp + c * vkq;
+                            }
+                        }
+                const double lmax = fmax(fabs(a[0][0]), fmax(fabs(a[1][1]), fabs(a[2][2])));
+                x = y = z = 0;
+                for (int i = 0; i < 3; ++i) {
+                    const double lam = a[i][i];
+                    if (!(lam > 1e-12 * lmax) || !(lmax > 0)) continue;
+                    const double w = (v[0][i] * b0 + v[1][i] * b1 + v[2][i] * b2) / lam;
+                    x += w * v[0][i];
+                    y += w * v[1][i];
+                    z += w * v[2][i];
+                }
+            }
             m[0] = x + mx;
             m[1] = y + my;
             m[2] = z + mz;

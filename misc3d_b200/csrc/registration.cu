@@ -951,8 +951,9 @@ int m3d_ransac_registration(m3d_ctx *ctx, const double *src_xyz, size_t ns, cons
 
 int m3d_least_squares_transform(m3d_ctx *ctx, const double *src_xyz, const double *dst_xyz, size_t n,
                                 int with_scaling, double *T_out) {
-    if (!ctx || !T_out || !src_xyz || !dst_xyz) return M3D_ERR_INVALID_ARG;
-    if (n < 3) return ctx->fail(M3D_ERR_TOO_FEW_POINTS, "There must be at least 3 points to solve the transformation");
+    if (!ctx || !T_out) return M3D_ERR_INVALID_ARG;
+    if (n < 3) return ctx->fail(M3D_ERR_TOO_FEW_POINTS, "The number of points pair is less than 3."); /* transform_estimation.cpp:29-31 */
+    if (!src_xyz || !dst_xyz) return ctx->fail(M3D_ERR_INVALID_ARG, "null point array");
     if (n >= (1ull << 32)) return ctx->fail(M3D_ERR_INVALID_ARG, "too many points");
     M3D_CUDA(ctx, cudaSetDevice(ctx->device));
     const int nb = std::max(1, std::min<int>(ctx->sm_count * 4, (int)((n + 255) / 256)));

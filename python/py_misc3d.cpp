@@ -216,14 +216,21 @@ PYBIND11_MODULE(py_misc3d, m) {
         py::arg("edge_length_threshold") = 0.9, py::kw_only(), py::arg("seed") = py::none());
     reg.def(
         "compute_transformation_least_square",
-        [](const py::object &src, const py::object &dst) {
-            registration::LeastSquareSolver solver;
+        /* both reference overloads (python/py_registration.cpp:12-31): PointCloud pair or (n, 3) ndarrays, scaling=False */
+        [](const py::object &src, const py::object &dst, bool scaling) {
+            registration::LeastSquareSolver solver(scaling);
             const auto s = rows3(py::hasattr(src, "points") ? py::object(src.attr("points")) : src, "src");
             const auto d = rows3(py::hasattr(dst, "points") ? py::object(dst.attr("points")) : dst, "dst");
-            return mat4(solver.Solve(s, d));
+            Matrix4d T;
+            {
+                py::gil_scoped_release nogil;
+                T = solver.Solve(s, d);
+            }
+            return mat4(T);
         },
-        "Compute 3D rigid transformation from corresponding point clouds using least square", py::arg("src"),
-        py::arg("dst"));
+        "Compute 3D transformation from corresponding point clouds using Least-Square method (point clouds or "
+        "numpy arrays with shape (n, 3))",
+        py::arg("src"), py::arg("dst"), py::arg("scaling") = false);
 
     py::enum_<VerbosityLevel>(m, "VerbosityLevel", py::arithmetic(), "VerbosityLevel")
         .value("Error", VerbosityLevel::Error)

@@ -43,6 +43,19 @@ int main(int argc, char **argv) {
         std::printf("plane %zu %.17g %.17g %.17g %.17g\n", c.second.points_.size(), c.first[0], c.first[1], c.first[2],
                     c.first[3]);
 
+    { /* KNearestSearch (knn.h:24-73): 5 nearest points of point 0 in the cloud; the first is the point itself */
+        misc3d::common::KNearestSearch knn(pc);
+        std::vector<size_t> idx;
+        std::vector<double> dist;
+        const std::vector<double> q = {pc.points_[0][0], pc.points_[0][1], pc.points_[0][2]};
+        const int k = knn.SearchKNN(q, 5, idx, dist);
+        std::printf("knn %d", k);
+        for (int i = 0; i < k; ++i) std::printf(" %zu %.17g", idx[i], dist[i]);
+        std::printf("\n");
+        const int kh = knn.SearchHybrid(q, dist.empty() ? 1.0 : dist.back(), 5, idx, dist); /* drops the last one (knn.cpp:129) */
+        std::printf("hybrid %d\n", kh);
+    }
+
     try { /* the reference throws std::runtime_error from LogError (ransac.h:483-485) */
         fit.SetProbability(1.5);
         std::printf("throw 0\n");

@@ -60,3 +60,9 @@ def test_reference_style_caller_matches_compiled_reference(tmp_path, capi):
         assert int(ln[1]) == int((labels == k).sum())
         np.testing.assert_allclose([float(v) for v in ln[2:6]], planes[k], rtol=1e-9, atol=1e-12)
     assert next(ln for ln in lines if ln[0] == "throw")[1] == "1"
+    knn = next(ln for ln in lines if ln[0] == "knn")
+    d = np.sqrt(((xyz - xyz[0]) ** 2).sum(1))
+    order = np.lexsort((np.arange(len(xyz)), d))[:5]
+    assert int(knn[1]) == 5 and [int(v) for v in knn[2::2]] == order.tolist()
+    np.testing.assert_allclose([float(v) for v in knn[3::2]], d[order], rtol=1e-12, atol=1e-15)
+    assert next(ln for ln in lines if ln[0] == "hybrid")[1] == "4"

@@ -90,3 +90,25 @@ def test_c4_sized_properties(ctx, capi):
     for r in rows:
         dist = ((B - A[:, [int(i0[r])]]) ** 2).sum(0)
         assert int(np.argmin(dist)) == int(i1[r])
+
+
+def test_knn_index_is_exact(ctx, capi):
+    """KNearestSearch's backend (m3d_knn_*): exact neighbours in ascending distance, ties to the lower index, Euclidean
+    (unsquared) distances, radius cut -- against numpy brute force, for descriptor (33-D) and point (3-D) data"""
+    rng = np.random.default_rng(3)
+    for dim, n, nq, k in ((33, 5000, 40, 7), (3, 20000, 25, 16), (3, 10, 3, 16)):
+        data = rng.uniform(0, 100, (dim, n))
+        data[:, 1] = data[:, 0]                      # an exact tie
+        q = np.c_[data[:, :2], rng.uniform(0, 100, (dim, nq - 2))]
+        idx, dist, cnt = ctx.knn_search(data, q, k)
+        for j in range(nq):
+            d = np.sqrt(((data - q[:, j:j + 1]) ** 2).sum(0))
+            order = np.lexsort((np.arange(n), d))[:k]
+            assert cnt[j] == min(k, n)
+            np.testing.assert_array_equal(idx[j, :cnt[j]], order)
+            np.testing.assert_allclose(dist[j, :cnt[j]], d[order], rtol=1e-12, atol=1e-12)
+        r = float(np.median(dist[:, min(k, n) // 2]))
+        idx2, dist2, cnt2 = ctx.knn_search(data, q, k, radius=r)
+        for j in range(nq):
+            assert cnt2[j] == int((dist[j, :cnt[j]] <= r).sum())
+            np.testing.assert_array_equal(idx2[j, :cnt2[j]], idx[j, :cnt2[j]])

@@ -519,3 +519,18 @@ def test_device_loop_several_waves(ctx, capi, orc):
     """more hypotheses than one device-side wave holds (2^18 per rank): the best is carried across waves"""
     xyz = synth.make_c1(n=2500, seed=13)
     _check_fit(ctx, capi, orc, capi.PLANE, xyz, None, 0.01, 300_000, 1.0, seed=5)
+
+
+def test_sphere_refit_of_degenerate_inliers_is_finite(ctx, capi):
+    """coplanar inliers make the sphere's least-squares system rank deficient: the refit must stay finite (the
+    reference's bdcSvd().solve() returns a minimum-norm solution; here the minimum-norm solution of the centred system)"""
+    rng = np.random.default_rng(8)
+    ang = rng.uniform(0, 2 * np.pi, 4000)
+    ring = np.c_[0.5 * np.cos(ang), 0.5 * np.sin(ang), np.zeros_like(ang)]  # a circle: every sphere through it fits
+    xyz = np.r_[ring, rng.uniform(-1, 1, (50, 3)) * np.array([1, 1, 0.0])]  # all points in the plane z = 0
+    rc, model, inl, st = ctx.ransac_fit(capi.SPHERE, xyz, None, 0.01, 300, 1.0, seed=4)
+    if st["found"]:
+        assert np.all(np.isfinite(model)), model
+        if rc == 1:
+            d = np.abs(np.linalg.norm(ring - model[:3], axis=1) - model[3])
+            assert np.median(d) < 0.05
