@@ -72,9 +72,11 @@ def test_offset_descriptors_and_empty_sets(ctx, capi, orc):
     assert len(i0) == 0 and len(i1) == 0
 
 
-def test_c4_sized_properties(ctx, capi):
+def test_c4_sized_properties(ctx, capi, orc):
     """BASELINE config C4 size (200k x 200k x 33): mutual pairs are consistent and recover the
-    planted correspondences (30 % of the descriptors are noisy copies)."""
+    planted correspondences (30 % of the descriptors are noisy copies); 2048 random query columns of each direction
+    against the oracle's exact search over the FULL 200k database (nanoflann accumulation order, ties to the lowest
+    index)."""
     d = synth.make_c4()
     i0, i1, ms = ctx.match_correspondence(d["src_feat"], d["dst_feat"])
     assert np.all(np.diff(i0.astype(np.int64)) > 0) and len(np.unique(i1)) == len(i1)
@@ -90,6 +92,15 @@ def test_c4_sized_properties(ctx, capi):
     for r in rows:
         dist = ((B - A[:, [int(i0[r])]]) ** 2).sum(0)
         assert int(np.argmin(dist)) == int(i1[r])
+    # one direction of the search on its own, against the oracle on the full database
+    nn, _ = ctx.nearest(A, B)
+    q = rng.choice(A.shape[1], 2048, replace=False)
+    np.testing.assert_array_equal(nn[q], orc.nearest(A[:, q], B))
+    nn_back, _ = ctx.nearest(B, A)
+    np.testing.assert_array_equal(nn_back[q], orc.nearest(B[:, q], A))
+    mutual = np.nonzero(nn_back[nn.astype(np.int64)] == np.arange(A.shape[1], dtype=np.uint64))[0]
+    np.testing.assert_array_equal(mutual, i0.astype(np.int64))      # the mutual filter, recomputed from the two searches
+    np.testing.assert_array_equal(nn[mutual], i1)
 
 
 def test_knn_index_is_exact(ctx, capi):

@@ -87,8 +87,9 @@ def test_least_squares_transform(ctx, capi, orc, scaling):
     assert np.linalg.norm(T - oT) <= 1e-9
 
 
-def test_c4_sized_registration_properties(ctx, capi):
-    """BASELINE config C4 size: 200k points, mutual matches, 50k hypotheses, no early exit"""
+def test_c4_sized_registration_properties(ctx, capi, orc):
+    """BASELINE config C4 size: 200k points, mutual matches, 50k hypotheses, no early exit; and the oracle's loop on
+    the same ~94k correspondences with 2000 hypotheses (statistics exact, transform bit for bit)"""
     d = synth.make_c4()
     i0, i1, ms = ctx.match_correspondence(d["src_feat"], d["dst_feat"])
     rc, T, st = ctx.ransac_registration(d["src"], d["dst"], i0, i1, 0.02, 50000, 0.9, 1.0, 1)
@@ -97,3 +98,35 @@ def test_c4_sized_registration_properties(ctx, capi):
     p = d["src"][i0.astype(np.int64)] @ T[:3, :3].T + T[:3, 3]
     good = int((((p - d["dst"][i1.astype(np.int64)]) ** 2).sum(1) < 0.02 ** 2).sum())
     assert abs(good - st["best_count"]) <= 2  # numpy evaluates T*p in a different operation order
+    for conf in (1.0, 0.999):
+        _check(ctx, orc, d["src"], d["dst"], i0, i1, 0.02, 2000, 0.9, conf, 3)
+
+
+def test_open3d_pin(ctx, capi):
+    """the GPU path against a real Open3D (tests/golden/reg_open3d.npz from tools/pin_open3d.py; skipped while absent)"""
+    path = os.path.join(GOLD, "reg_open3d.npz")
+    if not os.path.exists(path):
+        pytest.skip("tests/golden/reg_open3d.npz absent: run tools/pin_open3d.py where open3d is installed")
+    g = np.load(path)
+    d = synth.make_c4(n=3000, seed=5)
+    i0, i1 = g["i0"], g["i1"]
+    np.testing.assert_allclose(ctx.least_squares_transform(d["src"][i0], d["dst"][i1], False), g["T_ls"], rtol=0, atol=1e-9)
+    np.testing.assert_allclose(ctx.least_squares_transform(d["src"][i0], d["dst"][i1], True), g["T_ls_scale"], rtol=0, atol=1e-9)
+    rc, T, st = ctx.ransac_registration(d["src"], d["dst"], i0, i1, float(g["thr"]), int(g["max_iter"]), float(g["edge"]),
+                                        0.999, 1)
+    assert abs(st["best_count"] / len(i0) - float(g["fitness"])) < 0.02 and np.linalg.norm(T - g["T"]) < 0.05
+
+
+def test_gpu_agrees_with_the_independent_numpy_restatement(ctx, capi, orc):
+    """a19 without a compiled reference: the GPU loop against tests/reg_numpy_ref.py (numpy-only, np.linalg.svd) on the
+    recorded sample table -- statistics exactly, transform within 1e-9 (and far inside the 1e-5 Frobenius tolerance)"""
+    import reg_numpy_ref as ref
+    d = synth.make_c4(n=2500, seed=4)
+    i0, i1 = orc.match_correspondence(d["src_feat"], d["dst_feat"])
+    picks = orc.reg_sample_table(6, len(i0), 1500)
+    T, st = ref.ransac_registration_np(d["src"], d["dst"], i0.astype(np.int64), i1.astype(np.int64), picks, 0.02, 1500, 0.9, 0.999)
+    rc, gT, gst = ctx.ransac_registration(d["src"], d["dst"], i0, i1, 0.02, 1500, 0.9, 0.999, 6)
+    assert rc == 1
+    for k in ("best_index", "best_count", "evaluated", "stop_index"):
+        assert gst[k] == st[k], (k, gst, st)
+    np.testing.assert_allclose(gT, T, rtol=0, atol=1e-9)

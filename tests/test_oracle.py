@@ -190,3 +190,56 @@ def test_golden_real_scan(orc):
     assert rc == 0
     np.testing.assert_array_equal(planes, g["planes"])
     np.testing.assert_array_equal(labels.astype(np.int64), g["labels"])
+
+
+@pytest.mark.parametrize("conf", [0.999, 1.0])
+@pytest.mark.parametrize("seed,outliers", [(2, 0.0), (5, 0.6)])
+def test_registration_two_independent_restatements_agree(orc, seed, outliers, conf):
+    """rows a19/a20 have no compiled reference (Open3D is a third-party dependency that is not in the tree): the
+    oracle's C++ restatement of Appendix B must agree with an independently written numpy one (tests/reg_numpy_ref.py:
+    Kabsch via np.linalg.svd, vectorised scoring) on the same recorded sample table -- loop statistics exactly,
+    the 4 x 4 transform to 1e-9."""
+    import reg_numpy_ref as ref
+    d = synth.make_c4(n=2500, seed=seed)
+    i0, i1 = orc.match_correspondence(d["src_feat"], d["dst_feat"])
+    i0, i1 = i0.astype(np.int64), i1.astype(np.int64)
+    if outliers:
+        rng = np.random.default_rng(seed)
+        bad = rng.uniform(size=len(i1)) < outliers
+        i1 = i1.copy()
+        i1[bad] = rng.integers(0, 2500, int(bad.sum()))
+    max_iter = 1500
+    picks = orc.reg_sample_table(seed, len(i0), max_iter)
+    rc, oT, ost = orc.ransac_registration(d["src"], d["dst"], i0, i1, thr=0.02, max_iter=max_iter, edge_thr=0.9,
+                                          confidence=conf, seed=seed)
+    T, st = ref.ransac_registration_np(d["src"], d["dst"], i0, i1, picks, 0.02, max_iter, 0.9, conf)
+    assert rc == 1
+    for k in ("best_index", "best_count", "evaluated", "stop_index"):
+        assert st[k] == ost[k], (k, st, ost)
+    np.testing.assert_allclose(T, oT, rtol=0, atol=1e-9)
+    assert abs(st["best_rmse"] - ost["best_rmse"]) <= 1e-12
+    # least squares over all inlier pairs, with and without scaling (LeastSquareSolver = Eigen::umeyama)
+    for scaling in (False, True):
+        np.testing.assert_allclose(orc.umeyama(d["src"][i0], 1.7 * d["dst"][i1] if scaling else d["dst"][i1], scaling),
+                                   ref.umeyama_np(d["src"][i0], 1.7 * d["dst"][i1] if scaling else d["dst"][i1], scaling),
+                                   rtol=0, atol=1e-9)
+
+
+def test_open3d_pin(orc):
+    """rows a19 / a20 against a real Open3D: consumes tests/golden/reg_open3d.npz, which tools/pin_open3d.py writes on a
+    box where `import open3d` works (none in this image: skipped until the file exists)."""
+    path = os.path.join(GOLD, "reg_open3d.npz")
+    if not os.path.exists(path):
+        pytest.skip("tests/golden/reg_open3d.npz absent: run tools/pin_open3d.py where open3d is installed")
+    g = np.load(path)
+    d = synth.make_c4(n=3000, seed=5)
+    i0, i1 = g["i0"], g["i1"]
+    for t, T3 in zip(g["triples"], g["T3"]):             # the 3-point solve, transform by transform
+        np.testing.assert_allclose(orc.umeyama(d["src"][i0[t]], d["dst"][i1[t]], False), T3, rtol=0, atol=1e-9)
+    np.testing.assert_allclose(orc.umeyama(d["src"][i0], d["dst"][i1], False), g["T_ls"], rtol=0, atol=1e-9)
+    np.testing.assert_allclose(orc.umeyama(d["src"][i0], d["dst"][i1], True), g["T_ls_scale"], rtol=0, atol=1e-9)
+    rc, T, st = orc.ransac_registration(d["src"], d["dst"], i0, i1, thr=float(g["thr"]), max_iter=int(g["max_iter"]),
+                                        edge_thr=float(g["edge"]), confidence=0.999, seed=1)
+    # different sample streams, one dominant alignment: same inlier population, transforms within the 3-point noise
+    assert abs(st["best_count"] / len(i0) - float(g["fitness"])) < 0.02
+    assert np.linalg.norm(T - g["T"]) < 0.05
