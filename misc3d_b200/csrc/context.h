@@ -97,6 +97,11 @@ struct m3d_ctx {
     m3d::DevBuf d_tmp0, d_tmp1, d_tmp2, d_tmp3, d_tmp4, d_tmp5, d_queue, d_tiles, d_rownrm, d_rowmap, d_recs, d_draw;
     m3d::PinBuf h_samples, h_counts, h_small, h_stage, h_rownrm;
     m3d_cloud *scratch_cloud = nullptr; /* staging cloud of the host-buffer entry points */
+    /* chunked upload of the host-buffer fit (ransac.cu fit_host_chunked): a copy stream + one event per chunk */
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_chunk[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    m3d::DevBuf d_metas, d_models_all, d_valid_all;
+    m3d::PinBuf h_metas;
 
     /* sharding / exchange */
     int rank = 0, world = 1;

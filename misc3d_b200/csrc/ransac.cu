@@ -447,7 +447,26 @@ struct CloudView {
     const float4 *blob = nullptr; /* Morton-ordered copy (null: dense scoring only) */
     const uint32_t *perm = nullptr;
     const double *h_nrm = nullptr; /* normals left on the host (host-buffer entry point): upload per sample */
+    struct ChunkPlan *chunks = nullptr; /* host-buffer fit whose upload is still in flight (fit_host_chunked) */
 };
+
+/* The chunked host-buffer fit.  The caller's (pinned) cloud is uploaded in `count` chunks on a copy stream; every
+ * chunk is an independent cloud for the purposes of counting -- own bounding box / fp32 copy / Morton-ordered tiles
+ * -- and EvaluateModel's count is a sum over points, so the scoring kernel runs once per chunk, as soon as the chunk
+ * has arrived, while the next one is still on the PCIe bus.  The minimal models need sample points from anywhere in
+ * the cloud: they are solved beforehand by a kernel that gathers the k x H sample points straight from the pinned host
+ * buffer (zero-copy).  xyz / pts32 / blob / perm of the view are the buffers of the WHOLE cloud (chunks are tile
+ * aligned); RefineModel runs on the complete upload as before. */
+struct ChunkPlan {
+    int count = 0;
+    uint32_t begin[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}; /* point offsets, multiples of kTile; begin[count] = n */
+    const double *dev_of_host_xyz = nullptr;          /* device-mapped address of the caller's pinned points  */
+    const double *dev_of_host_nrm = nullptr;          /* ... normals (cylinder) or null                        */
+    CloudMeta *metas = nullptr;                       /* device, one per chunk                                 */
+    uint32_t *keys = nullptr, *hist = nullptr;        /* Morton sort scratch (re-used chunk after chunk)       */
+    bool prepped[8] = {false, false, false, false, false, false, false, false};
+};
+constexpr int kRetryUnchunked = 1001; /* internal: a chunk holds NaN / inf coordinates, use the plain upload path */
 
 /* one full FitModel on a device-resident cloud.  On return the minimal best model sits in
  * d_small->model, pass 1+2 results in d_small->mid, and (when `seg` is null) the ascending
@@ -511,6 +530,49 @@ int draw_table_device(m3d_ctx *ctx, uint32_t seed, uint32_t n, int k, uint32_t r
 }
 
 constexpr int kRetryOnHost = 1000; /* internal: the device-side loop gave up, run the host loop */
+
+/* bounding box, fp32 copy and Morton-ordered tiles of chunk c (the kernels of prepare_cloud / ensure_sorted on a
+ * slice); enqueued behind the chunk's arrival event */
+int prep_chunk(m3d_ctx *ctx, const CloudView &v, ChunkPlan &pl, int c) {
+    if (pl.prepped[c]) return M3D_OK;
+    M3D_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_chunk[c], 0));
+    const uint32_t b = pl.begin[c], n = pl.begin[c + 1] - pl.begin[c];
+    const double *xyz = v.xyz + 3 * (size_t)b;
+    float4 *pts32 = const_cast<float4 *>(v.pts32) + b;
+    float4 *blob = const_cast<float4 *>(v.blob) + (size_t)(b / kTile) * kBlobF4;
+    uint32_t *perm = const_cast<uint32_t *>(v.perm) + b;
+    CloudMeta *meta = pl.metas + c;
+    const int nb = std::max(1, std::min<int>(ctx->sm_count * 8, (int)((n + 255) / 256)));
+    M3D_CUDA(ctx, ctx->d_part.reserve(sizeof(BBoxPart) * (size_t)nb + sizeof(double) * nb));
+    BBoxPart *bp = ctx->d_part.as<BBoxPart>();
+    double *mp = reinterpret_cast<double *>(bp + nb);
+    bbox_kernel<<<nb, 256, 0, ctx->stream>>>(xyz, n, bp);
+    M3D_LAUNCHED(ctx);
+    bbox_final_kernel<<<1, 256, 0, ctx->stream>>>(bp, nb, meta);
+    M3D_LAUNCHED(ctx);
+    convert_kernel<<<nb, 256, 0, ctx->stream>>>(xyz, n, meta, pts32, mp);
+    M3D_LAUNCHED(ctx);
+    convert_final_kernel<<<1, 256, 0, ctx->stream>>>(mp, nb, meta);
+    M3D_LAUNCHED(ctx);
+    const uint32_t ntiles = (n + kTile - 1) / kTile;
+    constexpr int kScanBlocks = kBins / (kScanBlock * kScanItems);
+    uint32_t *hist = pl.hist, *bsum = hist + kBins;
+    M3D_CUDA(ctx, cudaMemsetAsync(hist, 0, sizeof(uint32_t) * (size_t)kBins, ctx->stream));
+    morton_hist_kernel<<<nb, 256, 0, ctx->stream>>>(pts32, n, meta, pl.keys, hist);
+    M3D_LAUNCHED(ctx);
+    scan_sums_kernel<<<kScanBlocks, kScanBlock, 0, ctx->stream>>>(hist, bsum);
+    M3D_LAUNCHED(ctx);
+    scan_top_kernel<<<1, kScanBlock, 0, ctx->stream>>>(bsum, kScanBlocks);
+    M3D_LAUNCHED(ctx);
+    scan_apply_kernel<<<kScanBlocks, kScanBlock, 0, ctx->stream>>>(hist, bsum);
+    M3D_LAUNCHED(ctx);
+    morton_scatter_kernel<<<nb, 256, 0, ctx->stream>>>(pts32, n, pl.keys, hist, blob, perm);
+    M3D_LAUNCHED(ctx);
+    tile_bounds_kernel<<<ntiles, kTile, 0, ctx->stream>>>(blob, n, meta);
+    M3D_LAUNCHED(ctx);
+    pl.prepped[c] = true;
+    return M3D_OK;
+}
 
 struct Fit {
     m3d_ctx *ctx;
@@ -779,6 +841,15 @@ struct Fit {
                 M3D_CUDA(ctx, cudaMemcpyAsync(ctx->d_rownrm.p, dst, sizeof(double) * 3 * cnt, cudaMemcpyHostToDevice, ctx->stream));
             }
         }
+        ChunkPlan *pl = v.chunks;
+        if (pl) { /* all minimal models now, from the caller's pinned buffer (the upload is still in flight) */
+            if (!dev_draw) return ctx->fail(M3D_ERR_INTERNAL, "chunked fit without a device-side sample draw");
+            M3D_CUDA(ctx, ctx->d_models_all.reserve(sizeof(double) * 8 * (size_t)rows_all));
+            M3D_CUDA(ctx, ctx->d_valid_all.reserve((size_t)rows_all));
+            if (int rc = fit_rows_kind(ctx, kind, pl->dev_of_host_xyz, pl->dev_of_host_nrm, ctx->d_samples.as<uint32_t>(),
+                                       rows_all, ctx->d_models_all.as<double>(), ctx->d_valid_all.as<uint8_t>()))
+                return rc;
+        }
         wave_base = 0, wave_rows = rows_all; /* the whole table is resident: stage_row never needs the host */
         M3D_CUDA(ctx, ctx->d_recs.reserve(sizeof(BestRec) * (size_t)(R + 1)));
         BestRec *d_local = ctx->d_recs.as<BestRec>(), *d_all = d_local + 1;
@@ -793,11 +864,28 @@ struct Fit {
             M3D_CUDA(ctx, ctx->d_counts.reserve(sizeof(uint32_t) * (size_t)std::max<uint32_t>(S, 1)));
             M3D_CUDA(ctx, cudaMemsetAsync(ctx->d_counts.p, 0, sizeof(uint32_t) * (size_t)std::max<uint32_t>(S, 1), ctx->stream));
             M3D_CUDA(ctx, cudaEventRecord(ev_s0, ctx->stream));
-            if (mine) {
+            if (mine && !pl) {
                 ScoreArgs a = score_args(0, mine);
                 a.samples = ctx->d_samples.as<uint32_t>() + (size_t)done * k;
                 if (host_nrm) a.row_nrm = ctx->d_rownrm.as<double>() + (size_t)done * k * 3;
                 if (int rc = launch_score_kind(ctx, kind, cloud_for_flags, a, exact_only)) return rc;
+            }
+            for (int c = 0; pl && c < pl->count; ++c) { /* one launch per chunk, behind the chunk's arrival */
+                if (int rc = prep_chunk(ctx, v, *pl, c)) return rc;
+                if (!mine) continue;
+                ScoreArgs a = score_args(0, mine);
+                a.samples = ctx->d_samples.as<uint32_t>() + (size_t)done * k;
+                a.models_in = ctx->d_models_all.as<double>() + (size_t)done * 8;
+                a.valid_in = ctx->d_valid_all.as<uint8_t>() + (size_t)done;
+                const uint32_t b = pl->begin[c];
+                a.xyz = v.xyz + 3 * (size_t)b;
+                a.nrm = nullptr;
+                a.pts32 = v.pts32 + b;
+                a.blob = v.blob + (size_t)(b / kTile) * kBlobF4;
+                a.perm = v.perm + b;
+                a.meta = pl->metas + c;
+                a.n = pl->begin[c + 1] - b;
+                if (int rc = launch_score_kind(ctx, kind, cloud_for_flags, a, false)) return rc;
             }
             M3D_CUDA(ctx, cudaEventRecord(ev_s1, ctx->stream));
             wave_best_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->d_counts.as<uint32_t>(), mine, (uint32_t)R, (uint32_t)rank, n,
@@ -812,8 +900,13 @@ struct Fit {
             if (speculate)
                 if (int rc = enqueue_refine()) return rc;
             M3D_CUDA(ctx, cudaMemcpyAsync(hs, ds, sizeof(SmallDev), cudaMemcpyDeviceToHost, ctx->stream));
+            if (pl && done == 0)
+                M3D_CUDA(ctx, cudaMemcpyAsync(ctx->h_metas.p, pl->metas, sizeof(CloudMeta) * pl->count, cudaMemcpyDeviceToHost, ctx->stream));
             if (speculate) M3D_CUDA(ctx, cudaEventRecord(ev_b, ctx->stream));
             M3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            if (pl && done == 0) /* NaN / inf coordinates need the fp64 reference-order kernel: plain upload path */
+                for (int c = 0; c < pl->count; ++c)
+                    if (ctx->h_metas.as<CloudMeta>()[c].nonfinite) return kRetryUnchunked;
             float ms = 0;
             cudaEventElapsedTime(&ms, ev_s0, ev_s1);
             score_ms += ms;
@@ -946,6 +1039,7 @@ int fit_view(m3d_ctx *ctx, int kind, const m3d_cloud *cloud_for_flags, const Clo
     if (p.probability >= 1.0 && !loop_on_host()) {
         const int rc = f.run_on_device();
         if (rc != kRetryOnHost) return rc;
+        if (v.chunks) return kRetryUnchunked; /* the host loop needs the whole cloud prepared */
         Fit g(ctx, kind, cloud_for_flags, v, p, seg, res); /* fresh state */
         if (int rc2 = g.setup()) return rc2;
         return g.run_on_host();
@@ -990,6 +1084,114 @@ void m3d_cloud_free(m3d_cloud *c) {
 }
 size_t m3d_cloud_size(const m3d_cloud *c) { return c ? c->n : 0; }
 
+} /* extern "C" */
+
+namespace {
+/* results of a finished fit -> the caller's buffers (model, ascending inlier indices) */
+int deliver(m3d_ctx *ctx, int kind, const FitResult &res, double *model_out, size_t *inl_out, size_t *n_inl,
+            m3d_ransac_stats *stats) {
+    if (stats) *stats = res.st;
+    if (res.st.found) {
+        /* model = refined parameters, inliers = those of the minimal model (ransac.h:621-622) */
+        for (int i = 0; i < param_count(kind); ++i) model_out[i] = res.refined[i];
+        *n_inl = (size_t)res.n_inl;
+        if (inl_out && res.n_inl) {
+            static_assert(sizeof(size_t) == sizeof(unsigned long long), "size_t must be 64-bit");
+            M3D_CUDA(ctx, cudaMemcpyAsync(inl_out, ctx->d_inl.p, sizeof(size_t) * (size_t)res.n_inl,
+                                          cudaMemcpyDeviceToHost, ctx->stream));
+            M3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        }
+    }
+    return res.ret;
+}
+
+/* device-mapped address of a pinned (page-locked, mapped) host buffer, or null for pageable memory */
+const double *mapped_address(const double *host) {
+    if (!host) return nullptr;
+    cudaPointerAttributes at{};
+    if (cudaPointerGetAttributes(&at, host) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    if (at.type != cudaMemoryTypeHost || !at.devicePointer) return nullptr;
+    return static_cast<const double *>(at.devicePointer);
+}
+
+int e2e_chunks() { /* M3D_E2E_CHUNKS: 1 = plain upload (round-1 path), default 4 */
+    static const int v = getenv("M3D_E2E_CHUNKS") ? std::max(1, std::min(8, atoi(getenv("M3D_E2E_CHUNKS")))) : 4;
+    return v;
+}
+
+/* The host-buffer fit with the upload overlapped (see ChunkPlan).  Returns kRetryUnchunked when the call does not
+ * qualify or has to be redone through the plain upload path. */
+int fit_host_chunked(m3d_ctx *ctx, int kind, const double *xyz, const double *nrm, size_t n, const m3d_ransac_params *p,
+                     double *model_out, size_t *inl_out, size_t *n_inl, m3d_ransac_stats *stats) {
+    const int k = sample_size(kind);
+    const int want = e2e_chunks();
+    if (want < 2 || p->probability < 1.0 || loop_on_host() || score_path() != 2 || n < (size_t)want * 64 * kTile ||
+        p->max_iteration == 0 || p->max_iteration > (1u << 18) * (uint64_t)std::max(ctx->world, 1) ||
+        (p->flags & (M3D_FLAG_EXACT_ONLY | M3D_FLAG_DENSE | M3D_FLAG_CLASSIFY)) || !(p->threshold > 0) ||
+        !device_draw_eligible((uint32_t)n, k, p->max_iteration))
+        return kRetryUnchunked;
+    const double *dxyz = mapped_address(xyz);
+    const double *dnrm = kind == kCylinder ? mapped_address(nrm) : nullptr;
+    if (!dxyz || (kind == kCylinder && !dnrm)) return kRetryUnchunked; /* pageable memory: plain path */
+    if (!ctx->copy_stream) {
+        M3D_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+        for (auto &e : ctx->ev_chunk) M3D_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    if (!ctx->scratch_cloud) ctx->scratch_cloud = new m3d_cloud();
+    m3d_cloud *c = ctx->scratch_cloud;
+    c->ctx = ctx;
+    c->n = n;
+    c->sorted = false;
+    c->has_normals = false;
+    c->h_nrm = nullptr;
+    c->h_meta = CloudMeta{};
+    const uint32_t ntiles = (uint32_t)((n + kTile - 1) / kTile);
+    ChunkPlan pl;
+    pl.count = want;
+    const uint32_t per = (ntiles + want - 1) / want;
+    for (int i = 0; i <= want; ++i) pl.begin[i] = (uint32_t)std::min<size_t>(n, (size_t)per * i * kTile);
+    constexpr int kScanBlocks = kBins / (kScanBlock * kScanItems);
+    M3D_CUDA(ctx, c->xyz.reserve(sizeof(double) * 3 * n));
+    M3D_CUDA(ctx, c->pts32.reserve(sizeof(float4) * n));
+    M3D_CUDA(ctx, c->blob.reserve(sizeof(float4) * ((size_t)ntiles + want) * kBlobF4));
+    M3D_CUDA(ctx, c->perm.reserve(sizeof(uint32_t) * ((size_t)ntiles + want) * kTile));
+    M3D_CUDA(ctx, c->keys.reserve(sizeof(uint32_t) * ((size_t)per * kTile)));
+    M3D_CUDA(ctx, c->hist.reserve(sizeof(uint32_t) * ((size_t)kBins + kScanBlocks)));
+    M3D_CUDA(ctx, ctx->d_metas.reserve(sizeof(CloudMeta) * 8));
+    M3D_CUDA(ctx, ctx->h_metas.reserve(sizeof(CloudMeta) * 8));
+    pl.metas = ctx->d_metas.as<CloudMeta>();
+    pl.keys = c->keys.as<uint32_t>();
+    pl.hist = c->hist.as<uint32_t>();
+    pl.dev_of_host_xyz = dxyz;
+    pl.dev_of_host_nrm = dnrm;
+    /* the copies: chunk after chunk on the copy stream, one event each */
+    for (int i = 0; i < want; ++i) {
+        const size_t b = pl.begin[i], cnt = pl.begin[i + 1] - pl.begin[i];
+        if (cnt)
+            M3D_CUDA(ctx, cudaMemcpyAsync(c->xyz.as<double>() + 3 * b, xyz + 3 * b, sizeof(double) * 3 * cnt,
+                                          cudaMemcpyHostToDevice, ctx->copy_stream));
+        M3D_CUDA(ctx, cudaEventRecord(ctx->ev_chunk[i], ctx->copy_stream));
+    }
+    CloudView v{c->xyz.as<double>(), dnrm, c->pts32.as<float4>(), pl.metas, (uint32_t)n, false};
+    v.blob = c->blob.as<float4>();
+    v.perm = c->perm.as<uint32_t>();
+    v.chunks = &pl;
+    FitResult res;
+    const int rc = fit_view(ctx, kind, c, v, *p, nullptr, &res);
+    if (rc != M3D_OK) {
+        cudaStreamSynchronize(ctx->copy_stream); /* nothing of this call may still be writing the staging buffers */
+        cudaStreamSynchronize(ctx->stream);
+        return rc;
+    }
+    return deliver(ctx, kind, res, model_out, inl_out, n_inl, stats);
+}
+}  // namespace
+
+extern "C" {
+
 int m3d_ransac_fit_cloud(m3d_ctx *ctx, int kind, const m3d_cloud *cloud, const m3d_ransac_params *p,
                          double *model_out, size_t *inl_out, size_t *n_inl, m3d_ransac_stats *stats) {
     if (!ctx || !cloud || !model_out || !n_inl) return M3D_ERR_INVALID_ARG;
@@ -1009,19 +1211,7 @@ int m3d_ransac_fit_cloud(m3d_ctx *ctx, int kind, const m3d_cloud *cloud, const m
     }
     FitResult res;
     if (int rc = fit_view(ctx, kind, cloud, v, *p, nullptr, &res)) return rc;
-    if (stats) *stats = res.st;
-    if (res.st.found) {
-        /* model = refined parameters, inliers = those of the minimal model (ransac.h:621-622) */
-        for (int i = 0; i < param_count(kind); ++i) model_out[i] = res.refined[i];
-        *n_inl = (size_t)res.n_inl;
-        if (inl_out && res.n_inl) {
-            static_assert(sizeof(size_t) == sizeof(unsigned long long), "size_t must be 64-bit");
-            M3D_CUDA(ctx, cudaMemcpyAsync(inl_out, ctx->d_inl.p, sizeof(size_t) * (size_t)res.n_inl,
-                                          cudaMemcpyDeviceToHost, ctx->stream));
-            M3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        }
-    }
-    return res.ret;
+    return deliver(ctx, kind, res, model_out, inl_out, n_inl, stats);
 }
 
 int m3d_ransac_fit(m3d_ctx *ctx, int kind, const double *xyz, const double *nrm, size_t n,
@@ -1034,6 +1224,13 @@ int m3d_ransac_fit(m3d_ctx *ctx, int kind, const double *xyz, const double *nrm,
     if (int rc = check_params(ctx, kind, n, nrm != nullptr, p)) return rc;
     if (n >= (size_t)kInvalidBit) return ctx->fail(M3D_ERR_INVALID_ARG, "clouds of >= 2^31 points are not supported");
     M3D_CUDA(ctx, cudaSetDevice(ctx->device));
+    {
+        const int rc = fit_host_chunked(ctx, kind, xyz, nrm, n, p, model_out, inl_out, n_inl, stats);
+        if (rc != kRetryUnchunked) return rc;
+        for (int i = 0; i < 8; ++i) model_out[i] = 0;
+        *n_inl = 0;
+        if (stats) memset(stats, 0, sizeof *stats);
+    }
     /* the staging cloud lives in the context: repeated calls re-use its device buffers */
     if (!ctx->scratch_cloud) ctx->scratch_cloud = new m3d_cloud();
     /* the normals stay on the host: the fit reads them at the sample points only (cylinder MinimalFit,

@@ -553,6 +553,11 @@ struct ScoreArgs {
     const double *row_nrm;   /* optional: normals of the sampled points only, [row][k][3] (see fit_row) */
     const CloudMeta *meta;
     const uint32_t *samples; /* rows x k of this wave (device)                          */
+    /* optional: the minimal models of ALL wave rows, computed beforehand ([wave row][8] + MinimalFit flags).  Set by
+     * the chunked host-buffer fit: a launch then scores one chunk of the cloud (xyz / pts32 / blob / perm / meta / n
+     * describe the chunk) while later chunks are still being uploaded, and the sample points may lie in any chunk. */
+    const double *models_in;
+    const uint8_t *valid_in;
     uint32_t *counts;        /* [rows]: inlier count (atomicAdd per chunk), bit31 = MinimalFit false */
     unsigned long long *resolves;
     double *models;        /* [rows][8] minimal models (written by the point-chunk-0 CTAs)  */

@@ -170,7 +170,14 @@ __global__ void __launch_bounds__(THREADS + 32, CellCfg<THREADS>::kMinBlocks) sc
                 } else { /* queue full: decide here with the reference arithmetic */
                     const uint32_t prov = e.y >> 31, pt = a.perm[e.y & 0x7fffffffu];
                     double m[8];
-                    const bool ok = fit_row<KIND>(a.xyz, a.nrm, a.samples, a.src_row(e.x), m, a.row_nrm);
+                    bool ok;
+                    if (a.models_in) {
+                        const uint32_t sr = a.src_row(e.x);
+                        ok = a.valid_in[sr] != 0;
+                        for (int i = 0; i < 8; ++i) m[i] = a.models_in[(size_t)sr * 8 + i];
+                    } else {
+                        ok = fit_row<KIND>(a.xyz, a.nrm, a.samples, a.src_row(e.x), m, a.row_nrm);
+                    }
                     uint32_t in = 0;
                     if (ok) {
                         ex::Dist<KIND> dist;
@@ -193,7 +200,16 @@ __global__ void __launch_bounds__(THREADS + 32, CellCfg<THREADS>::kMinBlocks) sc
         row[h] = mine ? blockIdx.x * NH + hl : 0xffffffffu;
         double m[8];
         bool ok = false;
-        if (row[h] < a.rows) ok = fit_row<KIND>(a.xyz, a.nrm, a.samples, a.src_row(row[h]), m, a.row_nrm);
+        if (row[h] < a.rows) {
+            if (a.models_in) { /* chunked launch: the model was solved before the upload finished */
+                const uint32_t sr = a.src_row(row[h]);
+                ok = a.valid_in[sr] != 0;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) m[i] = a.models_in[(size_t)sr * 8 + i];
+            } else {
+                ok = fit_row<KIND>(a.xyz, a.nrm, a.samples, a.src_row(row[h]), m, a.row_nrm);
+            }
+        }
         invalid[h] = (row[h] < a.rows) && !ok;
         if (blockIdx.y == 0 && row[h] < a.rows) {
 #pragma unroll

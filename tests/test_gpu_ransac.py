@@ -534,3 +534,43 @@ def test_sphere_refit_of_degenerate_inliers_is_finite(ctx, capi):
     assert st["found"] == 1 and np.all(np.isfinite(model)), (st, model)
     d = np.abs(np.linalg.norm(ring - model[:3], axis=1) - model[3])
     assert np.median(d) < 0.05
+
+
+# ---------------------------------------------------------------------------------------------------
+# the chunked host-buffer fit (pinned caller buffers): the cloud is uploaded in chunks on a copy stream, each chunk is
+# scored as it arrives, the minimal models come from a zero-copy gather of the sample points
+def _pinned(a):
+    import torch
+    t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    return t, t.numpy()
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_chunked_pinned_fit_parity(ctx, capi, orc, kind):
+    """>= 262144 points in pinned memory, probability 1: the overlapped-upload path == the oracle's sequential loop and
+    == the same call on pageable memory (plain upload path)"""
+    xyz, nrm = synth.make_c2(n=300_000, seed=41)
+    nrm = nrm if kind == 2 else None
+    keep, pxyz = _pinned(xyz)
+    keepn, pnrm = _pinned(nrm) if nrm is not None else (None, None)
+    for seed, H in ((3, 700), (4, 1500)):
+        before = ctx.launches
+        rc, model, inl, st = ctx.ransac_fit(kind, pxyz, pnrm, 0.01, H, 1.0, seed=seed)
+        n_launch = ctx.launches - before
+        rc2, model2, inl2, st2 = ctx.ransac_fit(kind, xyz, nrm, 0.01, H, 1.0, seed=seed)      # pageable: plain path
+        assert n_launch > ctx.launches - before - n_launch                                     # chunk pipelines ran
+        assert rc == rc2 and np.array_equal(inl, inl2) and np.array_equal(model, model2)
+        orc_rc, omodel, oinl, ost = orc.ransac_fit(kind, xyz, nrm, thr=0.01, max_it=H, prob=1.0, seed=seed)
+        assert rc == orc_rc and np.array_equal(inl, oinl)
+        for key in ("best_index", "best_count", "iterations_run", "stop_index", "found"):
+            assert st[key] == ost[key] == st2[key], (key, st, ost)
+
+
+def test_chunked_pinned_fit_falls_back_on_nonfinite_points(ctx, capi, orc):
+    xyz = synth.make_c1(n=300_000, seed=42)
+    xyz[123456, 1] = np.nan
+    xyz[7] = np.inf
+    keep, pxyz = _pinned(xyz)
+    rc, model, inl, st = ctx.ransac_fit(capi.PLANE, pxyz, None, 0.01, 300, 1.0, seed=2)
+    orc_rc, omodel, oinl, ost = orc.ransac_fit(orc.PLANE, xyz, thr=0.01, max_it=300, prob=1.0, seed=2)
+    assert rc == orc_rc and np.array_equal(inl, oinl) and st["best_index"] == ost["best_index"]
