@@ -122,6 +122,9 @@ typedef struct m3d_ransac_params {
 #define M3D_FLAG_DENSE 4u      /* score every point-hypothesis pair (no bounding-sphere culling) */
 #define M3D_FLAG_CLASSIFY 8u   /* round-1 culling kernel (M3D_SCORE_PATH=cull) only: always pre-sort the hypotheses into
                                   culled / dense ones (default there: launches of >= 12288 rows) */
+#define M3D_FLAG_CHUNKED_UPLOAD 32u /* m3d_ransac_fit, pinned buffers, probability 1: score the cloud chunk by chunk behind
+                                       its upload (experimental: measured slower than the default) */
+#define M3D_FLAG_PLAIN_UPLOAD 64u   /* m3d_ransac_fit: upload, prepare, then fit, all on one stream (the round-1 path) */
 #define M3D_FLAG_STATS 16u     /* run the counting build of the scoring kernel (slower); read with m3d_score_stats */
 
 typedef struct m3d_ransac_stats {

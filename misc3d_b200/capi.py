@@ -18,6 +18,7 @@ KSAMPLE = {PLANE: 3, SPHERE: 4, CYLINDER: 2}
 NPARAM = {PLANE: 4, SPHERE: 4, CYLINDER: 7}
 MATCH_FLANN, MATCH_ANNOY = 0, 1
 FLAG_EXACT_ONLY, FLAG_NO_REFIT, FLAG_DENSE, FLAG_CLASSIFY, FLAG_STATS = 1, 2, 4, 8, 16
+FLAG_CHUNKED_UPLOAD, FLAG_PLAIN_UPLOAD = 32, 64
 
 OK = 0
 ERR_INVALID_ARG, ERR_TOO_FEW_POINTS, ERR_PROBABILITY, ERR_NO_NORMALS = -1, -2, -3, -4

@@ -38,23 +38,51 @@ struct SmallDev { /* layout of ctx->d_small */
     RowBreaks draw;     /* outcome of the device-side sample draw                     */
 };
 
+/* bounding box + fp32 copy of n points (3 kernels) */
+int convert_points(m3d_ctx *ctx, const double *xyz, uint32_t n, CloudMeta *meta, float4 *pts32) {
+    const int nb = std::max(1, std::min<int>(ctx->sm_count * 8, (int)((n + 255) / 256)));
+    M3D_CUDA(ctx, ctx->d_part.reserve(sizeof(BBoxPart) * (size_t)nb));
+    BBoxPart *bp = ctx->d_part.as<BBoxPart>();
+    bbox_kernel<<<nb, 256, 0, ctx->stream>>>(xyz, n, bp);
+    M3D_LAUNCHED(ctx);
+    bbox_final_kernel<<<1, 256, 0, ctx->stream>>>(bp, nb, meta);
+    M3D_LAUNCHED(ctx);
+    convert_kernel<<<nb, 256, 0, ctx->stream>>>(xyz, n, meta, pts32);
+    M3D_LAUNCHED(ctx);
+    return M3D_OK;
+}
+/* Morton-ordered tile blob of n points: counting sort over a 2^bits cubed grid (histogram, 3-kernel scan, scatter)
+ * + bounding spheres.  hist needs (1 << 3 bits) + bins / 2048 words, keys n words. */
+size_t morton_hist_words(int bits) { return ((size_t)1 << (3 * bits)) + (((size_t)1 << (3 * bits)) / (kScanBlock * kScanItems)); }
+int morton_sort(m3d_ctx *ctx, const float4 *pts32, uint32_t n, const CloudMeta *meta, uint32_t *keys, uint32_t *hist,
+                float4 *blob, uint32_t *perm) {
+    const int bits = morton_bits(n);
+    const uint32_t bins = 1u << (3 * bits);
+    const int scan_blocks = (int)(bins / (kScanBlock * kScanItems));
+    uint32_t *bsum = hist + bins;
+    const uint32_t ntiles = (n + kTile - 1) / kTile;
+    M3D_CUDA(ctx, cudaMemsetAsync(hist, 0, sizeof(uint32_t) * (size_t)bins, ctx->stream));
+    const int nb = std::max(1, std::min<int>(ctx->sm_count * 8, (int)((n + 255) / 256)));
+    morton_hist_kernel<<<nb, 256, 0, ctx->stream>>>(pts32, n, meta, bits, keys, hist);
+    M3D_LAUNCHED(ctx);
+    scan_sums_kernel<<<scan_blocks, kScanBlock, 0, ctx->stream>>>(hist, bsum);
+    M3D_LAUNCHED(ctx);
+    scan_top_kernel<<<1, kScanBlock, 0, ctx->stream>>>(bsum, scan_blocks);
+    M3D_LAUNCHED(ctx);
+    scan_apply_kernel<<<scan_blocks, kScanBlock, 0, ctx->stream>>>(hist, bsum);
+    M3D_LAUNCHED(ctx);
+    morton_scatter_kernel<<<nb, 256, 0, ctx->stream>>>(pts32, n, keys, hist, blob, perm);
+    M3D_LAUNCHED(ctx);
+    tile_bounds_kernel<<<ntiles, kTile, 0, ctx->stream>>>(blob, n, meta);
+    M3D_LAUNCHED(ctx);
+    return M3D_OK;
+}
+
 int prepare_cloud(m3d_ctx *ctx, m3d_cloud *c) {
     const uint32_t n = (uint32_t)c->n;
     M3D_CUDA(ctx, c->pts32.reserve(sizeof(float4) * (size_t)std::max<uint32_t>(n, 1)));
     M3D_CUDA(ctx, c->meta.reserve(sizeof(CloudMeta)));
-    const int nb = std::max(1, std::min<int>(ctx->sm_count * 8, (int)((n + 255) / 256)));
-    M3D_CUDA(ctx, ctx->d_part.reserve(sizeof(BBoxPart) * (size_t)nb + sizeof(double) * nb));
-    BBoxPart *bp = ctx->d_part.as<BBoxPart>();
-    double *mp = reinterpret_cast<double *>(bp + nb);
-    bbox_kernel<<<nb, 256, 0, ctx->stream>>>(c->xyz.as<double>(), n, bp);
-    M3D_LAUNCHED(ctx);
-    bbox_final_kernel<<<1, 256, 0, ctx->stream>>>(bp, nb, c->meta.as<CloudMeta>());
-    M3D_LAUNCHED(ctx);
-    convert_kernel<<<nb, 256, 0, ctx->stream>>>(c->xyz.as<double>(), n, c->meta.as<CloudMeta>(),
-                                                c->pts32.as<float4>(), mp);
-    M3D_LAUNCHED(ctx);
-    convert_final_kernel<<<1, 256, 0, ctx->stream>>>(mp, nb, c->meta.as<CloudMeta>());
-    M3D_LAUNCHED(ctx);
+    if (int rc = convert_points(ctx, c->xyz.as<double>(), n, c->meta.as<CloudMeta>(), c->pts32.as<float4>())) return rc;
     M3D_CUDA(ctx, cudaMemcpyAsync(&c->h_meta, c->meta.p, sizeof(CloudMeta), cudaMemcpyDeviceToHost, ctx->stream));
     M3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return M3D_OK;
@@ -112,30 +140,13 @@ int ensure_sorted(m3d_ctx *ctx, const m3d_cloud *c) {
     if (!cull_enabled() || c->n < kCullMinPoints || c->h_meta.nonfinite) return M3D_OK;
     const uint32_t n = (uint32_t)c->n;
     const uint32_t ntiles = (n + kTile - 1) / kTile;
-    constexpr int kScanBlocks = kBins / (kScanBlock * kScanItems);
-    static_assert(kScanBlocks <= kScanBlock, "top-level scan is one block");
     M3D_CUDA(ctx, c->blob.reserve(sizeof(float4) * (size_t)ntiles * kBlobF4));
     M3D_CUDA(ctx, c->perm.reserve(sizeof(uint32_t) * (size_t)ntiles * kTile));
     M3D_CUDA(ctx, c->keys.reserve(sizeof(uint32_t) * (size_t)n));
-    M3D_CUDA(ctx, c->hist.reserve(sizeof(uint32_t) * ((size_t)kBins + kScanBlocks)));
-    uint32_t *hist = c->hist.as<uint32_t>();
-    uint32_t *bsum = hist + kBins;
-    M3D_CUDA(ctx, cudaMemsetAsync(hist, 0, sizeof(uint32_t) * (size_t)kBins, ctx->stream));
-    const int nb = std::max(1, std::min<int>(ctx->sm_count * 8, (int)((n + 255) / 256)));
-    morton_hist_kernel<<<nb, 256, 0, ctx->stream>>>(c->pts32.as<float4>(), n, c->meta.as<CloudMeta>(),
-                                                    c->keys.as<uint32_t>(), hist);
-    M3D_LAUNCHED(ctx);
-    scan_sums_kernel<<<kScanBlocks, kScanBlock, 0, ctx->stream>>>(hist, bsum);
-    M3D_LAUNCHED(ctx);
-    scan_top_kernel<<<1, kScanBlock, 0, ctx->stream>>>(bsum, kScanBlocks);
-    M3D_LAUNCHED(ctx);
-    scan_apply_kernel<<<kScanBlocks, kScanBlock, 0, ctx->stream>>>(hist, bsum);
-    M3D_LAUNCHED(ctx);
-    morton_scatter_kernel<<<nb, 256, 0, ctx->stream>>>(c->pts32.as<float4>(), n, c->keys.as<uint32_t>(), hist,
-                                                       c->blob.as<float4>(), c->perm.as<uint32_t>());
-    M3D_LAUNCHED(ctx);
-    tile_bounds_kernel<<<ntiles, kTile, 0, ctx->stream>>>(c->blob.as<float4>(), n, c->meta.as<CloudMeta>());
-    M3D_LAUNCHED(ctx);
+    M3D_CUDA(ctx, c->hist.reserve(sizeof(uint32_t) * morton_hist_words(morton_bits(n))));
+    if (int rc = morton_sort(ctx, c->pts32.as<float4>(), n, c->meta.as<CloudMeta>(), c->keys.as<uint32_t>(),
+                             c->hist.as<uint32_t>(), c->blob.as<float4>(), c->perm.as<uint32_t>()))
+        return rc;
     c->sorted = true;
     return M3D_OK;
 }
@@ -162,15 +173,14 @@ int launch_cull_t(m3d_ctx *ctx, const ScoreArgs &a, uint32_t ntiles) {
     return M3D_OK;
 }
 
-template <int KIND, int THREADS, int NH, bool STATS>
-int launch_cell_t(m3d_ctx *ctx, const ScoreArgs &a, uint32_t ntiles) {
+template <int KIND, int THREADS, int NH, bool STATS, bool PRE>
+int launch_cell_tt(m3d_ctx *ctx, const ScoreArgs &a, uint32_t ntiles) {
+    auto kern = score_cell_kernel<KIND, THREADS, NH, STATS, PRE>;
     const size_t smem = CellSmem<KIND, THREADS, NH>::bytes();
-    M3D_CUDA(ctx, cudaFuncSetAttribute(score_cell_kernel<KIND, THREADS, NH, STATS>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    M3D_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const uint32_t hb = (a.rows + NH - 1) / NH;
     int per_sm = 0;
-    M3D_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, score_cell_kernel<KIND, THREADS, NH, STATS>,
-                                                                 THREADS + 32, smem));
+    M3D_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, THREADS + 32, smem));
     const uint32_t slots = (uint32_t)ctx->sm_count * (uint32_t)std::max(per_sm, 1);
     uint32_t per_hb = std::max<uint32_t>(1, (slots + hb - 1) / hb);
     per_hb = std::min(per_hb, ntiles);
@@ -179,9 +189,14 @@ int launch_cell_t(m3d_ctx *ctx, const ScoreArgs &a, uint32_t ntiles) {
     ScoreArgs b = a;
     b.tile_counter = ctx->d_tiles.as<uint32_t>();
     dim3 grid(hb, per_hb);
-    score_cell_kernel<KIND, THREADS, NH, STATS><<<grid, THREADS + 32, smem, ctx->stream>>>(b);
+    kern<<<grid, THREADS + 32, smem, ctx->stream>>>(b);
     M3D_LAUNCHED(ctx);
     return M3D_OK;
+}
+template <int KIND, int THREADS, int NH, bool STATS>
+int launch_cell_t(m3d_ctx *ctx, const ScoreArgs &a, uint32_t ntiles) {
+    if (a.models_in) return launch_cell_tt<KIND, THREADS, NH, STATS, true>(ctx, a, ntiles);
+    return launch_cell_tt<KIND, THREADS, NH, STATS, false>(ctx, a, ntiles);
 }
 
 /* ---- launch of the hot kernel for one (wave, kind) */
@@ -465,6 +480,22 @@ struct ChunkPlan {
     CloudMeta *metas = nullptr;                       /* device, one per chunk                                 */
     uint32_t *keys = nullptr, *hist = nullptr;        /* Morton sort scratch (re-used chunk after chunk)       */
     bool prepped[8] = {false, false, false, false, false, false, false, false};
+    bool pre_models = false;  /* count >= 2: minimal models solved beforehand from the pinned buffer (zero-copy)   */
+    const double *h_xyz = nullptr; /* the caller's buffer and its destination: the copies are issued by the fit, */
+    double *d_xyz = nullptr;       /* right behind the device-side sample draw (so that the two overlap)          */
+    bool copies_issued = false;
+    int issue_copies(m3d_ctx *ctx) {
+        if (copies_issued) return M3D_OK;
+        copies_issued = true;
+        for (int i = 0; i < count; ++i) {
+            const size_t b = begin[i], cnt = begin[i + 1] - begin[i];
+            if (cnt)
+                M3D_CUDA(ctx, cudaMemcpyAsync(d_xyz + 3 * b, h_xyz + 3 * b, sizeof(double) * 3 * cnt, cudaMemcpyHostToDevice,
+                                              ctx->copy_stream));
+            M3D_CUDA(ctx, cudaEventRecord(ctx->ev_chunk[i], ctx->copy_stream));
+        }
+        return M3D_OK;
+    }
 };
 constexpr int kRetryUnchunked = 1001; /* internal: a chunk holds NaN / inf coordinates, use the plain upload path */
 
@@ -537,39 +568,11 @@ int prep_chunk(m3d_ctx *ctx, const CloudView &v, ChunkPlan &pl, int c) {
     if (pl.prepped[c]) return M3D_OK;
     M3D_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_chunk[c], 0));
     const uint32_t b = pl.begin[c], n = pl.begin[c + 1] - pl.begin[c];
-    const double *xyz = v.xyz + 3 * (size_t)b;
     float4 *pts32 = const_cast<float4 *>(v.pts32) + b;
-    float4 *blob = const_cast<float4 *>(v.blob) + (size_t)(b / kTile) * kBlobF4;
-    uint32_t *perm = const_cast<uint32_t *>(v.perm) + b;
-    CloudMeta *meta = pl.metas + c;
-    const int nb = std::max(1, std::min<int>(ctx->sm_count * 8, (int)((n + 255) / 256)));
-    M3D_CUDA(ctx, ctx->d_part.reserve(sizeof(BBoxPart) * (size_t)nb + sizeof(double) * nb));
-    BBoxPart *bp = ctx->d_part.as<BBoxPart>();
-    double *mp = reinterpret_cast<double *>(bp + nb);
-    bbox_kernel<<<nb, 256, 0, ctx->stream>>>(xyz, n, bp);
-    M3D_LAUNCHED(ctx);
-    bbox_final_kernel<<<1, 256, 0, ctx->stream>>>(bp, nb, meta);
-    M3D_LAUNCHED(ctx);
-    convert_kernel<<<nb, 256, 0, ctx->stream>>>(xyz, n, meta, pts32, mp);
-    M3D_LAUNCHED(ctx);
-    convert_final_kernel<<<1, 256, 0, ctx->stream>>>(mp, nb, meta);
-    M3D_LAUNCHED(ctx);
-    const uint32_t ntiles = (n + kTile - 1) / kTile;
-    constexpr int kScanBlocks = kBins / (kScanBlock * kScanItems);
-    uint32_t *hist = pl.hist, *bsum = hist + kBins;
-    M3D_CUDA(ctx, cudaMemsetAsync(hist, 0, sizeof(uint32_t) * (size_t)kBins, ctx->stream));
-    morton_hist_kernel<<<nb, 256, 0, ctx->stream>>>(pts32, n, meta, pl.keys, hist);
-    M3D_LAUNCHED(ctx);
-    scan_sums_kernel<<<kScanBlocks, kScanBlock, 0, ctx->stream>>>(hist, bsum);
-    M3D_LAUNCHED(ctx);
-    scan_top_kernel<<<1, kScanBlock, 0, ctx->stream>>>(bsum, kScanBlocks);
-    M3D_LAUNCHED(ctx);
-    scan_apply_kernel<<<kScanBlocks, kScanBlock, 0, ctx->stream>>>(hist, bsum);
-    M3D_LAUNCHED(ctx);
-    morton_scatter_kernel<<<nb, 256, 0, ctx->stream>>>(pts32, n, pl.keys, hist, blob, perm);
-    M3D_LAUNCHED(ctx);
-    tile_bounds_kernel<<<ntiles, kTile, 0, ctx->stream>>>(blob, n, meta);
-    M3D_LAUNCHED(ctx);
+    if (int rc = convert_points(ctx, v.xyz + 3 * (size_t)b, n, pl.metas + c, pts32)) return rc;
+    if (int rc = morton_sort(ctx, pts32, n, pl.metas + c, pl.keys, pl.hist,
+                             const_cast<float4 *>(v.blob) + (size_t)(b / kTile) * kBlobF4, const_cast<uint32_t *>(v.perm) + b))
+        return rc;
     pl.prepped[c] = true;
     return M3D_OK;
 }
@@ -816,6 +819,8 @@ struct Fit {
         M3D_CUDA(ctx, ctx->d_samples.reserve(sizeof(uint32_t) * (size_t)rows_all * k));
         const bool dev_draw = !host_nrm && device_draw_eligible(n, k, rows_all);
         std::vector<uint32_t> h_table;
+        if (v.chunks && !dev_draw)
+            if (int rc = v.chunks->issue_copies(ctx)) return rc; /* the host draw below overlaps the DMA (pinned buffers) */
         if (dev_draw) {
             M3D_CUDA(ctx, cudaEventRecord(ev_d0, ctx->stream));
             if (int rc = draw_table_device(ctx, p.seed, n, k, rows_all, ctx->d_samples.as<uint32_t>(), &ds->draw)) return rc;
@@ -842,7 +847,9 @@ struct Fit {
             }
         }
         ChunkPlan *pl = v.chunks;
-        if (pl) { /* all minimal models now, from the caller's pinned buffer (the upload is still in flight) */
+        if (pl)
+            if (int rc = pl->issue_copies(ctx)) return rc; /* behind the draw kernels: the two overlap */
+        if (pl && pl->pre_models) { /* all minimal models now, from the caller's pinned buffer (the upload is still in flight) */
             if (!dev_draw) return ctx->fail(M3D_ERR_INTERNAL, "chunked fit without a device-side sample draw");
             M3D_CUDA(ctx, ctx->d_models_all.reserve(sizeof(double) * 8 * (size_t)rows_all));
             M3D_CUDA(ctx, ctx->d_valid_all.reserve((size_t)rows_all));
@@ -875,11 +882,14 @@ struct Fit {
                 if (!mine) continue;
                 ScoreArgs a = score_args(0, mine);
                 a.samples = ctx->d_samples.as<uint32_t>() + (size_t)done * k;
-                a.models_in = ctx->d_models_all.as<double>() + (size_t)done * 8;
-                a.valid_in = ctx->d_valid_all.as<uint8_t>() + (size_t)done;
+                if (host_nrm) a.row_nrm = ctx->d_rownrm.as<double>() + (size_t)done * k * 3;
+                if (pl->pre_models) {
+                    a.models_in = ctx->d_models_all.as<double>() + (size_t)done * 8;
+                    a.valid_in = ctx->d_valid_all.as<uint8_t>() + (size_t)done;
+                    a.nrm = nullptr;
+                }
                 const uint32_t b = pl->begin[c];
                 a.xyz = v.xyz + 3 * (size_t)b;
-                a.nrm = nullptr;
                 a.pts32 = v.pts32 + b;
                 a.blob = v.blob + (size_t)(b / kTile) * kBlobF4;
                 a.perm = v.perm + b;
@@ -1117,8 +1127,10 @@ const double *mapped_address(const double *host) {
     return static_cast<const double *>(at.devicePointer);
 }
 
-int e2e_chunks() { /* M3D_E2E_CHUNKS: 1 = plain upload (round-1 path), default 4 */
-    static const int v = getenv("M3D_E2E_CHUNKS") ? std::max(1, std::min(8, atoi(getenv("M3D_E2E_CHUNKS")))) : 4;
+int e2e_chunks() { /* M3D_E2E_CHUNKS: 0 = plain upload (round-1 path); 1 (default) = one chunk: the upload runs on the
+                    * copy stream while the sample table is drawn and the minimal models are solved from the pinned
+                    * buffer; 2..8 = scoring chunk by chunk behind the upload */
+    static const int v = getenv("M3D_E2E_CHUNKS") ? std::max(0, std::min(8, atoi(getenv("M3D_E2E_CHUNKS")))) : 1;
     return v;
 }
 
@@ -1127,15 +1139,18 @@ int e2e_chunks() { /* M3D_E2E_CHUNKS: 1 = plain upload (round-1 path), default 4
 int fit_host_chunked(m3d_ctx *ctx, int kind, const double *xyz, const double *nrm, size_t n, const m3d_ransac_params *p,
                      double *model_out, size_t *inl_out, size_t *n_inl, m3d_ransac_stats *stats) {
     const int k = sample_size(kind);
-    const int want = e2e_chunks();
-    if (want < 2 || p->probability < 1.0 || loop_on_host() || score_path() != 2 || n < (size_t)want * 64 * kTile ||
+    const int want = (p->flags & M3D_FLAG_CHUNKED_UPLOAD) ? std::max(4, e2e_chunks()) : e2e_chunks();
+    if (want < 1 || (p->flags & M3D_FLAG_PLAIN_UPLOAD) || p->probability < 1.0 || loop_on_host() || score_path() != 2 ||
+        n < (size_t)want * 64 * kTile ||
         p->max_iteration == 0 || p->max_iteration > (1u << 18) * (uint64_t)std::max(ctx->world, 1) ||
         (p->flags & (M3D_FLAG_EXACT_ONLY | M3D_FLAG_DENSE | M3D_FLAG_CLASSIFY)) || !(p->threshold > 0) ||
-        !device_draw_eligible((uint32_t)n, k, p->max_iteration))
+        (want >= 2 && !device_draw_eligible((uint32_t)n, k, p->max_iteration)))
         return kRetryUnchunked;
-    const double *dxyz = mapped_address(xyz);
-    const double *dnrm = kind == kCylinder ? mapped_address(nrm) : nullptr;
-    if (!dxyz || (kind == kCylinder && !dnrm)) return kRetryUnchunked; /* pageable memory: plain path */
+    const bool multi = want >= 2; /* scoring chunk by chunk needs the zero-copy model solve, i.e. pinned buffers */
+    const double *dxyz = multi ? mapped_address(xyz) : nullptr;
+    const double *dnrm = (multi && kind == kCylinder) ? mapped_address(nrm) : nullptr;
+    if (multi && (!dxyz || (kind == kCylinder && !dnrm))) return kRetryUnchunked; /* pageable memory: plain path */
+    if (!multi && kind != kCylinder && !device_draw_eligible((uint32_t)n, k, p->max_iteration)) return kRetryUnchunked;
     if (!ctx->copy_stream) {
         M3D_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
         for (auto &e : ctx->ev_chunk) M3D_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -1153,13 +1168,12 @@ int fit_host_chunked(m3d_ctx *ctx, int kind, const double *xyz, const double *nr
     pl.count = want;
     const uint32_t per = (ntiles + want - 1) / want;
     for (int i = 0; i <= want; ++i) pl.begin[i] = (uint32_t)std::min<size_t>(n, (size_t)per * i * kTile);
-    constexpr int kScanBlocks = kBins / (kScanBlock * kScanItems);
     M3D_CUDA(ctx, c->xyz.reserve(sizeof(double) * 3 * n));
     M3D_CUDA(ctx, c->pts32.reserve(sizeof(float4) * n));
     M3D_CUDA(ctx, c->blob.reserve(sizeof(float4) * ((size_t)ntiles + want) * kBlobF4));
     M3D_CUDA(ctx, c->perm.reserve(sizeof(uint32_t) * ((size_t)ntiles + want) * kTile));
     M3D_CUDA(ctx, c->keys.reserve(sizeof(uint32_t) * ((size_t)per * kTile)));
-    M3D_CUDA(ctx, c->hist.reserve(sizeof(uint32_t) * ((size_t)kBins + kScanBlocks)));
+    M3D_CUDA(ctx, c->hist.reserve(sizeof(uint32_t) * morton_hist_words(morton_bits(per * kTile))));
     M3D_CUDA(ctx, ctx->d_metas.reserve(sizeof(CloudMeta) * 8));
     M3D_CUDA(ctx, ctx->h_metas.reserve(sizeof(CloudMeta) * 8));
     pl.metas = ctx->d_metas.as<CloudMeta>();
@@ -1167,21 +1181,18 @@ int fit_host_chunked(m3d_ctx *ctx, int kind, const double *xyz, const double *nr
     pl.hist = c->hist.as<uint32_t>();
     pl.dev_of_host_xyz = dxyz;
     pl.dev_of_host_nrm = dnrm;
-    /* the copies: chunk after chunk on the copy stream, one event each */
-    for (int i = 0; i < want; ++i) {
-        const size_t b = pl.begin[i], cnt = pl.begin[i + 1] - pl.begin[i];
-        if (cnt)
-            M3D_CUDA(ctx, cudaMemcpyAsync(c->xyz.as<double>() + 3 * b, xyz + 3 * b, sizeof(double) * 3 * cnt,
-                                          cudaMemcpyHostToDevice, ctx->copy_stream));
-        M3D_CUDA(ctx, cudaEventRecord(ctx->ev_chunk[i], ctx->copy_stream));
-    }
+    pl.pre_models = multi;
+    pl.h_xyz = xyz;
+    pl.d_xyz = c->xyz.as<double>();
     CloudView v{c->xyz.as<double>(), dnrm, c->pts32.as<float4>(), pl.metas, (uint32_t)n, false};
+    if (!multi) v.h_nrm = nrm; /* single chunk: the cylinder's sample normals are gathered on the host, behind the DMA */
     v.blob = c->blob.as<float4>();
     v.perm = c->perm.as<uint32_t>();
     v.chunks = &pl;
     FitResult res;
     const int rc = fit_view(ctx, kind, c, v, *p, nullptr, &res);
     if (rc != M3D_OK) {
+        if (!pl.copies_issued && rc == kRetryUnchunked) return rc;
         cudaStreamSynchronize(ctx->copy_stream); /* nothing of this call may still be writing the staging buffers */
         cudaStreamSynchronize(ctx->stream);
         return rc;

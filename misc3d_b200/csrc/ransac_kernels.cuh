@@ -1,7 +1,7 @@
 /*
  * ransac_kernels.cuh -- sm_100a kernels of the RANSAC primitive-fitting path.
  *
- *   cloud preparation   bbox_kernel / bbox_final_kernel / convert_kernel / convert_final_kernel
+ *   cloud preparation   bbox_kernel / bbox_final_kernel / convert_kernel
  *   hot kernel          score_kernel<KIND,THREADS,HPT>   (sample gather -> minimal solve ->
  *                       all-point inlier count, fp32 guard-banded + fp64 reference-order resolve)
  *   reference-order     score_exact_kernel<KIND>         (fp64 only; debug / non-finite clouds)
@@ -198,47 +198,29 @@ __global__ void __launch_bounds__(256) bbox_final_kernel(const BBoxPart *__restr
         r.mraw = fmax(r.mraw, sh[k].mraw);
         r.nonfinite |= sh[k].nonfinite;
     }
+    /* mc = max |centred coordinate| over the cloud: attained at a face of the bounding box (x - c is monotone in x,
+     * and so is its rounding), hence computable here without another pass */
+    double mc = 0;
     for (int c = 0; c < 3; ++c) {
-        const double ctr = 0.5 * (r.mn[c] + r.mx[c]);
-        meta->center[c] = isfinite(ctr) ? ctr : 0.0;
+        const double ctr0 = 0.5 * (r.mn[c] + r.mx[c]);
+        const double ctr = isfinite(ctr0) ? ctr0 : 0.0;
+        meta->center[c] = ctr;
+        mc = fmax(mc, fmax(fabs(r.mn[c] - ctr), fabs(r.mx[c] - ctr)));
     }
     meta->mraw = r.mraw;
     meta->nonfinite = r.nonfinite;
-    meta->mc = 0;
+    meta->mc = isfinite(mc) ? mc : 0.0;
 }
 
-/* pts32[i] = {x-cx, y-cy, z-cz, |p-c|^2}; per-block max |centred coordinate| */
+/* pts32[i] = {x-cx, y-cy, z-cz, |p-c|^2} */
 __global__ void __launch_bounds__(256) convert_kernel(const double *__restrict__ xyz, uint32_t n,
                                                       const CloudMeta *__restrict__ meta,
-                                                      float4 *__restrict__ pts32,
-                                                      double *__restrict__ part) {
+                                                      float4 *__restrict__ pts32) {
     const double cx = meta->center[0], cy = meta->center[1], cz = meta->center[2];
-    double mc = 0;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const double x = xyz[3 * (size_t)i] - cx, y = xyz[3 * (size_t)i + 1] - cy,
                      z = xyz[3 * (size_t)i + 2] - cz;
-        mc = fmax(mc, fmax(fabs(x), fmax(fabs(y), fabs(z))));
         pts32[i] = make_float4((float)x, (float)y, (float)z, (float)(x * x + y * y + z * z));
-    }
-    __shared__ double sh[8];
-    mc = warp_max(mc);
-    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = mc;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        for (int k = 1; k < 8; ++k) mc = fmax(mc, sh[k]);
-        part[blockIdx.x] = mc;
-    }
-}
-__global__ void __launch_bounds__(256) convert_final_kernel(const double *__restrict__ part, int nparts, CloudMeta *meta) {
-    double mc = 0;
-    for (int k = threadIdx.x; k < nparts; k += blockDim.x) mc = fmax(mc, part[k]);
-    __shared__ double sh[8];
-    mc = warp_max(mc);
-    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = mc;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        for (int k = 1; k < 8; ++k) mc = fmax(mc, sh[k]);
-        meta->mc = mc;
     }
 }
 

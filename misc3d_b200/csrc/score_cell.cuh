@@ -38,7 +38,7 @@ __device__ unsigned long long g_cell_stats[8];
 template <int THREADS>
 struct CellCfg {
     static constexpr int kStages = THREADS >= 384 ? 3 : 2;     /* TMA ring depth                              */
-    static constexpr int kMinBlocks = THREADS >= 384 ? 1 : (THREADS >= 256 ? 2 : 4);
+    static constexpr int kMinBlocks = THREADS >= 384 ? 1 : (THREADS >= 192 ? 2 : 4);
 };
 
 template <int KIND, int THREADS, int NH>
@@ -91,7 +91,9 @@ __device__ __forceinline__ void load_fast_cull(const float4 *hyp, uint32_t h, Fa
     }
 }
 
-template <int KIND, int THREADS, int NH, bool STATS>
+/* PRE = the minimal models were solved beforehand (ScoreArgs::models_in; the host-buffer fit whose upload is still in
+ * flight): a separate instantiation, so that the branch does not perturb the register allocation of the common one */
+template <int KIND, int THREADS, int NH, bool STATS, bool PRE = false>
 __global__ void __launch_bounds__(THREADS + 32, CellCfg<THREADS>::kMinBlocks) score_cell_kernel(const ScoreArgs a) {
     constexpr int HPT = (NH + THREADS - 1) / THREADS; /* hypotheses a consumer thread prepares in the prologue */
     constexpr int NC = KIND == kCylinder ? 8 : 4;
@@ -171,7 +173,7 @@ __global__ void __launch_bounds__(THREADS + 32, CellCfg<THREADS>::kMinBlocks) sc
                     const uint32_t prov = e.y >> 31, pt = a.perm[e.y & 0x7fffffffu];
                     double m[8];
                     bool ok;
-                    if (a.models_in) {
+                    if (PRE) {
                         const uint32_t sr = a.src_row(e.x);
                         ok = a.valid_in[sr] != 0;
                         for (int i = 0; i < 8; ++i) m[i] = a.models_in[(size_t)sr * 8 + i];
@@ -201,7 +203,7 @@ __global__ void __launch_bounds__(THREADS + 32, CellCfg<THREADS>::kMinBlocks) sc
         double m[8];
         bool ok = false;
         if (row[h] < a.rows) {
-            if (a.models_in) { /* chunked launch: the model was solved before the upload finished */
+            if (PRE) {
                 const uint32_t sr = a.src_row(row[h]);
                 ok = a.valid_in[sr] != 0;
 #pragma unroll

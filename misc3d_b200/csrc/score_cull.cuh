@@ -33,8 +33,15 @@ constexpr int kStageF4 = kBlobF4 + kCellPts;    /* + one all-NaN dummy cell per 
 #define M3D_CULL_STAGES 4
 #endif
 constexpr int kCullStages = M3D_CULL_STAGES; /* ring depth: slack between the fastest and the slowest warp of a CTA */
-constexpr int kGridBits = 7;                 /* Morton grid 128^3                                    */
+constexpr int kGridBits = 7;                 /* finest Morton grid: 128^3 (clouds of >= ~1M points)   */
 constexpr uint32_t kBins = 1u << (3 * kGridBits);
+/* grid resolution for n points: about one bin per point, 32^3 .. 128^3 (the cost of the counting sort's scans is
+ * proportional to the number of bins, which matters when a cloud is sorted chunk by chunk) */
+inline int morton_bits(uint32_t n) {
+    int b = 5;
+    while (b < kGridBits && (1ull << (3 * b)) < (unsigned long long)n) ++b;
+    return b;
+}
 constexpr int kScanBlock = 1024, kScanItems = 2; /* scan: 2048 bins per block                        */
 
 __device__ __forceinline__ uint32_t part1by2(uint32_t x) { /* 7 bits -> every third bit */
@@ -48,11 +55,11 @@ __device__ __forceinline__ uint32_t part1by2(uint32_t x) { /* 7 bits -> every th
 
 /* key = Morton code of the point's grid cell inside the cube [-mc, mc]^3 around the bbox centre */
 __global__ void __launch_bounds__(256) morton_hist_kernel(const float4 *__restrict__ pts32, uint32_t n,
-                                                          const CloudMeta *__restrict__ meta,
+                                                          const CloudMeta *__restrict__ meta, int bits,
                                                           uint32_t *__restrict__ keys, uint32_t *__restrict__ hist) {
     const float mc = (float)meta->mc;
-    const float scale = mc > 0.f ? (float)(1 << (kGridBits - 1)) / mc : 0.f;
-    const int gmax = (1 << kGridBits) - 1;
+    const float scale = mc > 0.f ? (float)(1 << (bits - 1)) / mc : 0.f;
+    const int gmax = (1 << bits) - 1;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const float4 p = pts32[i];
         const int gx = min(gmax, max(0, (int)((p.x + mc) * scale)));

@@ -555,10 +555,12 @@ def test_chunked_pinned_fit_parity(ctx, capi, orc, kind):
     keepn, pnrm = _pinned(nrm) if nrm is not None else (None, None)
     for seed, H in ((3, 700), (4, 1500)):
         before = ctx.launches
-        rc, model, inl, st = ctx.ransac_fit(kind, pxyz, pnrm, 0.01, H, 1.0, seed=seed)
+        rc, model, inl, st = ctx.ransac_fit(kind, pxyz, pnrm, 0.01, H, 1.0, seed=seed, flags=capi.FLAG_CHUNKED_UPLOAD)
         n_launch = ctx.launches - before
-        rc2, model2, inl2, st2 = ctx.ransac_fit(kind, xyz, nrm, 0.01, H, 1.0, seed=seed)      # pageable: plain path
+        rc2, model2, inl2, st2 = ctx.ransac_fit(kind, xyz, nrm, 0.01, H, 1.0, seed=seed, flags=capi.FLAG_PLAIN_UPLOAD)
         assert n_launch > ctx.launches - before - n_launch                                     # chunk pipelines ran
+        rc3, model3, inl3, st3 = ctx.ransac_fit(kind, pxyz, pnrm, 0.01, H, 1.0, seed=seed)     # default: one chunk
+        assert rc == rc3 and np.array_equal(inl, inl3) and np.array_equal(model, model3) and st3["best_index"] == st["best_index"]
         assert rc == rc2 and np.array_equal(inl, inl2) and np.array_equal(model, model2)
         orc_rc, omodel, oinl, ost = orc.ransac_fit(kind, xyz, nrm, thr=0.01, max_it=H, prob=1.0, seed=seed)
         assert rc == orc_rc and np.array_equal(inl, oinl)
@@ -571,6 +573,7 @@ def test_chunked_pinned_fit_falls_back_on_nonfinite_points(ctx, capi, orc):
     xyz[123456, 1] = np.nan
     xyz[7] = np.inf
     keep, pxyz = _pinned(xyz)
-    rc, model, inl, st = ctx.ransac_fit(capi.PLANE, pxyz, None, 0.01, 300, 1.0, seed=2)
     orc_rc, omodel, oinl, ost = orc.ransac_fit(orc.PLANE, xyz, thr=0.01, max_it=300, prob=1.0, seed=2)
-    assert rc == orc_rc and np.array_equal(inl, oinl) and st["best_index"] == ost["best_index"]
+    for flags in (0, capi.FLAG_CHUNKED_UPLOAD):
+        rc, model, inl, st = ctx.ransac_fit(capi.PLANE, pxyz, None, 0.01, 300, 1.0, seed=2, flags=flags)
+        assert rc == orc_rc and np.array_equal(inl, oinl) and st["best_index"] == ost["best_index"]
