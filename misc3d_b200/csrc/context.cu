@@ -7,9 +7,13 @@
 #include <dlfcn.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
+#include <condition_variable>
 #include <limits>
+#include <mutex>
 #include <random>
+#include <thread>
 #include <vector>
 
 #include "scan.h"
@@ -93,6 +97,107 @@ int exchange_allgather(m3d_ctx *ctx, const void *d_send, void *d_recv, size_t by
     return ctx->fail(M3D_ERR_NCCL, "world size %d but no exchange configured", ctx->world);
 }
 
+}  // namespace m3d
+
+/* ---------------------------------------------------------------- staged upload of pageable buffers */
+struct CopyPool {
+    static constexpr size_t kPiece = 2u << 20;
+    std::vector<std::thread> workers;
+    std::mutex mu;
+    std::condition_variable cv;
+    bool stop = false;
+    uint64_t job_id = 0; /* bumped per job */
+    const char *src = nullptr;
+    char *dst = nullptr;
+    size_t bytes = 0, pieces = 0;
+    std::atomic<size_t> next{0};
+    std::atomic<int> active{0};
+    std::vector<std::atomic<uint8_t>> done;
+    CopyPool(int n) : done(4096) {
+        for (int i = 0; i < n; ++i) workers.emplace_back([this] { run(); });
+    }
+    ~CopyPool() {
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            stop = true;
+        }
+        cv.notify_all();
+        for (auto &t : workers) t.join();
+    }
+    bool work_one() {
+        const size_t i = next.fetch_add(1, std::memory_order_relaxed);
+        if (i >= pieces) return false;
+        const size_t off = i * kPiece, len = std::min(kPiece, bytes - off);
+        memcpy(dst + off, src + off, len);
+        done[i].store(1, std::memory_order_release);
+        return true;
+    }
+    void work() {
+        while (work_one()) {
+        }
+    }
+    void run() {
+        uint64_t seen = 0;
+        for (;;) {
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return stop || job_id != seen; });
+                if (stop) return;
+                seen = job_id;
+                active.fetch_add(1);
+            }
+            work();
+            active.fetch_sub(1);
+        }
+    }
+    void start(const void *s, void *d, size_t n) {
+        while (active.load() != 0) std::this_thread::yield(); /* stragglers of the previous job */
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            src = static_cast<const char *>(s);
+            dst = static_cast<char *>(d);
+            bytes = n;
+            pieces = (n + kPiece - 1) / kPiece;
+            for (size_t i = 0; i < pieces; ++i) done[i].store(0, std::memory_order_relaxed);
+            next.store(0);
+            ++job_id;
+        }
+        cv.notify_all();
+    }
+};
+
+namespace m3d {
+int host_to_device(m3d_ctx *ctx, void *dst, const void *src, size_t bytes, cudaStream_t stream) {
+    static const bool staged_ok = !(getenv("M3D_STAGED_UPLOAD") && atoi(getenv("M3D_STAGED_UPLOAD")) == 0);
+    bool pageable = false;
+    if (staged_ok && bytes >= (4u << 20) && bytes <= CopyPool::kPiece * 4096) {
+        cudaPointerAttributes at{};
+        if (cudaPointerGetAttributes(&at, src) != cudaSuccess) cudaGetLastError();
+        else pageable = at.type == cudaMemoryTypeUnregistered;
+    }
+    if (!pageable) {
+        M3D_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream));
+        return M3D_OK;
+    }
+    /* the previous staged upload may still be in flight on the copy engine (another stream): it must have drained before
+     * the staging buffer is overwritten */
+    M3D_CUDA(ctx, cudaStreamSynchronize(stream));
+    M3D_CUDA(ctx, ctx->h_upload.reserve(bytes));
+    if (!ctx->pool) {
+        static const int nthreads = getenv("M3D_UPLOAD_THREADS") ? std::max(1, std::min(32, atoi(getenv("M3D_UPLOAD_THREADS")))) : 1;
+        ctx->pool = new CopyPool(nthreads);
+    }
+    CopyPool &P = *ctx->pool;
+    char *stage = ctx->h_upload.as<char>();
+    P.start(src, stage, bytes);
+    for (size_t i = 0; i < P.pieces; ++i) {
+        while (!P.done[i].load(std::memory_order_acquire)) /* help staging (one piece at a time) until piece i is there */
+            if (!P.work_one()) std::this_thread::yield();
+        const size_t off = i * CopyPool::kPiece, len = std::min(CopyPool::kPiece, bytes - off);
+        M3D_CUDA(ctx, cudaMemcpyAsync(static_cast<char *>(dst) + off, stage + off, len, cudaMemcpyHostToDevice, stream));
+    }
+    return M3D_OK;
+}
 }  // namespace m3d
 
 using namespace m3d;
@@ -239,13 +344,14 @@ void m3d_ctx_destroy(m3d_ctx *c) {
                     &c->d_tmp3,    &c->d_tmp4,   &c->d_tmp5,      &c->d_queue,    &c->d_tiles, &c->d_rownrm, &c->d_rowmap, &c->d_recs, &c->d_draw,
                     &c->d_metas,   &c->d_models_all, &c->d_valid_all};
     for (auto *b : db) b->release();
-    PinBuf *pb[] = {&c->h_samples, &c->h_counts, &c->h_small, &c->h_stage, &c->h_rownrm, &c->h_metas};
+    PinBuf *pb[] = {&c->h_samples, &c->h_counts, &c->h_small, &c->h_stage, &c->h_rownrm, &c->h_metas, &c->h_upload};
     for (auto *b : pb) b->release();
     for (auto &e : c->ev)
         if (e) cudaEventDestroy(e);
     for (auto &e : c->ev_chunk)
         if (e) cudaEventDestroy(e);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    delete c->pool;
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }

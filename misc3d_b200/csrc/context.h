@@ -101,7 +101,8 @@ struct m3d_ctx {
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_chunk[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     m3d::DevBuf d_metas, d_models_all, d_valid_all;
-    m3d::PinBuf h_metas;
+    m3d::PinBuf h_metas, h_upload; /* h_upload: pinned staging of pageable uploads */
+    struct CopyPool *pool = nullptr;
 
     /* sharding / exchange */
     int rank = 0, world = 1;
@@ -139,6 +140,11 @@ struct m3d_ctx {
     } while (0)
 
 namespace m3d {
+/* host -> device copy of a caller buffer on `stream`.  Pinned sources go straight to cudaMemcpyAsync; PAGEABLE ones
+ * (what numpy / Open3D callers hold) are first copied into a pinned staging buffer by a few worker threads, piece by
+ * piece, each piece handed to the copy engine as soon as it is staged -- the driver's own pageable path stages with one
+ * thread (~18 GB/s measured), this one is bound by the DMA instead. */
+int host_to_device(m3d_ctx *ctx, void *dst, const void *src, size_t bytes, cudaStream_t stream);
 /* all-gather `bytes_per_rank` bytes per rank of device memory (NCCL or the caller's callback) */
 int exchange_allgather(m3d_ctx *ctx, const void *d_send, void *d_recv, size_t bytes_per_rank);
 }  // namespace m3d

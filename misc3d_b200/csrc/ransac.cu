@@ -98,7 +98,13 @@ int cloud_fill(m3d_ctx *ctx, m3d_cloud *c, const double *xyz, const double *nrm,
     const size_t bytes = sizeof(double) * 3 * std::max<size_t>(n, 1);
     M3D_CUDA(ctx, c->xyz.reserve(bytes));
     if (nrm) M3D_CUDA(ctx, c->nrm.reserve(bytes));
-    if (n) {
+    if (n && kind == cudaMemcpyHostToDevice) {
+        if (int rc = host_to_device(ctx, c->xyz.p, xyz, sizeof(double) * 3 * n, ctx->stream)) return rc;
+        if (nrm) {
+            M3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); /* one staging buffer: the first upload has to drain */
+            if (int rc = host_to_device(ctx, c->nrm.p, nrm, sizeof(double) * 3 * n, ctx->stream)) return rc;
+        }
+    } else if (n) {
         M3D_CUDA(ctx, cudaMemcpyAsync(c->xyz.p, xyz, sizeof(double) * 3 * n, kind, ctx->stream));
         if (nrm) M3D_CUDA(ctx, cudaMemcpyAsync(c->nrm.p, nrm, sizeof(double) * 3 * n, kind, ctx->stream));
     }
@@ -490,8 +496,7 @@ struct ChunkPlan {
         for (int i = 0; i < count; ++i) {
             const size_t b = begin[i], cnt = begin[i + 1] - begin[i];
             if (cnt)
-                M3D_CUDA(ctx, cudaMemcpyAsync(d_xyz + 3 * b, h_xyz + 3 * b, sizeof(double) * 3 * cnt, cudaMemcpyHostToDevice,
-                                              ctx->copy_stream));
+                if (int rc = host_to_device(ctx, d_xyz + 3 * b, h_xyz + 3 * b, sizeof(double) * 3 * cnt, ctx->copy_stream)) return rc;
             M3D_CUDA(ctx, cudaEventRecord(ctx->ev_chunk[i], ctx->copy_stream));
         }
         return M3D_OK;
