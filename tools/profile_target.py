@@ -29,7 +29,8 @@ elif what == "stats":  # work counters of the scoring kernel (statistics build, 
         print(kind, st["score_ms"], json.dumps(s))
 else:
     d = synth.make_c4()
-    i0, i1, ms = ctx.match_correspondence(d["src_feat"], d["dst_feat"])
-    print("match", ms, len(i0))
+    for rep in range(3):
+        i0, i1, ms = ctx.match_correspondence(d["src_feat"], d["dst_feat"])
+        print("match", rep, ms, len(i0))
     rc, T, st = ctx.ransac_registration(d["src"], d["dst"], i0, i1, 0.02, 50000, 0.9, 1.0, 1)
     print("reg", st)
