@@ -42,44 +42,66 @@ __device__ __forceinline__ uint32_t mt_reduce(uint32_t x, uint32_t size, uint64_
     return size <= 1 ? 0u : (uint32_t)__umul64hi(magic * (uint64_t)x, (uint64_t)size);
 }
 
-/* One CTA.  The recurrence mt[i+624] = f(mt[i], mt[i+1], mt[i+397]) is sequential over blocks of 624
- * words but 227-wide inside a block: three phases per block ([0,227) reads only the old state,
- * [227,454) and [454,624) read what the phase before wrote), double-buffered so that no phase overwrites
- * a word another thread still reads.  Every word is tempered, reduced modulo the cloud size and stored
- * by the thread that produced it: out[b*624 + i] = the (b*624+i)-th value of `rng() % size`. */
+/* One CTA, ONE barrier per block of 624 words.  The recurrence x[n+624] = f(x[n], x[n+1], x[n+397]) is sequential
+ * over blocks but 227-wide inside one: thread t owns elements t, 227+t and 454+t of every block.  The "far" operand
+ * of element 227+t is element t of the same block and that of 454+t is element 227+t -- both produced by the SAME
+ * thread one step earlier, so they stay in registers; only the neighbour operand x[n+1] (and the far operand of the
+ * first 227 elements) comes from other threads, out of the previous block, through a double-buffered copy of the state
+ * in shared memory.  The one element that needs a value of its own block from another thread -- 623 = f(.., new[0],
+ * new[396]) -- is deferred to the next iteration, where every thread recomputes it from three broadcast loads.
+ * Every word is tempered, reduced modulo the cloud size and stored by the thread that produced it:
+ * out[b*624 + i] = the (b*624+i)-th value of `rng() % size`.  (The first version used three barriers per block and
+ * took ~0.45 us per block: 0.18 ms for the 80k-row table of an 8-GPU fit, on every rank.) */
 __global__ void __launch_bounds__(256) mt_stream_kernel(const MtInit init, uint32_t size, uint64_t magic,
                                                         uint32_t nblocks, uint32_t *__restrict__ out) {
     __shared__ uint32_t st[2][624];
-    const int tid = threadIdx.x;
-    for (int i = tid; i < 624; i += 256) st[0][i] = init.mt[i];
+    __shared__ uint32_t s623[2];
+    const int t = threadIdx.x;
+    const bool live = t < 227; /* threads 227..255 only keep the barriers whole */
+    /* registers: this thread's elements of the previous block */
+    uint32_t a = 0, b = 0, c = 0;
+    if (live) {
+        a = init.mt[t], b = init.mt[227 + t], c = t < 170 ? init.mt[454 + t] : 0u;
+        st[0][t] = a;
+        st[0][227 + t] = b;
+        if (t < 170) st[0][454 + t] = c;
+    }
     __syncthreads();
-    int cur = 0;
-    for (uint32_t b = 0; b < nblocks; ++b) {
-        const uint32_t *c = st[cur];
-        uint32_t *nx = st[cur ^ 1];
-        uint32_t *o = out + (size_t)b * 624;
-        if (tid < 227) {
-            const int i = tid;
-            const uint32_t v = mt_twist(c[i], c[i + 1], c[i + 397]);
-            nx[i] = v;
-            o[i] = mt_reduce(mt_temper(v), size, magic);
+    for (uint32_t blk = 0; blk < nblocks; ++blk) {
+        const int par = blk & 1;
+        if (live) {
+            const uint32_t *s = st[par];
+            /* element 623 of the previous block (for blk == 0: of the seed state, which is complete) */
+            uint32_t e623;
+            if (blk == 0) {
+                e623 = s[623];
+            } else {
+                e623 = mt_twist(s623[par], s[0], s[396]);
+                if (t == 169) out[(size_t)(blk - 1) * 624 + 623] = mt_reduce(mt_temper(e623), size, magic);
+            }
+            if (t == 169) s623[par ^ 1] = e623; /* "old[623]" of the next iteration */
+            uint32_t *o = out + (size_t)blk * 624;
+            const uint32_t nA = mt_twist(a, s[t + 1], t == 226 ? e623 : s[t + 397]);
+            o[t] = mt_reduce(mt_temper(nA), size, magic);
+            const uint32_t nB = mt_twist(b, s[228 + t], nA);
+            o[227 + t] = mt_reduce(mt_temper(nB), size, magic);
+            uint32_t nC = 0;
+            if (t < 169) {
+                nC = mt_twist(c, t == 168 ? e623 : s[455 + t], nB);
+                o[454 + t] = mt_reduce(mt_temper(nC), size, magic);
+            }
+            uint32_t *w = st[par ^ 1];
+            w[t] = nA;
+            w[227 + t] = nB;
+            if (t < 169) w[454 + t] = nC;
+            a = nA, b = nB, c = nC;
         }
         __syncthreads();
-        if (tid < 227) {
-            const int i = 227 + tid;
-            const uint32_t v = mt_twist(c[i], c[i + 1], nx[i - 227]);
-            nx[i] = v;
-            o[i] = mt_reduce(mt_temper(v), size, magic);
-        }
-        __syncthreads();
-        if (tid < 170) {
-            const int i = 454 + tid;
-            const uint32_t v = mt_twist(c[i], i == 623 ? nx[0] : c[i + 1], nx[i - 227]);
-            nx[i] = v;
-            o[i] = mt_reduce(mt_temper(v), size, magic);
-        }
-        __syncthreads();
-        cur ^= 1;
+    }
+    if (nblocks && t == 169) { /* the deferred last element */
+        const int par = nblocks & 1;
+        const uint32_t e623 = mt_twist(s623[par], st[par][0], st[par][396]);
+        out[(size_t)(nblocks - 1) * 624 + 623] = mt_reduce(mt_temper(e623), size, magic);
     }
 }
 
@@ -121,11 +143,13 @@ __global__ void __launch_bounds__(1024) row_breaks_kernel(const uint32_t *__rest
         if (threadIdx.x == 0) rb->status = 1;
         return;
     }
-    for (uint32_t i = threadIdx.x; i < kDupCap; i += blockDim.x) sl[i] = i < nd ? list[i] : 0xffffffffu;
+    uint32_t cap = 2; /* sort the next power of two >= nd entries (typically a handful) */
+    while (cap < nd) cap <<= 1;
+    for (uint32_t i = threadIdx.x; i < cap; i += blockDim.x) sl[i] = i < nd ? list[i] : 0xffffffffu;
     __syncthreads();
-    for (uint32_t size = 2; size <= kDupCap; size <<= 1) /* bitonic sort, ascending */
+    for (uint32_t size = 2; size <= cap; size <<= 1) /* bitonic sort, ascending */
         for (uint32_t stride = size >> 1; stride; stride >>= 1) {
-            for (uint32_t i = threadIdx.x; i < kDupCap / 2; i += blockDim.x) {
+            for (uint32_t i = threadIdx.x; i < cap / 2; i += blockDim.x) {
                 const uint32_t lo = 2 * i - (i & (stride - 1)), hi = lo + stride;
                 const bool up = (lo & size) == 0;
                 const uint32_t a = sl[lo], b = sl[hi];

@@ -46,7 +46,9 @@ emit(config="C1 fit_plane 50k pts / 100 it (e2e host buffers)", gpu_ms=1e3 * t, 
 xyz = synth.make_c3()
 t, (rc, planes, labels, ms) = timed(lambda: ctx.segment_plane_iterative(xyz, 0.01, 100, 0.05, seed=1))
 tc, (orc_rc, oplanes, olabels) = timed(lambda: orc.segment_plane_iterative(xyz, 0.01, 100, 0.05, seed=1, omp=True), 1)
+t32, _ = timed(lambda: ctx.segment_plane_iterative(xyz, 0.01, 100, 0.05, seed=1, labels32=True))
 emit(config="C3 segment_plane_iterative 2M pts, 6-plane scene, 100 it/round (e2e host buffers)", gpu_ms=1e3 * t,
+     gpu_ms_labels32=1e3 * t32,
      device_fit_ms=ms, planes=int(len(planes)), cpu_omp_ms=1e3 * tc, cores=cores, rc=rc,
      note="CPU = oracle OpenMP rounds (not seed-comparable: shared sampler order)")
 
