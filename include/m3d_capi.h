@@ -268,6 +268,24 @@ int m3d_ransac_registration(m3d_ctx *ctx, const double *src_xyz, size_t ns, cons
                             double threshold, int max_iter, double edge_thr, double confidence,
                             uint32_t seed, double *T_out, m3d_reg_stats *stats);
 
+/* ---------------------------------------------- the Open3D steps around the path (f3, f4) */
+/* open3d::pipelines::registration::ComputeFPFHFeature(cloud, KDTreeSearchParamHybrid(radius, max_nn)) -- what the
+ * reference's callers run on the host to get the descriptors match_correspondence consumes
+ * (examples/cpp/transform_estimation.cpp:20-33, examples/python/transform_estimation.py:12-27).
+ *   xyz, nrm: n x 3 float64 host (normals are required: M3D_ERR_NO_NORMALS); feat_out: 33 x n float64 column-major
+ *   (Feature::data_), directly usable as m3d_match_correspondence input.  1 <= max_nn <= 128.
+ * Neighbour sets are exact (uniform grid in HBM, ascending (squared distance, index)); arithmetic fp64. */
+int m3d_compute_fpfh(m3d_ctx *ctx, const double *xyz, const double *nrm, size_t n, double radius, int max_nn,
+                     double *feat_out, float *device_ms);
+/* open3d::pipelines::registration::RegistrationICP(src, dst, max_distance, init,
+ * TransformationEstimationPointToPoint(false), ICPConvergenceCriteria(relative_fitness, relative_rmse, max_iteration))
+ * -- the refinement the reference's callers run after compute_transformation_ransac
+ * (examples/cpp/transform_estimation.cpp:82-86, src/pipeline.cpp:800-812).  T_init: 16 doubles row-major or NULL
+ * (identity); T_out row-major; fitness = correspondences / ns, inlier_rmse = sqrt(sum d^2 / correspondences). */
+int m3d_icp_point_to_point(m3d_ctx *ctx, const double *src_xyz, size_t ns, const double *dst_xyz, size_t nd,
+                           double max_distance, const double *T_init, int max_iteration, double relative_fitness,
+                           double relative_rmse, double *T_out, double *fitness, double *inlier_rmse, int *iterations);
+
 /* Replaces LeastSquareSolver::Solve = Eigen::umeyama over all pairs
  * (src/transform_estimation.cpp:49-66).  src/dst: n x 3 float64 host.  n < 3 -> M3D_ERR_TOO_FEW_POINTS
  * (the reference throws "The number of points pair is less than 3.", transform_estimation.cpp:29-31). */

@@ -376,6 +376,39 @@ private:
     bool has_seed_ = false;
 };
 
+/* The Open3D calls that surround the path in the reference's callers (examples/cpp/transform_estimation.cpp:20-33,
+ * 82-86): not Misc3D API, offered so that descriptors and the refinement need not leave the GPU build. */
+/* open3d::pipelines::registration::ComputeFPFHFeature(cloud, KDTreeSearchParamHybrid(radius, max_nn)):
+ * 33 x n column-major descriptors (usable as FeatureMatrix{33, n, data}) */
+inline std::vector<double> ComputeFPFHFeature(const PointCloud &cloud, double radius, int max_nn = 100) {
+    if (!cloud.HasNormals() && cloud.HasPoints()) LogError("Failed because input point cloud has no normal.");
+    m3d_ctx *ctx = b200::DefaultContext();
+    std::vector<double> out(33 * cloud.points_.size());
+    const size_t n = cloud.points_.size();
+    if (n == 0) return out;
+    if (m3d_compute_fpfh(ctx, cloud.points_[0].data(), cloud.normals_[0].data(), n, radius, max_nn, out.data(), nullptr) != M3D_OK)
+        b200::Raise(ctx);
+    return out;
+}
+struct ICPResult {
+    Matrix4d transformation_{};
+    double fitness_ = 0, inlier_rmse_ = 0;
+    int iterations_ = 0;
+};
+/* open3d::pipelines::registration::RegistrationICP, TransformationEstimationPointToPoint(false) */
+inline ICPResult RegistrationICP(const PointCloud &source, const PointCloud &target, double max_correspondence_distance,
+                                 const Matrix4d &init = Matrix4d{1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1},
+                                 int max_iteration = 30, double relative_fitness = 1e-6, double relative_rmse = 1e-6) {
+    m3d_ctx *ctx = b200::DefaultContext();
+    ICPResult r;
+    const int rc = m3d_icp_point_to_point(ctx, source.points_.empty() ? nullptr : source.points_[0].data(), source.points_.size(),
+                                          target.points_.empty() ? nullptr : target.points_[0].data(), target.points_.size(),
+                                          max_correspondence_distance, init.data(), max_iteration, relative_fitness,
+                                          relative_rmse, r.transformation_.data(), &r.fitness_, &r.inlier_rmse_, &r.iterations_);
+    if (rc != M3D_OK) b200::Raise(ctx);
+    return r;
+}
+
 class LeastSquareSolver { /* transform_estimation.cpp:49-66 */
 public:
     explicit LeastSquareSolver(bool scaling = false) : scaling_(scaling) {}

@@ -33,6 +33,7 @@ EXPORTS = [
     "m3d_ordered_scan", "m3d_segment_plane_iterative", "m3d_match_correspondence", "m3d_nearest",
     "m3d_ransac_registration", "m3d_least_squares_transform", "m3d_shard_rows", "m3d_sample_table_device", "m3d_score_stats",
     "m3d_knn_create", "m3d_knn_free", "m3d_knn_search", "m3d_segment_plane_iterative_u32",
+    "m3d_compute_fpfh", "m3d_icp_point_to_point",
 ]
 
 
@@ -419,6 +420,31 @@ class Context:
         finally:
             lib().m3d_knn_free(h)
         return idx[:nq, :k], dist[:nq, :k], cnt[:nq]
+
+    def compute_fpfh(self, xyz, normals, radius, max_nn=100):
+        """Open3D ComputeFPFHFeature (m3d_compute_fpfh): (33, n) float64 F-order descriptors, device_ms"""
+        xyz = _f64(xyz).reshape(-1, 3)
+        nrm = None if normals is None else _f64(normals).reshape(-1, 3)
+        n = len(xyz)
+        out = np.zeros((max(n, 1), 33))
+        ms = C.c_float(0)
+        self._check(lib().m3d_compute_fpfh(self.h, _p(xyz), _p(nrm), C.c_size_t(n), C.c_double(radius), C.c_int(max_nn),
+                                           _p(out), C.byref(ms)))
+        return np.asfortranarray(out[:n].T), float(ms.value)
+
+    def icp_point_to_point(self, src, dst, max_distance, T_init=None, max_iteration=30, relative_fitness=1e-6,
+                           relative_rmse=1e-6):
+        """Open3D RegistrationICP, point to point (m3d_icp_point_to_point): (T, fitness, inlier_rmse, iterations)"""
+        src = _f64(src).reshape(-1, 3)
+        dst = _f64(dst).reshape(-1, 3)
+        T0 = None if T_init is None else np.ascontiguousarray(T_init, dtype=np.float64).reshape(16)
+        T = np.zeros(16)
+        fit, rmse, it = C.c_double(0), C.c_double(0), C.c_int(0)
+        self._check(lib().m3d_icp_point_to_point(self.h, _p(src), C.c_size_t(len(src)), _p(dst), C.c_size_t(len(dst)),
+                                                 C.c_double(max_distance), _p(T0), C.c_int(max_iteration),
+                                                 C.c_double(relative_fitness), C.c_double(relative_rmse), _p(T),
+                                                 C.byref(fit), C.byref(rmse), C.byref(it)))
+        return T.reshape(4, 4).copy(), float(fit.value), float(rmse.value), int(it.value)
 
     def least_squares_transform(self, src, dst, with_scaling=False):
         src = _f64(src).reshape(-1, 3)

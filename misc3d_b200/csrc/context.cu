@@ -202,6 +202,9 @@ int host_to_device(m3d_ctx *ctx, void *dst, const void *src, size_t bytes, cudaS
 
 using namespace m3d;
 
+struct m3d_feat_scratch;
+extern "C" void m3d_feat_scratch_free(m3d_feat_scratch *f);
+
 /* fp32 FFMA throughput probe: the denominator of the scoring kernel's ALU roofline
  * (MEASURED_PEAKS.json only carries HBM and bf16 tensor peaks) */
 __global__ void __launch_bounds__(256) ffma_probe_kernel(float *out, int iters, float a, float b) {
@@ -352,6 +355,7 @@ void m3d_ctx_destroy(m3d_ctx *c) {
         if (e) cudaEventDestroy(e);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     delete c->pool;
+    m3d_feat_scratch_free(c->feat);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }

@@ -103,6 +103,7 @@ struct m3d_ctx {
     m3d::DevBuf d_metas, d_models_all, d_valid_all;
     m3d::PinBuf h_metas, h_upload; /* h_upload: pinned staging of pageable uploads */
     struct CopyPool *pool = nullptr;
+    struct m3d_feat_scratch *feat = nullptr; /* device buffers of the FPFH / ICP entry points (features.cu) */
 
     /* sharding / exchange */
     int rank = 0, world = 1;

@@ -111,3 +111,25 @@ def make_c4(n=200_000, seed=SEED, dim=33, sigma=0.002, true_frac=0.3):
 
 def make_c5(n=4_000_000, seed=SEED):
     return make_c1(n=n, seed=seed)
+
+
+def make_surface_pair(n=20_000, seed=SEED, sigma=0.0):
+    """a registration pair with ANALYTIC normals for the FPFH -> match -> RANSAC -> ICP chain: points on the bumpy
+    height field z = 0.25 sin(3x) cos(2y) + 0.1 sin(7x + 5y) over [-1, 1]^2 (locally distinctive, so descriptors
+    discriminate), dst = R src[perm] + t (+ noise).  Returns dict(src, src_nrm, dst, dst_nrm, T_true, perm)."""
+    rng = np.random.default_rng(seed)
+    x, y = rng.uniform(-1, 1, n), rng.uniform(-1, 1, n)
+    z = 0.25 * np.sin(3 * x) * np.cos(2 * y) + 0.1 * np.sin(7 * x + 5 * y)
+    zx = 0.75 * np.cos(3 * x) * np.cos(2 * y) + 0.7 * np.cos(7 * x + 5 * y)
+    zy = -0.5 * np.sin(3 * x) * np.sin(2 * y) + 0.5 * np.cos(7 * x + 5 * y)
+    src = np.c_[x, y, z]
+    nrm = np.c_[-zx, -zy, np.ones(n)]
+    nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
+    R = rotation_about((1, 2, -1), 25.0)
+    t = np.array([0.3, -0.1, 0.2])
+    perm = rng.permutation(n)
+    dst = src[perm] @ R.T + t + rng.normal(0, sigma, size=(n, 3)) if sigma else src[perm] @ R.T + t
+    T = np.eye(4)
+    T[:3, :3], T[:3, 3] = R, t
+    return dict(src=np.ascontiguousarray(src), src_nrm=np.ascontiguousarray(nrm), dst=np.ascontiguousarray(dst),
+                dst_nrm=np.ascontiguousarray(nrm[perm] @ R.T), T_true=T, perm=perm)

@@ -37,7 +37,7 @@ class RegStats(C.Structure):
 
 
 def build(force=False):
-    src = [os.path.join(_HERE, f) for f in ("m3d_oracle.cpp", "m3d_oracle.h", "Makefile")]
+    src = [os.path.join(_HERE, f) for f in ("m3d_oracle.cpp", "m3d_oracle_features.cpp", "m3d_oracle.h", "Makefile")]
     if (not force and os.path.exists(_LIB)
             and all(os.path.getmtime(_LIB) >= os.path.getmtime(s) for s in src)):
         return _LIB
@@ -197,6 +197,39 @@ def ransac_registration(src, dst, c0, c1, thr=0.01, max_iter=100000, edge_thr=0.
                                        C.c_uint32(seed & 0xFFFFFFFF), int(omp), _p(T),
                                        C.byref(st))
     return rc, T.reshape(4, 4), st.as_dict()
+
+
+def fpfh(xyz, nrm, radius, max_nn):
+    """Open3D ComputeFPFHFeature(cloud, KDTreeSearchParamHybrid(radius, max_nn)) restated: (33, n) F-order array"""
+    xyz, nrm = _f64(xyz), _f64(nrm)
+    n = len(xyz)
+    out = np.zeros((n, 33))
+    rc = lib().orc_fpfh(_p(xyz), _p(nrm), C.c_size_t(n), C.c_double(radius), int(max_nn), _p(out))
+    if rc != 0:
+        raise RuntimeError("orc_fpfh: the cloud has no normals")
+    return np.asfortranarray(out.T)
+
+
+def hybrid_search_all(xyz, radius, max_nn):
+    xyz = _f64(xyz)
+    n = len(xyz)
+    idx = np.zeros((n, max_nn), dtype=np.uint32)
+    d2 = np.zeros((n, max_nn))
+    cnt = np.zeros(n, dtype=np.uint32)
+    lib().orc_hybrid_search_all(_p(xyz), C.c_size_t(n), C.c_double(radius), int(max_nn), _p(idx, C.c_uint32), _p(d2),
+                                _p(cnt, C.c_uint32))
+    return idx, d2, cnt
+
+
+def icp(src, dst, max_dist, T_init=None, max_iter=30, rel_fitness=1e-6, rel_rmse=1e-6):
+    """Open3D RegistrationICP (point to point) restated: (T, fitness, inlier_rmse, iterations)"""
+    src, dst = _f64(src), _f64(dst)
+    T0 = np.eye(4) if T_init is None else np.ascontiguousarray(T_init, dtype=np.float64)
+    T = np.zeros(16)
+    fit, rmse, it = C.c_double(0), C.c_double(0), C.c_int(0)
+    lib().orc_icp(_p(src), C.c_size_t(len(src)), _p(dst), C.c_size_t(len(dst)), C.c_double(max_dist), _p(T0), int(max_iter),
+                  C.c_double(rel_fitness), C.c_double(rel_rmse), _p(T), C.byref(fit), C.byref(rmse), C.byref(it))
+    return T.reshape(4, 4), fit.value, rmse.value, it.value
 
 
 def omp_threads():

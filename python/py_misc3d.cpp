@@ -232,6 +232,46 @@ PYBIND11_MODULE(py_misc3d, m) {
         "numpy arrays with shape (n, 3))",
         py::arg("src"), py::arg("dst"), py::arg("scaling") = false);
 
+    /* extensions (not in the reference's module): the Open3D steps its callers run around this path, on the GPU */
+    reg.def(
+        "compute_fpfh_feature",
+        [](const py::object &pcd, double radius, int max_nn) {
+            PointCloud pc = cloud_from_py(pcd);
+            std::vector<double> f;
+            {
+                py::gil_scoped_release nogil;
+                f = registration::ComputeFPFHFeature(pc, radius, max_nn);
+            }
+            py::array_t<double, py::array::f_style> a({(py::ssize_t)33, (py::ssize_t)pc.points_.size()});
+            if (!f.empty()) std::memcpy(a.mutable_data(), f.data(), sizeof(double) * f.size());
+            return a;
+        },
+        "open3d.pipelines.registration.compute_fpfh_feature(pcd, KDTreeSearchParamHybrid(radius, max_nn)) on the GPU: "
+        "(33, n) float64 array, usable as match_correspondence input",
+        py::arg("pcd"), py::arg("radius"), py::arg("max_nn") = 100);
+    reg.def(
+        "registration_icp",
+        [](const py::object &src, const py::object &dst, double max_correspondence_distance, const py::object &init,
+           int max_iteration, double relative_fitness, double relative_rmse) {
+            PointCloud s = cloud_from_py(src), d = cloud_from_py(dst);
+            Matrix4d T0{1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+            if (!init.is_none()) {
+                DArray a = DArray::ensure(init);
+                if (!a || a.size() != 16) throw py::type_error("init must be a (4, 4) float64 array");
+                std::memcpy(T0.data(), a.data(), sizeof(double) * 16);
+            }
+            registration::ICPResult r;
+            {
+                py::gil_scoped_release nogil;
+                r = registration::RegistrationICP(s, d, max_correspondence_distance, T0, max_iteration, relative_fitness,
+                                                  relative_rmse);
+            }
+            return py::make_tuple(mat4(r.transformation_), r.fitness_, r.inlier_rmse_, r.iterations_);
+        },
+        "open3d.pipelines.registration.registration_icp (point to point) on the GPU: (T, fitness, inlier_rmse, iterations)",
+        py::arg("src"), py::arg("dst"), py::arg("max_correspondence_distance"), py::arg("init") = py::none(),
+        py::arg("max_iteration") = 30, py::arg("relative_fitness") = 1e-6, py::arg("relative_rmse") = 1e-6);
+
     py::enum_<VerbosityLevel>(m, "VerbosityLevel", py::arithmetic(), "VerbosityLevel")
         .value("Error", VerbosityLevel::Error)
         .value("Warning", VerbosityLevel::Warning)
