@@ -72,6 +72,17 @@ t, (rc, T, st) = timed(lambda: ctx.ransac_registration(d["src"], d["dst"], i0, i
 emit(config="C4c compute_transformation_ransac default confidence 0.999 (early exit)", gpu_ms=1e3 * t,
      stop_index=st["stop_index"], evaluated=st["evaluated"])
 
+# the Open3D steps around C4 (f3 / f4): FPFH of both clouds and the ICP refinement, 200k points each ----------------
+dp = synth.make_surface_pair(n=200000, seed=2, sigma=0.0005)
+t, (f, ms) = timed(lambda: ctx.compute_fpfh(dp["src"], dp["src_nrm"], 0.03, 100), 2)
+emit(config="f3 compute_fpfh 200k pts, radius 0.03, max_nn 100 (e2e host buffers: 4.8 MB x2 up, 52.8 MB down)", gpu_ms=1e3 * t,
+     device_ms=ms)
+T0 = dp["T_true"].copy()
+T0[:3, 3] += 0.01
+t, (T, fit, rmse, it) = timed(lambda: ctx.icp_point_to_point(dp["src"], dp["dst"], 0.02, T0, 30), 2)
+emit(config="f4 icp_point_to_point 200k <-> 200k pts, max_distance 0.02 (e2e host buffers)", gpu_ms=1e3 * t, iterations=it,
+     fitness=fit, inlier_rmse=rmse, err_vs_truth=float(np.linalg.norm(T - dp["T_true"])))
+
 # C5 (single GPU share shown for 1 GPU: all 100k hypotheses) -------------------------------------
 xyz = synth.make_c5()
 cloud = ctx.upload(xyz)
