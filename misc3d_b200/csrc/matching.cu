@@ -490,6 +490,15 @@ static int launch_exact(m3d_ctx *ctx, const FeatDev &A, const FeatDev &B, int di
     return M3D_OK;
 }
 
+/* M3D_MATCH_TC=2 selects the two-CTA (cta_group::2) tcgen05 kernel.  It halves the L2 -> SM operand stream (ncu: 65 GB
+ * instead of 130 GB per direction) and returns identical results, but measured SLOWER than the one-CTA kernel (15.6 ms
+ * vs 13.9 ms per direction at C4): the per-tile hand-shake across the pair paces it (12.8 ms with the MMAs and the
+ * operand traffic switched off).  Kept as an experiment; default: the one-CTA kernel. */
+static bool tc_two_cta() {
+    static const bool v = getenv("M3D_MATCH_TC") && atoi(getenv("M3D_MATCH_TC")) == 2;
+    return v;
+}
+
 static int nn_direction(m3d_ctx *ctx, const FeatDev &A, const FeatDev &B, int dim, int KP, int path,
                         const uint32_t *d_maxnorm_B, uint32_t *d_nn, uint32_t *d_amb, uint32_t *d_amb_count) {
     if (path == 2) {
@@ -506,7 +515,9 @@ static int nn_direction(m3d_ctx *ctx, const FeatDev &A, const FeatDev &B, int di
         ta.amb_count = d_amb_count;
         const size_t smem = (size_t)(tc::kRB + tc::kBStages) * tc::kRows * ta.KPr * 2 + 128;
         /* scratch of the candidate refinement */
-        const uint32_t atiles = (A.ntiles + tc::kRB - 1) / tc::kRB * tc::kRB;
+        const bool two = tc_two_cta();
+        const uint32_t atiles = two ? (A.ntiles + 1) / 2 * 2 : (A.ntiles + tc::kRB - 1) / tc::kRB * tc::kRB; /* whole pairs */
+        const size_t smem2 = (size_t)tc::kRows * ta.KPr * 2 + (size_t)tc::kB2Stages * (tc::kRows / 2) * ta.KPr * 2 + 512;
         M3D_CUDA(ctx, ctx->d_models.reserve((size_t)atiles * tc::kRows * ta.KPr * 2));                 /* slot tiles */
         M3D_CUDA(ctx, ctx->d_queue.reserve(sizeof(uint32_t) * (size_t)A.count * tc::kCandCap + 64));  /* candidates */
         M3D_CUDA(ctx, ctx->d_counts.reserve(sizeof(float) * 3 * (size_t)A.count + 64));               /* cut, slot_cut, cand_count */
@@ -520,7 +531,13 @@ static int nn_direction(m3d_ctx *ctx, const FeatDev &A, const FeatDev &B, int di
         M3D_CUDA(ctx, cudaMemsetAsync(d_list2_count, 0, sizeof(uint32_t), ctx->stream));
         M3D_CUDA(ctx, cudaFuncSetAttribute(tc::nn_top2_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         M3D_CUDA(ctx, cudaFuncSetAttribute(tc::nn_top2_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        tc::nn_top2_tc_kernel<false><<<atiles / tc::kRB, 192, smem, ctx->stream>>>(ta);
+        if (two) {
+            M3D_CUDA(ctx, cudaFuncSetAttribute(tc::nn_top2_tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+            M3D_CUDA(ctx, cudaFuncSetAttribute(tc::nn_top2_tc2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+            tc::nn_top2_tc2_kernel<false><<<atiles, tc::kTc2Threads, smem2, ctx->stream>>>(ta);
+        } else {
+            tc::nn_top2_tc_kernel<false><<<atiles / tc::kRB, 192, smem, ctx->stream>>>(ta);
+        }
         M3D_LAUNCHED(ctx);
         /* rows too close to call: second GEMM pass over just those rows collecting every column within
          * the error bound of the best key, then the fp64 reference-order decision among the candidates */
@@ -535,7 +552,10 @@ static int nn_direction(m3d_ctx *ctx, const FeatDev &A, const FeatDev &B, int di
         tb.cand = ctx->d_queue.as<uint32_t>();
         tb.cand_count = d_cand_count;
         tb.col_splits = 8;
-        tc::nn_top2_tc_kernel<true><<<dim3(atiles / tc::kRB, tb.col_splits), 192, smem, ctx->stream>>>(tb);
+        if (two)
+            tc::nn_top2_tc2_kernel<true><<<dim3(atiles, tb.col_splits), tc::kTc2Threads, smem2, ctx->stream>>>(tb);
+        else
+            tc::nn_top2_tc_kernel<true><<<dim3(atiles / tc::kRB, tb.col_splits), 192, smem, ctx->stream>>>(tb);
         M3D_LAUNCHED(ctx);
         cand_exact_kernel<<<ctx->sm_count * 2, 128, 0, ctx->stream>>>(A.f64, B.f64, dim, d_amb, d_amb_count, tb.cand,
                                                                      d_cand_count, d_nn, d_list2, d_list2_count);
@@ -575,7 +595,7 @@ static int match_impl(m3d_ctx *ctx, const double *src, size_t ns, const double *
     const size_t fa = sizeof(double) * (size_t)dim * ns, fb = sizeof(double) * (size_t)dim * nd;
     const int KPr = tc::kprime(dim);
     /* tensor-core path: per set one query-form and one database-form tile array (bf16) */
-    const uint32_t at = (A.ntiles + tc::kRB - 1) / tc::kRB * tc::kRB, bt = (B.ntiles + tc::kRB - 1) / tc::kRB * tc::kRB;
+    const uint32_t at = (A.ntiles + 1) / 2 * 2, bt = (B.ntiles + 1) / 2 * 2; /* query-form arrays are padded to whole CTA pairs */
     const size_t ta = path == 2 ? (size_t)2 * at * tc::kRows * KPr * 2
                                 : (path == 1 ? sizeof(float) * (size_t)A.ntiles * (KP + 1) * kMT : 16);
     const size_t tb = path == 2 ? (size_t)2 * bt * tc::kRows * KPr * 2
@@ -618,18 +638,19 @@ static int match_impl(m3d_ctx *ctx, const double *src, size_t ns, const double *
         feat_center_kernel<<<1, 128, 0, ctx->stream>>>(sc->mn, sc->mx, dim, sc->center);
         M3D_LAUNCHED(ctx);
         if (path == 2) {
+            const int drows = tc_two_cta() ? 64 : 128; /* rows per database tile */
             tc::feat_split_kernel<<<at, tc::kRows, 0, ctx->stream>>>(A.f64, A.count, dim, KPr, sc->center, 0, A.tq,
-                                                                        A.norms, &sc->maxnorm[0]);
+                                                                        A.norms, &sc->maxnorm[0], 128);
             M3D_LAUNCHED(ctx);
             tc::feat_split_kernel<<<B.ntiles, tc::kRows, 0, ctx->stream>>>(B.f64, B.count, dim, KPr, sc->center, 1, B.td,
-                                                                        B.norms, &sc->maxnorm[1]);
+                                                                        B.norms, &sc->maxnorm[1], drows);
             M3D_LAUNCHED(ctx);
             if (both_directions) {
                 tc::feat_split_kernel<<<bt, tc::kRows, 0, ctx->stream>>>(B.f64, B.count, dim, KPr, sc->center, 0,
-                                                                            B.tq, B.norms, &sc->maxnorm[1]);
+                                                                            B.tq, B.norms, &sc->maxnorm[1], 128);
                 M3D_LAUNCHED(ctx);
                 tc::feat_split_kernel<<<A.ntiles, tc::kRows, 0, ctx->stream>>>(A.f64, A.count, dim, KPr, sc->center, 1,
-                                                                            A.td, A.norms, &sc->maxnorm[0]);
+                                                                            A.td, A.norms, &sc->maxnorm[0], drows);
                 M3D_LAUNCHED(ctx);
             }
         } else {

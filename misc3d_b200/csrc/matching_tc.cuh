@@ -29,6 +29,9 @@
 #ifndef M3D_TC_EXP
 #define M3D_TC_EXP 0
 #endif
+#ifndef M3D_TC2_EXP
+#define M3D_TC2_EXP 0
+#endif
 
 namespace m3d {
 namespace tc {
@@ -73,10 +76,10 @@ __device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t
 
 /* shared-memory matrix descriptor, K-major, no swizzle (cute::UMMA::SmemDescriptor bit layout):
  * [0,14) start>>4 | [16,30) leading byte offset>>4 | [32,46) stride byte offset>>4 | [46,48) version=1 */
-__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo_bytes = kChunkBytes) {
     uint64_t d = 0;
     d |= (uint64_t)((smem_addr >> 4) & 0x3fff);
-    d |= (uint64_t)((kChunkBytes >> 4) & 0x3fff) << 16; /* LBO: next 8-wide K chunk          */
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16;   /* LBO: next 8-wide K chunk (rows of the tile x 16 B) */
     d |= (uint64_t)((128 >> 4) & 0x3fff) << 32;         /* SBO: next group of 8 rows         */
     d |= (uint64_t)1 << 46;                             /* descriptor version (Blackwell)    */
     return d;
@@ -126,11 +129,14 @@ __global__ void __launch_bounds__(128) feat_split_kernel(const double *__restric
                                                          int KPr, const double *__restrict__ center, int role,
                                                          __nv_bfloat16 *__restrict__ tiles,
                                                          float *__restrict__ norms,
-                                                         uint32_t *__restrict__ maxnorm_bits) {
-    const uint32_t tile = blockIdx.x, r = threadIdx.x;
-    const uint32_t j = tile * kRows + r;
-    __nv_bfloat16 *t = tiles + (size_t)tile * kRows * KPr;
-    auto put = [&](int kk, float v) { t[(size_t)(kk >> 3) * (kChunkBytes / 2) + r * 8 + (kk & 7)] = __float2bfloat16_rn(v); };
+                                                         uint32_t *__restrict__ maxnorm_bits, int tile_rows) {
+    /* tile_rows = rows per tile of the output layout: 128, or 64 for the database form of the two-CTA kernel (each CTA
+     * of a pair holds half of a 128-column database tile) */
+    const uint32_t j = blockIdx.x * kRows + threadIdx.x;
+    const uint32_t tile = j / (uint32_t)tile_rows, r = j % (uint32_t)tile_rows;
+    __nv_bfloat16 *t = tiles + (size_t)tile * tile_rows * KPr;
+    const size_t chunk = (size_t)tile_rows * 8; /* elements per 8-wide K chunk of a tile */
+    auto put = [&](int kk, float v) { t[(size_t)(kk >> 3) * chunk + r * 8 + (kk & 7)] = __float2bfloat16_rn(v); };
     const float sc = role ? -2.f : 1.f;
     double n2 = 0;
     if (j < count) {
@@ -199,11 +205,12 @@ struct TcArgs {
 constexpr int kCandCap = 32;
 
 /* one tile of the top-2 scan: 128 fp32 keys of this thread's row (4 x 32 TMEM columns) */
-__device__ __forceinline__ void scan_tile(const float (&v)[4][32], uint32_t jbase, uint32_t ncol, float &m1, float &m2,
-                                          uint32_t &i1) {
+template <int G>
+__device__ __forceinline__ void scan_tile(const float (&v)[G][32], uint32_t jbase, uint32_t ncol, float &m1, float &m2,
+                                          uint32_t &i1, uint32_t col0 = 0) {
 #pragma unroll
-    for (int g = 0; g < 4; ++g) {
-        const uint32_t c0 = 32u * g;
+    for (int g = 0; g < G; ++g) {
+        const uint32_t c0 = col0 + 32u * g;
         /* cheap screen: min of the 32 values (FMNMX3 tree); the running (best, second best) changes
          * O(log n) times per row, so the update below is the rare path */
         float lo = fminf(fminf(v[g][0], v[g][1]), v[g][2]);
@@ -228,11 +235,12 @@ __device__ __forceinline__ void scan_tile(const float (&v)[4][32], uint32_t jbas
 }
 
 /* candidate pass: every column whose key is within the cut-off of this row */
-__device__ __forceinline__ void collect_tile(const float (&v)[4][32], uint32_t jbase, uint32_t ncol, float cut,
-                                             uint32_t *cand, uint32_t *cand_count) {
+template <int G>
+__device__ __forceinline__ void collect_tile(const float (&v)[G][32], uint32_t jbase, uint32_t ncol, float cut,
+                                             uint32_t *cand, uint32_t *cand_count, uint32_t col0 = 0) {
 #pragma unroll
-    for (int g = 0; g < 4; ++g) {
-        const uint32_t c0 = 32u * g;
+    for (int g = 0; g < G; ++g) {
+        const uint32_t c0 = col0 + 32u * g;
         float lo = fminf(fminf(v[g][0], v[g][1]), v[g][2]);
 #pragma unroll
         for (int i = 3; i + 1 < 32; i += 2) lo = fminf(fminf(lo, v[g][i]), v[g][i + 1]);
@@ -369,10 +377,10 @@ __global__ void __launch_bounds__(192, 1) nn_top2_tc_kernel(const TcArgs a) {
                 }
                 if (CAND) {
                     const uint32_t slot = (blockIdx.x * kRB + rb) * kRows + q * 32 + lane;
-                    if (slot < nslots) collect_tile(v, jbase, ncol, cutv[rb], a.cand + (size_t)slot * kCandCap,
+                    if (slot < nslots) collect_tile<4>(v, jbase, ncol, cutv[rb], a.cand + (size_t)slot * kCandCap,
                                                     a.cand_count + slot);
                 } else {
-                    scan_tile(v, jbase, ncol, m1[rb], m2[rb], i1[rb]);
+                    scan_tile<4>(v, jbase, ncol, m1[rb], m2[rb], i1[rb]);
                 }
             }
         }
@@ -397,6 +405,233 @@ __global__ void __launch_bounds__(192, 1) nn_top2_tc_kernel(const TcArgs a) {
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    }
+}
+
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * The two-CTA form (tcgen05 cta_group::2): a CLUSTER OF TWO CTAs (one SM pair) computes a 256 x 128 block of keys per
+ * database tile.  Each CTA keeps its own 128 query rows (A) and loads only HALF of every database tile -- 64 of the 128
+ * columns (B) -- and the pair's tensor cores read both halves: the L2 -> SM operand stream per SM is halved, which is
+ * what bounded the one-CTA kernel (53 KB per 128 x 128 tile, ~9.3 TB/s chip-wide, tensor pipe 56 %).
+ *   both CTAs   warp 0: TMA producer of the CTA's A tile and B halves (6-stage ring); warps 2-5: epilogue on the CTA's
+ *               own accumulator (its 128 rows x 128 columns in its own TMEM)
+ *   leader      warp 1: single-thread tcgen05.mma.cta_group::2 issuer (M 256 x N 128 x K 16); tcgen05.commit multicast
+ *               to both CTAs frees the ring slot / publishes the accumulator in both
+ *   peer        warp 1: relay -- forwards "my half has landed" to the leader's barriers (remote mbarrier arrive)
+ * The peer's epilogue warps release the accumulator buffer on the LEADER's barrier (the leader issues the MMAs that
+ * overwrite it).  Database tiles are stored as 64-row tiles (feat_split_kernel, tile_rows = 64). */
+constexpr int kB2Stages = 6;
+constexpr int kTc2Threads = 320; /* producer warp, MMA / relay warp, 8 epilogue warps */
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+/* arrive on the mbarrier at this CTA-local address in CTA `rank` of the cluster */
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t *bar, uint32_t rank) {
+    uint32_t remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(rank));
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t *bar, uint32_t parity) { /* acquire at cluster scope */
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT_C:\n"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE_C;\n"
+        "bra LAB_WAIT_C;\n"
+        "DONE_C:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void umma2_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma2_commit(uint64_t *bar, uint16_t cta_mask) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                     smem_u32(bar)),
+                 "h"(cta_mask)
+                 : "memory");
+}
+
+template <bool CAND>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTc2Threads, 1) nn_top2_tc2_kernel(const TcArgs a) {
+    /* fewer ambiguous rows than the grid was sized for: decided per pair (a CTA that left could not be waited for) */
+    if (CAND && (blockIdx.x / 2) * 2 * kRows >= *a.slot_count) return;
+    constexpr int kAcc = 4; /* accumulator buffers: all 512 TMEM columns */
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const uint32_t crank = cluster_ctarank(); /* 0 = leader */
+    const uint32_t tile_bytes = (uint32_t)kRows * a.KPr * 2;
+    const uint32_t half_bytes = tile_bytes / 2; /* 64 database rows */
+    unsigned char *As = smem_raw;
+    unsigned char *Bs = smem_raw + tile_bytes;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + tile_bytes + (size_t)kB2Stages * half_bytes);
+    uint64_t *a_full = bars, *peer_a = bars + 1, *b_full = bars + 2, *peer_b = b_full + kB2Stages,
+             *b_empty = peer_b + kB2Stages, *t_full = b_empty + kB2Stages, *t_empty = t_full + kAcc;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(t_empty + kAcc);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t ntb_all = (a.nb + kRows - 1) / kRows;
+    const uint32_t per = CAND ? (ntb_all + a.col_splits - 1) / a.col_splits : ntb_all;
+    const uint32_t tb0 = CAND ? min(ntb_all, blockIdx.y * per) : 0u;
+    const uint32_t ntb = min(ntb_all, tb0 + per) - tb0;
+    const int nk = a.KPr / 16;
+    /* FOUR accumulator buffers: the release of a buffer crosses the pair (the peer's epilogue arrives on the leader's
+     * barrier), and with two buffers that round trip sat on the MMA issuer's critical path */
+
+    if (tid == 0) {
+        mbar_init(a_full, 1);
+        mbar_init(peer_a, 1);
+        for (int s = 0; s < kB2Stages; ++s) {
+            mbar_init(&b_full[s], 1);
+            mbar_init(&peer_b[s], 1);
+            mbar_init(&b_empty[s], 1); /* one multicast commit of the leader per use */
+        }
+        for (int s = 0; s < kAcc; ++s) {
+            mbar_init(&t_full[s], 1);
+            mbar_init(&t_empty[s], 16); /* 8 epilogue warps of each CTA (used in the leader only) */
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kAcc * 128)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all(); /* both CTAs' barriers and accumulators exist before anybody signals across */
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) { /* ---------------- TMA producer: own query rows, own half of every database tile */
+            tma_load_1d(As, a.Aq + (size_t)blockIdx.x * kRows * a.KPr, tile_bytes, a_full);
+            for (uint32_t t = 0; t < ntb; ++t) {
+                const int st = t % kB2Stages;
+                mbar_wait(&b_empty[st], ((t / kB2Stages) & 1) ^ 1);
+#if M3D_TC2_EXP == 2 /* timing experiment (wrong results): 512 bytes per stage instead of a half tile */
+                tma_load_1d(Bs + (size_t)st * half_bytes, reinterpret_cast<const unsigned char *>(a.Bd), 512, &b_full[st]);
+#else
+                tma_load_1d(Bs + (size_t)st * half_bytes,
+                            reinterpret_cast<const unsigned char *>(a.Bd) + ((size_t)(tb0 + t) * 2 + crank) * half_bytes,
+                            half_bytes, &b_full[st]);
+#endif
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && crank == 0) { /* ---------------- MMA issuer (leader) */
+            const uint32_t idesc = umma_idesc(256, 128);
+            mbar_wait(a_full, 0);
+            mbar_wait(peer_a, 0);
+            for (uint32_t t = 0; t < ntb; ++t) {
+                const int st = t % kB2Stages, buf = t % kAcc;
+                mbar_wait(&b_full[st], (t / kB2Stages) & 1);
+                mbar_wait(&peer_b[st], (t / kB2Stages) & 1);
+                mbar_wait(&t_empty[buf], ((t / kAcc) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t b0 = smem_u32(Bs + (size_t)st * half_bytes);
+                const uint32_t a0 = smem_u32(As);
+                const uint32_t d0 = tmem_base + (uint32_t)buf * 128u;
+#if M3D_TC2_EXP == 3 /* timing experiment (wrong results): one MMA per tile */
+                for (int ks = 0; ks < 1; ++ks)
+#else
+                for (int ks = 0; ks < nk; ++ks)
+#endif
+                    umma2_bf16(d0, umma_desc(a0 + ks * 2 * kChunkBytes, kChunkBytes),
+                               umma_desc(b0 + ks * 2 * (kChunkBytes / 2), kChunkBytes / 2), idesc, ks > 0 ? 1u : 0u);
+                umma2_commit(&b_empty[st], 0x3); /* the slot is free in BOTH CTAs once these MMAs have read it */
+                umma2_commit(&t_full[buf], 0x3); /* both CTAs' accumulators are ready                          */
+            }
+        } else if (lane == 0) { /* ---------------- relay (peer): tell the leader when my operands have landed */
+            mbar_wait(a_full, 0);
+            mbar_arrive_remote(peer_a, 0);
+            for (uint32_t t = 0; t < ntb; ++t) {
+                const int st = t % kB2Stages;
+                mbar_wait(&b_full[st], (t / kB2Stages) & 1);
+                mbar_arrive_remote(&peer_b[st], 0);
+            }
+        }
+    } else { /* ---------------- epilogue warps 2..9: TMEM lane quarter = warp % 4 (a warp can only read its quarter),
+              * column half = (warp - 2) / 4: two warps share a quarter and scan 64 of the 128 columns each.  (With four
+              * warps the scan of 128 keys per row and tile paced the whole kernel: 12.8 ms with the MMAs and the
+              * operand traffic switched off.) */
+        const uint32_t q = (uint32_t)warp & 3u, half = (uint32_t)(warp - 2) >> 2;
+        float m1 = INFINITY, m2 = INFINITY, cutv = -INFINITY;
+        uint32_t i1 = 0;
+        const uint32_t nslots = CAND ? *a.slot_count : 0u;
+        const uint32_t my = blockIdx.x * kRows + q * 32 + lane; /* row (or slot) of this thread */
+        if (CAND && my < nslots) cutv = a.slot_cut[my];
+        for (uint32_t t = 0; t < ntb; ++t) {
+            const int buf = t % kAcc;
+            mbar_wait(&t_full[buf], (t / kAcc) & 1);
+            tc_fence_after();
+            const uint32_t jbase = (tb0 + t) * kRows;
+            const uint32_t ncol = min((uint32_t)kRows, a.nb - jbase);
+            float v[2][32];
+            const uint32_t tbase = tmem_base + ((q * 32u) << 16) + (uint32_t)buf * 128u + half * 64u;
+#pragma unroll
+            for (int g = 0; g < 2; ++g) tmem_ld32(tbase + 32u * g, v[g]);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) { /* the buffer is free as soon as the values sit in registers: tell the leader */
+                if (crank == 0) mbar_arrive(&t_empty[buf]);
+                else mbar_arrive_remote(&t_empty[buf], 0);
+            }
+#if M3D_TC2_EXP == 1 /* timing experiment (wrong results): no scan of the keys */
+            m1 = fminf(m1, v[0][lane & 31]);
+#else
+            if (CAND) {
+                if (my < nslots) collect_tile<2>(v, jbase, ncol, cutv, a.cand + (size_t)my * kCandCap, a.cand_count + my, half * 64u);
+            } else {
+                scan_tile<2>(v, jbase, ncol, m1, m2, i1, half * 64u);
+            }
+#endif
+        }
+        if (!CAND) { /* merge the two column halves of every row (through the idle operand ring) */
+            float4 *xch = reinterpret_cast<float4 *>(Bs);
+            __syncwarp();
+            asm volatile("bar.sync 3, 256;" ::: "memory"); /* all epilogue warps are done with the last tile: ring is idle */
+            if (half == 1) xch[q * 32 + lane] = make_float4(m1, m2, __uint_as_float(i1), 0.f);
+            asm volatile("bar.sync 3, 256;" ::: "memory");
+            if (half == 0 && my < a.na) {
+                const float4 o = xch[q * 32 + lane];
+                /* the two smallest of {m1, m2, o.x, o.y}; an exact tie of the minima leaves a gap of 0 = ambiguous */
+                if (o.x < m1) {
+                    m2 = fminf(m1, o.y);
+                    m1 = o.x;
+                    i1 = __float_as_uint(o.z);
+                } else {
+                    m2 = fminf(m2, o.x);
+                }
+                const float bnmax = __uint_as_float(*a.maxnorm_bits);
+                a.nn[my] = i1;
+                const float E = (float)(2 * a.KPr + 64) * 1.1920929e-07f * (a.a_norms[my] + bnmax);
+                a.cut[my] = m1 + 2.5f * E;
+                if (!(m2 - m1 > 2.5f * E)) a.amb_list[atomicAdd(a.amb_count, 1u)] = my;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all(); /* nobody leaves while the pair may still signal it or read its shared memory */
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kAcc * 128) : "memory");
     }
 }
 
