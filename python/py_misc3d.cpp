@@ -70,26 +70,73 @@ py::array_t<double> to_numpy(const std::vector<double> &v) {
     return a;
 }
 
-template <class Fit, class ModelT>
+/* (points, normals) of a cloud argument as float64 C-contiguous (N, 3) arrays WITHOUT a copy when the caller's arrays
+ * already have that layout (numpy arrays; Open3D's Vector3dVector converts through numpy.asarray) */
+std::pair<DArray, DArray> cloud_arrays(const py::object &o, bool want_normals) {
+    py::object np = py::module_::import("numpy");
+    py::object pts, nrm = py::none();
+    if (py::hasattr(o, "points")) {
+        pts = np.attr("asarray")(o.attr("points"));
+        if (want_normals && py::hasattr(o, "normals")) nrm = np.attr("asarray")(o.attr("normals"));
+    } else if (py::isinstance<py::tuple>(o) && py::len(o) == 2) {
+        py::tuple t = o.cast<py::tuple>();
+        pts = t[0];
+        if (want_normals && !t[1].is_none()) nrm = t[1];
+    } else {
+        pts = o;
+    }
+    DArray a = DArray::ensure(pts);
+    if (!a || !((a.ndim() == 2 && a.shape(1) == 3) || a.size() == 0))
+        throw py::type_error("pc must be convertible to an (N, 3) float64 array");
+    DArray b;
+    if (!nrm.is_none()) {
+        b = DArray::ensure(nrm);
+        if (!b || b.size() != a.size()) b = DArray();
+    }
+    return {a, b};
+}
+
+/* FitPlane / FitSphere / FitCylinder (python/py_common.cpp:11-67): SetMaxIteration, SetProbability, SetPointCloud,
+ * FitModel -- the same sequence as the facade's RANSAC<> class, but on the caller's buffers (the reference's
+ * SetPointCloud deep copy has no observable effect here: the call does not return before the fit is done) */
+template <int KIND>
 std::tuple<py::array_t<double>, std::vector<size_t>> fit_primitive(const py::object &pc_obj, double threshold,
                                                                    size_t max_iteration, double probability,
                                                                    const py::object &seed, bool need_normals) {
-    PointCloud pc = cloud_from_py(pc_obj);
-    if (need_normals && !pc.HasNormals()) LogError("Fit cylinder requires normals."); /* py_common.cpp:50-52 */
-    Fit fit;
-    fit.SetMaxIteration(max_iteration);
-    fit.SetProbability(probability);
-    if (!seed.is_none()) fit.SetSeed(seed.cast<uint32_t>());
-    ModelT model;
-    std::vector<size_t> inliers;
-    fit.SetPointCloud(std::move(pc)); /* the converted cloud is ours: no second copy */
-    bool ret;
+    auto arrays = cloud_arrays(pc_obj, need_normals);
+    const DArray &pts = arrays.first, &nrm = arrays.second;
+    const size_t n = (size_t)(pts.size() / 3);
+    const bool has_normals = nrm && (size_t)(nrm.size() / 3) == n && n > 0;
+    if (need_normals && !has_normals) LogError("Fit cylinder requires normals."); /* py_common.cpp:50-52 */
+    if (probability <= 0 || probability > 1) LogError("Probability must be > 0 or <= 1.0"); /* ransac.h:482-487 */
+    m3d_ransac_params p{};
+    p.threshold = threshold;
+    p.max_iteration = max_iteration;
+    p.probability = probability;
+    p.seed = seed.is_none() ? b200::RandomSeed() : seed.cast<uint32_t>();
+    constexpr size_t NP = KIND == M3D_CYLINDER ? 7 : 4;
+    double out[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    std::vector<size_t> inliers(n);
+    size_t n_inl = 0;
+    m3d_ransac_stats st{};
+    int rc;
+    m3d_ctx *ctx = b200::DefaultContext();
     {
         py::gil_scoped_release nogil;
-        ret = fit.FitModel(threshold, model, inliers);
+        rc = m3d_ransac_fit(ctx, KIND, n ? pts.data() : nullptr, has_normals ? nrm.data() : nullptr, n, &p, out,
+                            inliers.data(), &n_inl, &st);
     }
-    if (!ret) model.parameters_.assign(4, 0.0); /* setZero(4), also for the cylinder (py_common.cpp:62) */
-    return std::make_tuple(to_numpy(model.parameters_), inliers);
+    inliers.resize(n_inl);
+    if (rc < 0) b200::Raise(ctx); /* lack of points: ransac.h:510-513 throws */
+    {
+        char line[160];
+        std::snprintf(line, sizeof line, "Find best model with %g%% inliers and run %llu iterations",
+                      n ? 100.0 * (double)st.best_count / (double)n : 0.0, (unsigned long long)st.iterations_run);
+        LogInfo(line); /* ransac.h:616-619 */
+    }
+    std::vector<double> params(rc == 1 ? NP : 4, 0.0); /* failure: setZero(4), also for the cylinder (py_common.cpp:62) */
+    if (rc == 1) params.assign(out, out + NP);
+    return std::make_tuple(to_numpy(params), std::move(inliers));
 }
 
 FArray feature_from_py(const py::object &o) {
@@ -124,24 +171,21 @@ PYBIND11_MODULE(py_misc3d, m) {
     common.def(
         "fit_plane",
         [](const py::object &pc, double threshold, size_t max_iteration, double probability, const py::object &seed) {
-            return fit_primitive<misc3d::common::RANSACPlane, misc3d::common::Plane>(pc, threshold, max_iteration,
-                                                                                    probability, seed, false);
+            return fit_primitive<M3D_PLANE>(pc, threshold, max_iteration, probability, seed, false);
         },
         "Fit a plane from point clouds", py::arg("pc"), py::arg("threshold") = 0.01, py::arg("max_iteration") = 1000,
         py::arg("probability") = 0.9999, py::kw_only(), py::arg("seed") = py::none());
     common.def(
         "fit_sphere",
         [](const py::object &pc, double threshold, size_t max_iteration, double probability, const py::object &seed) {
-            return fit_primitive<misc3d::common::RANSACShpere, misc3d::common::Sphere>(pc, threshold, max_iteration,
-                                                                                      probability, seed, false);
+            return fit_primitive<M3D_SPHERE>(pc, threshold, max_iteration, probability, seed, false);
         },
         "Fit a sphere from point clouds", py::arg("pc"), py::arg("threshold") = 0.01, py::arg("max_iteration") = 1000,
         py::arg("probability") = 0.9999, py::kw_only(), py::arg("seed") = py::none());
     common.def(
         "fit_cylinder",
         [](const py::object &pc, double threshold, size_t max_iteration, double probability, const py::object &seed) {
-            return fit_primitive<misc3d::common::RANSACCylinder, misc3d::common::Cylinder>(
-                pc, threshold, max_iteration, probability, seed, true);
+            return fit_primitive<M3D_CYLINDER>(pc, threshold, max_iteration, probability, seed, true);
         },
         "Fit a cylinder from point clouds", py::arg("pc"), py::arg("threshold") = 0.01,
         py::arg("max_iteration") = 1000, py::arg("probability") = 0.9999, py::kw_only(),

@@ -123,3 +123,26 @@ def test_knn_index_is_exact(ctx, capi):
         for j in range(nq):
             assert cnt2[j] == int((dist[j, :cnt[j]] <= r).sum())
             np.testing.assert_array_equal(idx2[j, :cnt2[j]], idx[j, :cnt2[j]])
+
+
+def test_two_cta_kernel_variant_in_a_subprocess(orc):
+    """the experimental cta_group::2 form of the tcgen05 search (M3D_MATCH_TC=2, read once per process) must return the
+    same mutual matches as the oracle"""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("import sys, numpy as np; sys.path.insert(0, %r); from misc3d_b200 import capi, synth; "
+            "d = synth.make_c4(n=20000, seed=3); c = capi.Context(0); "
+            "i0, i1, ms = c.match_correspondence(d['src_feat'], d['dst_feat']); "
+            "np.save(sys.argv[1], np.stack([i0, i1]))") % root
+    out = os.path.join(root, "gpurun_out", "_tc2_match.npy")
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    env = dict(os.environ, M3D_MATCH_TC="2")
+    r = subprocess.run([sys.executable, "-c", code, out], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    got = np.load(out)
+    d = synth.make_c4(n=20000, seed=3)
+    o0, o1 = orc.match_correspondence(d["src_feat"], d["dst_feat"])
+    np.testing.assert_array_equal(got[0], o0)
+    np.testing.assert_array_equal(got[1], o1)
