@@ -49,11 +49,12 @@ __device__ __forceinline__ uint32_t mt_reduce(uint32_t x, uint32_t size, uint64_
  * first 227 elements) comes from other threads, out of the previous block, through a double-buffered copy of the state
  * in shared memory.  The one element that needs a value of its own block from another thread -- 623 = f(.., new[0],
  * new[396]) -- is deferred to the next iteration, where every thread recomputes it from three broadcast loads.
- * Every word is tempered, reduced modulo the cloud size and stored by the thread that produced it:
- * out[b*624 + i] = the (b*624+i)-th value of `rng() % size`.  (The first version used three barriers per block and
- * took ~0.45 us per block: 0.18 ms for the 80k-row table of an 8-GPU fit, on every rank.) */
-__global__ void __launch_bounds__(256) mt_stream_kernel(const MtInit init, uint32_t size, uint64_t magic,
-                                                        uint32_t nblocks, uint32_t *__restrict__ out) {
+ * out[b*624 + i] = the RAW (b*624+i)-th state word; tempering and `% size` are left to stream_finish_kernel (grid-wide):
+ * nothing but the recurrence sits on the sequential path.  Measured 0.31 us per block (0.12 ms for the 392 blocks of the
+ * 80k-row table of an 8-GPU fit; the first version, three barriers per block with tempering and the 64-bit fastmod
+ * inline, took 0.45 us).  A variant that kept the global stores away from the barrier (shared-memory ring + copy
+ * warps) measured the same 0.31 us: the loop is bound by its dependent LDS -> twist x 3 -> STS -> barrier chain. */
+__global__ void __launch_bounds__(256) mt_stream_kernel(const MtInit init, uint32_t nblocks, uint32_t *__restrict__ out) {
     __shared__ uint32_t st[2][624];
     __shared__ uint32_t s623[2];
     const int t = threadIdx.x;
@@ -71,38 +72,44 @@ __global__ void __launch_bounds__(256) mt_stream_kernel(const MtInit init, uint3
         const int par = blk & 1;
         if (live) {
             const uint32_t *s = st[par];
-            /* element 623 of the previous block (for blk == 0: of the seed state, which is complete) */
-            uint32_t e623;
-            if (blk == 0) {
-                e623 = s[623];
-            } else {
-                e623 = mt_twist(s623[par], s[0], s[396]);
-                if (t == 169) out[(size_t)(blk - 1) * 624 + 623] = mt_reduce(mt_temper(e623), size, magic);
-            }
-            if (t == 169) s623[par ^ 1] = e623; /* "old[623]" of the next iteration */
             uint32_t *o = out + (size_t)blk * 624;
-            const uint32_t nA = mt_twist(a, s[t + 1], t == 226 ? e623 : s[t + 397]);
-            o[t] = mt_reduce(mt_temper(nA), size, magic);
-            const uint32_t nB = mt_twist(b, s[228 + t], nA);
-            o[227 + t] = mt_reduce(mt_temper(nB), size, magic);
-            uint32_t nC = 0;
-            if (t < 169) {
-                nC = mt_twist(c, t == 168 ? e623 : s[455 + t], nB);
-                o[454 + t] = mt_reduce(mt_temper(nC), size, magic);
+            /* the common case first: nothing here waits for element 623 of the previous block */
+            uint32_t nA = mt_twist(a, s[t + 1], s[t + 397]); /* t == 226 reads the stale s[623]: redone below */
+            uint32_t e623 = 0;
+            const bool special = (t >> 5) == 5 || (t >> 5) == 7; /* the warps of threads 168, 169 and 226: the users of
+                                                                  * element 623 of the previous block (whole warps, so
+                                                                  * that the branch does not diverge) */
+            if (special) {
+                e623 = s[623];
+                if (blk != 0) { /* (for blk == 0 the seed state is complete) */
+                    e623 = mt_twist(s623[par], s[0], s[396]);
+                    if (t == 169) out[(size_t)(blk - 1) * 624 + 623] = e623;
+                }
+                if (t == 169) s623[par ^ 1] = e623; /* "old[623]" of the next iteration */
+                if (t == 226) nA = mt_twist(a, s[t + 1], e623);
             }
+            const uint32_t nB = mt_twist(b, s[228 + t], nA);
+            uint32_t nC = 0;
+            if (t < 169) nC = mt_twist(c, (special && t == 168) ? e623 : s[455 + t], nB);
             uint32_t *w = st[par ^ 1];
-            w[t] = nA;
-            w[227 + t] = nB;
-            if (t < 169) w[454 + t] = nC;
+            w[t] = nA, w[227 + t] = nB;
+            o[t] = nA, o[227 + t] = nB;
+            if (t < 169) w[454 + t] = nC, o[454 + t] = nC;
             a = nA, b = nB, c = nC;
         }
         __syncthreads();
     }
     if (nblocks && t == 169) { /* the deferred last element */
         const int par = nblocks & 1;
-        const uint32_t e623 = mt_twist(s623[par], st[par][0], st[par][396]);
-        out[(size_t)(nblocks - 1) * 624 + 623] = mt_reduce(mt_temper(e623), size, magic);
+        out[(size_t)(nblocks - 1) * 624 + 623] = mt_twist(s623[par], st[par][0], st[par][396]);
     }
+}
+
+/* raw state words -> `rng() % size`: tempering and the exact modulo, grid-wide (kept off the sequential kernel) */
+__global__ void __launch_bounds__(256) stream_finish_kernel(uint32_t *__restrict__ stream, uint32_t len, uint32_t size,
+                                                            uint64_t magic) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < len; i += gridDim.x * blockDim.x)
+        stream[i] = mt_reduce(mt_temper(stream[i]), size, magic);
 }
 
 /* A row that starts at stream position s takes exactly k draws unless two of them coincide

@@ -552,9 +552,11 @@ int draw_table_device(m3d_ctx *ctx, uint32_t seed, uint32_t n, int k, uint32_t r
     for (uint32_t i = 1; i < 624; ++i) init.mt[i] = 1812433253u * (init.mt[i - 1] ^ (init.mt[i - 1] >> 30)) + i;
     const uint64_t magic = UINT64_MAX / n + 1;
     M3D_CUDA(ctx, cudaMemsetAsync(d_status, 0, sizeof(RowBreaks), ctx->stream));
-    mt_stream_kernel<<<1, 256, 0, ctx->stream>>>(init, n, magic, nblocks, stream);
+    mt_stream_kernel<<<1, 256, 0, ctx->stream>>>(init, nblocks, stream);
     M3D_LAUNCHED(ctx);
     const int nb = std::max(1, std::min<int>(ctx->sm_count * 4, (int)((len + 255) / 256)));
+    stream_finish_kernel<<<nb, 256, 0, ctx->stream>>>(stream, len, n, magic);
+    M3D_LAUNCHED(ctx);
     dup_positions_kernel<<<nb, 256, 0, ctx->stream>>>(stream, len, k, d_status, list);
     M3D_LAUNCHED(ctx);
     row_breaks_kernel<<<1, 1024, 0, ctx->stream>>>(stream, len, k, rows, d_status, list, brk);
