@@ -29,7 +29,7 @@ namespace m3d {
 __global__ void __launch_bounds__(256) knn_dist_kernel(const double *__restrict__ data, int dim, uint32_t n,
                                                        const double *__restrict__ queries, uint32_t nq,
                                                        double *__restrict__ dist) {
-    extern __shared__ double sq[]; /* the query */
+    extern __shared__ double sq[]; /* the query (+ 2 words of slack: the compiler reads it in 16-byte pairs) */
     const uint32_t q = blockIdx.y;
     for (int d = threadIdx.x; d < dim; d += blockDim.x) sq[d] = queries[(size_t)q * dim + d];
     __syncthreads();
@@ -173,7 +173,7 @@ int m3d_knn_search(m3d_ctx *ctx, m3d_knn *index, const double *queries, size_t n
         M3D_CUDA(ctx, cudaMemcpyAsync(index->q.p, queries + q0 * dim, sizeof(double) * (size_t)cq * dim,
                                       cudaMemcpyHostToDevice, ctx->stream));
         const int bx = std::max(1, std::min<int>((n + 255) / 256, std::max(1, ctx->sm_count * 8 / (int)std::min<uint32_t>(cq, 64))));
-        knn_dist_kernel<<<dim3(bx, cq), 256, sizeof(double) * dim, ctx->stream>>>(index->data.as<double>(), dim, n,
+        knn_dist_kernel<<<dim3(bx, cq), 256, sizeof(double) * ((size_t)dim + 2), ctx->stream>>>(index->data.as<double>(), dim, n,
                                                                                   index->q.as<double>(), cq,
                                                                                   index->dist.as<double>());
         M3D_LAUNCHED(ctx);
