@@ -323,11 +323,20 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    # value leg, N > 1: every rank gets the model, the inlier COUNT and the stats of every fit; the inlier index
+    # list (2.7 MB per fit) is copied to the host on rank 0 only -- the job has one result, and eight identical
+    # device->host copies at the same instant share PCIe uplinks (tools/numa_probe.py: GPUs 0-3 of the 8-GPU box
+    # drop to 16 GB/s each).  Every rank still builds the list on its GPU (RefineModel needs it).
+    # M3D_BENCH_INLIERS=all restores the copy on every rank.
+    inl_everywhere = os.environ.get("M3D_BENCH_INLIERS") == "all"
+    want_inl = rank == 0 or inl_everywhere
+
     def step_resident(seed):
         out = []
         for kind in KINDS:
-            rc, model, inl, st = ctx.ransac_fit_cloud(kind, cloud, THR, H, 1.0, seed=seed + kind, inl_buf=inl_buf)
-            out.append((rc, len(inl), st))
+            rc, model, inl, st = ctx.ransac_fit_cloud(kind, cloud, THR, H, 1.0, seed=seed + kind,
+                                                      inl_buf=inl_buf if want_inl else None, want_inliers=want_inl)
+            out.append((rc, len(inl) if inl is not None else 0, st))
         return out
 
     def step_e2e(seed, pts, nrms, buf):
@@ -524,7 +533,9 @@ def main():
                                f"{H_PER_PRIM} hypotheses per primitive per GPU, probability 1.0 (no early exit)",
                    "n_points": N_POINTS, "hypotheses_per_primitive": H, "threshold": THR,
                    "l2": "512 MiB flush write between timed steps", "sharding": f"hypotheses over {world} rank(s)",
-                   "seeds": "a different sample-table seed every step and primitive (no table re-use)"},
+                   "seeds": "a different sample-table seed every step and primitive (no table re-use)",
+                   "results_to_host": ("model, inlier count and stats on every rank; inlier index list on "
+                                       + ("every rank" if inl_everywhere or world == 1 else "rank 0"))},
         "point_hypotheses_per_sec": value * N_POINTS,
         "e2e": {"value": e2e_value, "unit": "hypotheses/s", "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": int(d2h), "api": "m3d_ransac_fit (host buffers, pinned)"},

@@ -344,7 +344,7 @@ void m3d_ctx_destroy(m3d_ctx *c) {
     if (c->scratch_cloud) m3d_cloud_free(c->scratch_cloud);
     DevBuf *db[] = {&c->d_samples, &c->d_counts, &c->d_counts_all, &c->d_blk, &c->d_part, &c->d_small,
                     &c->d_inl,     &c->d_models, &c->d_valid,      &c->d_tmp0, &c->d_tmp1, &c->d_tmp2,
-                    &c->d_tmp3,    &c->d_tmp4,   &c->d_tmp5,      &c->d_queue,    &c->d_tiles, &c->d_rownrm, &c->d_rowmap, &c->d_recs, &c->d_draw,
+                    &c->d_tmp3,    &c->d_tmp4,   &c->d_tmp5,      &c->d_queue,    &c->d_tiles, &c->d_rownrm, &c->d_rowmap, &c->d_recs, &c->d_draw, &c->d_mtjump,
                     &c->d_metas,   &c->d_models_all, &c->d_valid_all};
     for (auto *b : db) b->release();
     PinBuf *pb[] = {&c->h_samples, &c->h_counts, &c->h_small, &c->h_stage, &c->h_rownrm, &c->h_metas, &c->h_upload};

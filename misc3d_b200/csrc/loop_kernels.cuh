@@ -18,6 +18,7 @@
 #include <cstdint>
 
 #include "scan.h"
+#include "mt_jump_table.h"
 
 namespace m3d {
 
@@ -54,24 +55,19 @@ __device__ __forceinline__ uint32_t mt_reduce(uint32_t x, uint32_t size, uint64_
  * 80k-row table of an 8-GPU fit; the first version, three barriers per block with tempering and the 64-bit fastmod
  * inline, took 0.45 us).  A variant that kept the global stores away from the barrier (shared-memory ring + copy
  * warps) measured the same 0.31 us: the loop is bound by its dependent LDS -> twist x 3 -> STS -> barrier chain. */
-__global__ void __launch_bounds__(256) mt_stream_kernel(const MtInit init, uint32_t nblocks, uint32_t *__restrict__ out) {
-    __shared__ uint32_t st[2][624];
-    __shared__ uint32_t s623[2];
+struct MtSmem {
+    uint32_t st[2][624];
+    uint32_t s623[2];
+};
+/* the block loop: sm.st[0] and (a, b, c) hold the 624 words in front of the first block to produce */
+__device__ __forceinline__ void mt_run(MtSmem &sm, uint32_t a, uint32_t b, uint32_t c, uint32_t nblocks,
+                                       uint32_t *__restrict__ out) {
     const int t = threadIdx.x;
     const bool live = t < 227; /* threads 227..255 only keep the barriers whole */
-    /* registers: this thread's elements of the previous block */
-    uint32_t a = 0, b = 0, c = 0;
-    if (live) {
-        a = init.mt[t], b = init.mt[227 + t], c = t < 170 ? init.mt[454 + t] : 0u;
-        st[0][t] = a;
-        st[0][227 + t] = b;
-        if (t < 170) st[0][454 + t] = c;
-    }
-    __syncthreads();
     for (uint32_t blk = 0; blk < nblocks; ++blk) {
         const int par = blk & 1;
         if (live) {
-            const uint32_t *s = st[par];
+            const uint32_t *s = sm.st[par];
             uint32_t *o = out + (size_t)blk * 624;
             /* the common case first: nothing here waits for element 623 of the previous block */
             uint32_t nA = mt_twist(a, s[t + 1], s[t + 397]); /* t == 226 reads the stale s[623]: redone below */
@@ -81,17 +77,17 @@ __global__ void __launch_bounds__(256) mt_stream_kernel(const MtInit init, uint3
                                                                   * that the branch does not diverge) */
             if (special) {
                 e623 = s[623];
-                if (blk != 0) { /* (for blk == 0 the seed state is complete) */
-                    e623 = mt_twist(s623[par], s[0], s[396]);
+                if (blk != 0) { /* (for blk == 0 the given state is complete) */
+                    e623 = mt_twist(sm.s623[par], s[0], s[396]);
                     if (t == 169) out[(size_t)(blk - 1) * 624 + 623] = e623;
                 }
-                if (t == 169) s623[par ^ 1] = e623; /* "old[623]" of the next iteration */
+                if (t == 169) sm.s623[par ^ 1] = e623; /* "old[623]" of the next iteration */
                 if (t == 226) nA = mt_twist(a, s[t + 1], e623);
             }
             const uint32_t nB = mt_twist(b, s[228 + t], nA);
             uint32_t nC = 0;
             if (t < 169) nC = mt_twist(c, (special && t == 168) ? e623 : s[455 + t], nB);
-            uint32_t *w = st[par ^ 1];
+            uint32_t *w = sm.st[par ^ 1];
             w[t] = nA, w[227 + t] = nB;
             o[t] = nA, o[227 + t] = nB;
             if (t < 169) w[454 + t] = nC, o[454 + t] = nC;
@@ -101,8 +97,79 @@ __global__ void __launch_bounds__(256) mt_stream_kernel(const MtInit init, uint3
     }
     if (nblocks && t == 169) { /* the deferred last element */
         const int par = nblocks & 1;
-        out[(size_t)(nblocks - 1) * 624 + 623] = mt_twist(s623[par], st[par][0], st[par][396]);
+        out[(size_t)(nblocks - 1) * 624 + 623] = mt_twist(sm.s623[par], sm.st[par][0], sm.st[par][396]);
     }
+}
+
+/* blocks [0, nblocks) of the stream from the seed state.  `zero_windows` > 1: the windows (first blocks) of segments
+ * 1 .. zero_windows-1 are cleared for mt_jump_kernel's XOR accumulation. */
+__global__ void __launch_bounds__(256) mt_stream_kernel(const MtInit init, uint32_t nblocks, uint32_t *__restrict__ out,
+                                                        uint32_t zero_windows, uint32_t seg_blocks) {
+    __shared__ MtSmem sm;
+    const int t = threadIdx.x;
+    for (uint32_t p = 1; p < zero_windows; ++p)
+        for (int i = t; i < 624; i += 256) out[(size_t)p * seg_blocks * 624 + i] = 0u;
+    uint32_t a = 0, b = 0, c = 0;
+    if (t < 227) {
+        a = init.mt[t], b = init.mt[227 + t], c = t < 170 ? init.mt[454 + t] : 0u;
+        sm.st[0][t] = a;
+        sm.st[0][227 + t] = b;
+        if (t < 170) sm.st[0][454 + t] = c;
+    }
+    __syncthreads();
+    mt_run(sm, a, b, c, nblocks, out);
+}
+
+/* ---- jump-ahead.  The raw words obey one linear recurrence over GF(2) (characteristic polynomial of degree 19937), so
+ * the 624-word window at stream position J is  y[J + j] = XOR_{i : g_i = 1} y[i + j]  with g = x^J mod phi -- a binary
+ * convolution of the first 19937 + 623 words (kMtPrefixBlocks blocks) with a precomputed polynomial
+ * (mt_jump_table.h, tools/gen_mt_jump.py).  Segment p of the stream starts at block p * kMtSegBlocks; with its window
+ * known, one CTA per segment walks the recurrence, all segments at once.
+ * grid (kMtJumpChunks, segments - 1), 640 threads: CTA (c, p-1) adds the terms i in [416 c, 416 c + 416) to window p. */
+constexpr int kMtPrefixBlocks = 33;
+constexpr int kMtJumpChunks = 48;
+constexpr int kMtJumpBits = 416; /* 48 x 416 = 19968 = 624 x 32 */
+__global__ void __launch_bounds__(640) mt_jump_kernel(uint32_t *__restrict__ stream, const uint32_t *__restrict__ polys,
+                                                      uint32_t seg_blocks) {
+    __shared__ uint32_t ys[kMtJumpBits + 624];
+    __shared__ uint16_t terms[kMtJumpBits];
+    __shared__ uint32_t n_terms;
+    const int t = threadIdx.x, c = blockIdx.x, p = blockIdx.y + 1;
+    if (t == 0) n_terms = 0;
+    for (int i = t; i < kMtJumpBits + 623; i += 640) ys[i] = stream[c * kMtJumpBits + i];
+    __syncthreads();
+    if (t < kMtJumpBits) {
+        const int bit = c * kMtJumpBits + t;
+        if ((polys[(size_t)(p - 1) * 624 + (bit >> 5)] >> (bit & 31)) & 1u) terms[atomicAdd(&n_terms, 1u)] = (uint16_t)t;
+    }
+    __syncthreads();
+    if (t < 624) {
+        const uint32_t cnt = n_terms;
+        uint32_t acc = 0;
+        for (uint32_t i = 0; i < cnt; ++i) acc ^= ys[terms[i] + t];
+        if (cnt) atomicXor(stream + (size_t)p * seg_blocks * 624 + t, acc);
+    }
+}
+
+/* one CTA per segment: the window of segment p (block p * seg_blocks; for p == 0 the last prefix block) is the state,
+ * the CTA produces the blocks up to the next segment's window (the last segment: up to total_blocks) */
+__global__ void __launch_bounds__(256) mt_segments_kernel(uint32_t *__restrict__ stream, uint32_t seg_blocks,
+                                                          uint32_t nseg, uint32_t total_blocks) {
+    __shared__ MtSmem sm;
+    const int t = threadIdx.x;
+    const uint32_t p = blockIdx.x;
+    const uint32_t sb = p == 0 ? (uint32_t)kMtPrefixBlocks - 1 : p * seg_blocks;
+    const uint32_t end = (p + 1 == nseg) ? total_blocks : (p + 1) * seg_blocks;
+    const uint32_t *state = stream + (size_t)sb * 624;
+    uint32_t a = 0, b = 0, c = 0;
+    if (t < 227) {
+        a = state[t], b = state[227 + t], c = t < 170 ? state[454 + t] : 0u;
+        sm.st[0][t] = a;
+        sm.st[0][227 + t] = b;
+        if (t < 170) sm.st[0][454 + t] = c;
+    }
+    __syncthreads();
+    if (end > sb + 1) mt_run(sm, a, b, c, end - sb - 1, stream + (size_t)(sb + 1) * 624);
 }
 
 /* raw state words -> `rng() % size`: tempering and the exact modulo, grid-wide (kept off the sequential kernel) */

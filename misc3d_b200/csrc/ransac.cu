@@ -10,6 +10,7 @@
  */
 #include <algorithm>
 #include <cmath>
+#include <ctime>
 #include <vector>
 
 #include "context.h"
@@ -525,6 +526,40 @@ bool loop_on_host() {
     static const bool v = env_is("M3D_LOOP", "host");
     return v;
 }
+/* M3D_TRACE=1: host wall-clock per phase of m3d_ransac_fit_cloud, summed and printed at exit (a tuning aid) */
+struct HostTrace {
+    bool on = getenv("M3D_TRACE") != nullptr;
+    double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    double t = 0;
+    unsigned long long calls = 0;
+    bool armed = false; /* only fits of a resident cloud (m3d_ransac_fit_cloud) are traced */
+    long skip = getenv("M3D_TRACE") ? atol(getenv("M3D_TRACE")) : 0; /* value = warm-up fits to leave out */
+    void mark(int i) {
+        if (!on || !armed) return;
+        if (skip > 0) {
+            t = now();
+            return;
+        }
+        const double n = now();
+        if (t != 0) acc[i] += n - t;
+        t = n;
+    }
+    static double now() {
+        timespec ts;
+        clock_gettime(CLOCK_MONOTONIC, &ts);
+        return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+    }
+    ~HostTrace() {
+        if (!on || !calls) return;
+        const char *r = getenv("RANK");
+        fprintf(stderr,
+                "[m3d trace rank %s] %llu fits, ms per fit: between-calls %.4f  setup+draw-enqueue %.4f  score-enqueue %.4f  "
+                "exchange-enqueue %.4f  refine-enqueue %.4f  sync-wait %.4f  finish %.4f  deliver %.4f\n",
+                r ? r : "0", calls, acc[0] / calls, acc[1] / calls, acc[2] / calls, acc[3] / calls, acc[4] / calls,
+                acc[5] / calls, acc[6] / calls, acc[7] / calls);
+    }
+};
+HostTrace g_trace;
 bool sampler_on_host() {
     static const bool v = env_is("M3D_SAMPLER", "host");
     return v;
@@ -552,8 +587,24 @@ int draw_table_device(m3d_ctx *ctx, uint32_t seed, uint32_t n, int k, uint32_t r
     for (uint32_t i = 1; i < 624; ++i) init.mt[i] = 1812433253u * (init.mt[i - 1] ^ (init.mt[i - 1] >> 30)) + i;
     const uint64_t magic = UINT64_MAX / n + 1;
     M3D_CUDA(ctx, cudaMemsetAsync(d_status, 0, sizeof(RowBreaks), ctx->stream));
-    mt_stream_kernel<<<1, 256, 0, ctx->stream>>>(init, nblocks, stream);
-    M3D_LAUNCHED(ctx);
+    /* long tables: the stream is produced in segments that start from jumped-ahead states (loop_kernels.cuh) */
+    static const bool no_jump = env_is("M3D_MT_JUMP", "0");
+    if (nblocks >= 2u * kMtSegBlocks && !no_jump) {
+        const uint32_t nseg = std::min<uint32_t>(kMtMaxSegments, (nblocks + kMtSegBlocks - 1) / kMtSegBlocks);
+        if (!ctx->d_mtjump.p) {
+            M3D_CUDA(ctx, ctx->d_mtjump.reserve(sizeof kMtJump));
+            M3D_CUDA(ctx, cudaMemcpyAsync(ctx->d_mtjump.p, kMtJump, sizeof kMtJump, cudaMemcpyHostToDevice, ctx->stream));
+        }
+        mt_stream_kernel<<<1, 256, 0, ctx->stream>>>(init, kMtPrefixBlocks, stream, nseg, kMtSegBlocks);
+        M3D_LAUNCHED(ctx);
+        mt_jump_kernel<<<dim3(kMtJumpChunks, nseg - 1), 640, 0, ctx->stream>>>(stream, ctx->d_mtjump.as<uint32_t>(), kMtSegBlocks);
+        M3D_LAUNCHED(ctx);
+        mt_segments_kernel<<<nseg, 256, 0, ctx->stream>>>(stream, kMtSegBlocks, nseg, nblocks);
+        M3D_LAUNCHED(ctx);
+    } else {
+        mt_stream_kernel<<<1, 256, 0, ctx->stream>>>(init, nblocks, stream, 0, 0);
+        M3D_LAUNCHED(ctx);
+    }
     const int nb = std::max(1, std::min<int>(ctx->sm_count * 4, (int)((len + 255) / 256)));
     stream_finish_kernel<<<nb, 256, 0, ctx->stream>>>(stream, len, n, magic);
     M3D_LAUNCHED(ctx);
@@ -878,6 +929,7 @@ struct Fit {
             M3D_CUDA(ctx, ctx->d_counts.reserve(sizeof(uint32_t) * (size_t)std::max<uint32_t>(S, 1)));
             M3D_CUDA(ctx, cudaMemsetAsync(ctx->d_counts.p, 0, sizeof(uint32_t) * (size_t)std::max<uint32_t>(S, 1), ctx->stream));
             M3D_CUDA(ctx, cudaEventRecord(ev_s0, ctx->stream));
+            g_trace.mark(1);
             if (mine && !pl) {
                 ScoreArgs a = score_args(0, mine);
                 a.samples = ctx->d_samples.as<uint32_t>() + (size_t)done * k;
@@ -905,6 +957,7 @@ struct Fit {
                 if (int rc = launch_score_kind(ctx, kind, cloud_for_flags, a, false)) return rc;
             }
             M3D_CUDA(ctx, cudaEventRecord(ev_s1, ctx->stream));
+            g_trace.mark(2);
             wave_best_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->d_counts.as<uint32_t>(), mine, (uint32_t)R, (uint32_t)rank, n,
                                                           &ds->draw, d_local);
             M3D_LAUNCHED(ctx);
@@ -913,6 +966,7 @@ struct Fit {
                                                          host_nrm ? ctx->d_rownrm.as<double>() + (size_t)done * k * 3 : nullptr,
                                                          &ds->best, ds->sample, ds->row_nrm);
             M3D_LAUNCHED(ctx);
+            g_trace.mark(3);
             const bool speculate = (rows == H) && !seg;
             if (speculate)
                 if (int rc = enqueue_refine()) return rc;
@@ -920,7 +974,9 @@ struct Fit {
             if (pl && done == 0)
                 M3D_CUDA(ctx, cudaMemcpyAsync(ctx->h_metas.p, pl->metas, sizeof(CloudMeta) * pl->count, cudaMemcpyDeviceToHost, ctx->stream));
             if (speculate) M3D_CUDA(ctx, cudaEventRecord(ev_b, ctx->stream));
+            g_trace.mark(4);
             M3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            g_trace.mark(5);
             if (pl && done == 0) /* NaN / inf coordinates need the fp64 reference-order kernel: plain upload path */
                 for (int c = 0; c < pl->count; ++c)
                     if (ctx->h_metas.as<CloudMeta>()[c].nonfinite) return kRetryUnchunked;
@@ -1218,6 +1274,8 @@ int m3d_ransac_fit_cloud(m3d_ctx *ctx, int kind, const m3d_cloud *cloud, const m
     if (stats) memset(stats, 0, sizeof *stats);
     if (int rc = check_params(ctx, kind, cloud->n, cloud->has_normals, p)) return rc;
     M3D_CUDA(ctx, cudaSetDevice(ctx->device));
+    g_trace.armed = true;
+    g_trace.mark(0);
     CloudView v{cloud->xyz.as<double>(), (cloud->has_normals && !cloud->h_nrm) ? cloud->nrm.as<double>() : nullptr,
                 cloud->pts32.as<float4>(), cloud->meta.as<CloudMeta>(), (uint32_t)cloud->n,
                 cloud->h_meta.nonfinite != 0};
@@ -1229,7 +1287,13 @@ int m3d_ransac_fit_cloud(m3d_ctx *ctx, int kind, const m3d_cloud *cloud, const m
     }
     FitResult res;
     if (int rc = fit_view(ctx, kind, cloud, v, *p, nullptr, &res)) return rc;
-    return deliver(ctx, kind, res, model_out, inl_out, n_inl, stats);
+    g_trace.mark(6);
+    const int ret = deliver(ctx, kind, res, model_out, inl_out, n_inl, stats);
+    g_trace.mark(7);
+    g_trace.armed = false;
+    if (g_trace.skip > 0) --g_trace.skip;
+    else ++g_trace.calls;
+    return ret;
 }
 
 int m3d_ransac_fit(m3d_ctx *ctx, int kind, const double *xyz, const double *nrm, size_t n,

@@ -481,7 +481,11 @@ def test_full_size_properties_c5(ctx, capi, orc):
 # host replay (csrc/loop_kernels.cuh)
 @pytest.mark.parametrize("seed,n,k,rows", [(1, 1_000_000, 3, 10_000), (2, 1_000_000, 4, 10_000), (3, 1_000_000, 2, 80_000),
                                            (4, 5000, 4, 20_000), (5, 700, 3, 3000), (6, 40, 3, 400), (7, 2, 2, 100),
-                                           (8, 4_000_000, 3, 100_000), (9, 65536, 3, 1), (10, 123457, 2, 624 * 5)])
+                                           (8, 4_000_000, 3, 100_000), (9, 65536, 3, 1), (10, 123457, 2, 624 * 5),
+                                           # long tables: segments started from jumped-ahead generator states
+                                           (11, 1_000_000, 3, 80_000), (12, 1_000_000, 3, 300_000),
+                                           (13, 1_000_000, 4, 30_000), (14, 1_000_000, 3, 18_600),
+                                           (15, 1_000_000, 3, 18_500), (4294967295, 2_000_000, 3, 160_000)])
 def test_sample_table_device_equals_host(ctx, capi, seed, n, k, rows):
     """utils.h:81-97 (mt19937, % size, duplicate rejection) drawn on the GPU == the host stream, bit for bit;
     small clouds have many rejected draws (row boundaries shift), tiny ones make the device give up (None)"""

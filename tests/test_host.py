@@ -283,3 +283,36 @@ def test_bench_reference_arm_contract():
     r2 = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"],
                         capture_output=True, text=True, timeout=120, env=env2)
     assert r2.returncode == 0 and r2.stdout.strip() == ""
+
+
+def test_mt_jump_table_matches_generator():
+    """csrc/mt_jump_table.h (jump-ahead polynomials of mt19937 used by the device-side sample draw) is what
+    tools/gen_mt_jump.py produces, and every polynomial maps the first 19937+623 raw words of a stream onto the
+    624-word window at its segment start (checked against the sequentially generated stream)"""
+    import importlib.util
+    import re
+    spec = importlib.util.spec_from_file_location("gen_mt_jump", os.path.join(ROOT, "tools", "gen_mt_jump.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    text = open(os.path.join(ROOT, "misc3d_b200", "csrc", "mt_jump_table.h")).read()
+    assert f"kMtSegBlocks = {gen.SEG_BLOCKS};" in text and f"kMtMaxSegments = {gen.MAX_SEGMENTS};" in text
+    words = np.array([int(w, 16) for w in re.findall(r"0x([0-9a-f]{8})u", text)], dtype=np.uint32)
+    assert words.size == (gen.MAX_SEGMENTS - 1) * gen.WORDS
+    table = words.reshape(gen.MAX_SEGMENTS - 1, gen.WORDS)
+    y = gen.raw_stream(20240607, gen.SEG_BLOCKS * (gen.MAX_SEGMENTS - 1) + 1)
+    # the raw stream itself against numpy's mt19937 (tempered): temper(y) must equal random_raw()
+    t = y.copy()
+    t ^= t >> np.uint32(11)
+    t ^= (t << np.uint32(7)) & np.uint32(0x9D2C5680)
+    t ^= (t << np.uint32(15)) & np.uint32(0xEFC60000)
+    t ^= t >> np.uint32(18)
+    bg = np.random.MT19937()
+    bg._legacy_seeding(20240607)
+    np.testing.assert_array_equal(t[:5000], bg.random_raw(5000).astype(np.uint32))
+    for p in (1, 2, 7, gen.MAX_SEGMENTS - 1):
+        g = int.from_bytes(table[p - 1].astype("<u4").tobytes(), "little")
+        j = p * gen.SEG_BLOCKS * 624
+        np.testing.assert_array_equal(gen.apply_poly(g, y), y[j:j + 624])
+    polys = gen.build()
+    for p, g in enumerate(polys, 1):
+        assert int.from_bytes(table[p - 1].astype("<u4").tobytes(), "little") == g, p
