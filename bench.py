@@ -342,9 +342,9 @@ def main():
     def step_e2e(seed, pts, nrms, buf):
         d2h = 0
         for kind in KINDS:
-            rc, model, inl, st = ctx.ransac_fit(kind, pts, nrms if kind == 2 else None, THR, H, 1.0,
-                                                seed=seed + kind, inl_buf=buf)
-            d2h += inl.nbytes + 64 * world
+            rc, model, inl, st = ctx.ransac_fit(kind, pts, nrms if kind == 2 else None, THR, H, 1.0, seed=seed + kind,
+                                                inl_buf=buf if want_inl else None, want_inliers=want_inl)
+            d2h += (inl.nbytes if inl is not None else 0) + 64 * world
         return d2h
 
     def timed_e2e(step, n_warm=2):
@@ -404,7 +404,9 @@ def main():
     e2e_value, d2h = timed_e2e(lambda seed: step_e2e(seed, np_xyz, np_nrm, inl_buf))
     # three cloud uploads + the normals of the cylinder's sample points (2 per hypothesis; the caller's normal array
     # itself stays on the host) + the cylinder's host-drawn sample table (plane / sphere tables are drawn on the device)
-    h2d = 3 * xyz.nbytes + 2 * 24 * H + 2 * 4 * H
+    # (N > 1: every rank uploads 1/N of the cloud and the slices are all-gathered over NVLink; bytes are rank 0's)
+    sharded_upload = world > 1 and os.environ.get("M3D_SHARD_UPLOAD") != "0"
+    h2d = 3 * xyz.nbytes // (world if sharded_upload else 1) + 2 * 24 * H + 2 * 4 * H
     extras = {}
     if not args.no_extras:
         # the same call with what an Open3D / numpy caller actually holds: pageable arrays, pageable result buffer
@@ -433,6 +435,40 @@ def main():
                                                "inlier indices as a python list like the reference: O(n_inl) boxing included)"}
             except Exception as e:  # the shim is optional on the bench box
                 extras["e2e_pybind"] = {"value": None, "error": str(e)[:200]}
+        if world == 1:
+            # throughput of a caller that keeps two clouds in flight: two host threads, one context (own stream and
+            # scratch) each, the plain synchronous m3d_ransac_fit call in both -- the upload of one thread's cloud
+            # overlaps the scoring of the other's.  Same work per step as `e2e` (which stays the one-call-at-a-time number).
+            import threading
+            n_ctx = 2
+            ctxs = [capi.Context(local_rank) for _ in range(n_ctx)]
+            bufs = [torch.empty(N_POINTS, dtype=torch.int64).pin_memory().numpy().view(np.uint64) for _ in range(n_ctx)]
+
+            def run(i, seeds):
+                for seed in seeds:
+                    for kind in KINDS:
+                        ctxs[i].ransac_fit(kind, np_xyz, np_nrm if kind == 2 else None, THR, H, 1.0,
+                                           seed=seed + kind, inl_buf=bufs[i])
+
+            def both(seed_lists):
+                th = [threading.Thread(target=run, args=(i, seed_lists[i])) for i in range(n_ctx)]
+                for t_ in th:
+                    t_.start()
+                for t_ in th:
+                    t_.join()
+            both([[3000 + i] for i in range(n_ctx)])
+            steps_c = max(args.steps, n_ctx)
+            seeds = [[4000 + 3 * s_ for s_ in range(steps_c) if s_ % n_ctx == i] for i in range(n_ctx)]
+            barrier()
+            t0 = time.perf_counter()
+            both(seeds)
+            barrier()
+            dt = time.perf_counter() - t0
+            extras["e2e_concurrent"] = {"value": 3.0 * H * steps_c / dt, "unit": "hypotheses/s", "contexts": n_ctx,
+                                        "api": "m3d_ransac_fit (host buffers, pinned) called from two host threads, "
+                                               "one context each"}
+            for c_ in ctxs:
+                c_.close()
         extras["c5"] = c5_leg(ctx, capi, synth, dist, dev, rank, world)
 
     # work counters of the kernel (statistics build, one sharded launch per primitive, outside the timed region;
@@ -538,7 +574,9 @@ def main():
                                        + ("every rank" if inl_everywhere or world == 1 else "rank 0"))},
         "point_hypotheses_per_sec": value * N_POINTS,
         "e2e": {"value": e2e_value, "unit": "hypotheses/s", "h2d_bytes_per_step": int(h2d),
-                "d2h_bytes_per_step": int(d2h), "api": "m3d_ransac_fit (host buffers, pinned)"},
+                "d2h_bytes_per_step": int(d2h),
+                "api": "m3d_ransac_fit (host buffers, pinned)" + (
+                    "; each rank uploads 1/N of the replicated cloud, NVLink all-gather of the rest" if sharded_upload else "")},
         "gpu_launches": int(launches),
         "clocks": clk,
         "roofline": roofline, "roofline_alu": roofline_alu, "roofline_refine": roofline_refine, "per_primitive": per_kind,

@@ -63,6 +63,17 @@ static bool nccl_load(std::string *why) {
     return true;
 }
 
+bool exchange_has_nccl(const m3d_ctx *ctx) { return ctx->world > 1 && ctx->nccl_comm != nullptr; }
+
+int exchange_allgather_nccl(m3d_ctx *ctx, const void *d_send, void *d_recv, size_t bytes_per_rank, cudaStream_t stream) {
+    if (!exchange_has_nccl(ctx)) return ctx->fail(M3D_ERR_INTERNAL, "no NCCL communicator");
+    const int ncclChar = 0;
+    const int rc = g_nccl.AllGather(d_send, d_recv, bytes_per_rank, ncclChar, ctx->nccl_comm, stream);
+    if (rc != 0)
+        return ctx->fail(M3D_ERR_NCCL, "ncclAllGather: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error");
+    return M3D_OK;
+}
+
 int exchange_allgather(m3d_ctx *ctx, const void *d_send, void *d_recv, size_t bytes_per_rank) {
     if (ctx->world <= 1) {
         if (d_send != d_recv)

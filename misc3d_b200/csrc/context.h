@@ -148,4 +148,7 @@ namespace m3d {
 int host_to_device(m3d_ctx *ctx, void *dst, const void *src, size_t bytes, cudaStream_t stream);
 /* all-gather `bytes_per_rank` bytes per rank of device memory (NCCL or the caller's callback) */
 int exchange_allgather(m3d_ctx *ctx, const void *d_send, void *d_recv, size_t bytes_per_rank);
+/* ncclAllGather on `stream` (any stream of this context); only with a direct NCCL communicator (m3d_ctx_init_nccl) */
+bool exchange_has_nccl(const m3d_ctx *ctx);
+int exchange_allgather_nccl(m3d_ctx *ctx, const void *d_send, void *d_recv, size_t bytes_per_rank, cudaStream_t stream);
 }  // namespace m3d

@@ -491,9 +491,23 @@ struct ChunkPlan {
     const double *h_xyz = nullptr; /* the caller's buffer and its destination: the copies are issued by the fit, */
     double *d_xyz = nullptr;       /* right behind the device-side sample draw (so that the two overlap)          */
     bool copies_issued = false;
+    bool shard_upload = false; /* multi-rank fit over NCCL, one chunk: upload 1/R of the cloud, all-gather the rest */
     int issue_copies(m3d_ctx *ctx) {
         if (copies_issued) return M3D_OK;
         copies_issued = true;
+        if (shard_upload) {
+            /* every rank holds the same cloud in host memory: rank r uploads the r-th slice over its own PCIe link and
+             * the slices are all-gathered over NVLink (in place), instead of R identical 24 n-byte uploads that
+             * share the host's PCIe uplinks */
+            const size_t tot = 3 * (size_t)begin[count], R = (size_t)ctx->world;
+            const size_t S = (tot + R - 1) / R, off = S * (size_t)ctx->rank;
+            const size_t len = off < tot ? std::min(S, tot - off) : 0;
+            if (len)
+                if (int rc = host_to_device(ctx, d_xyz + off, h_xyz + off, sizeof(double) * len, ctx->copy_stream)) return rc;
+            if (int rc = exchange_allgather_nccl(ctx, d_xyz + off, d_xyz, sizeof(double) * S, ctx->copy_stream)) return rc;
+            M3D_CUDA(ctx, cudaEventRecord(ctx->ev_chunk[0], ctx->copy_stream));
+            return M3D_OK;
+        }
         for (int i = 0; i < count; ++i) {
             const size_t b = begin[i], cnt = begin[i + 1] - begin[i];
             if (cnt)
@@ -1231,7 +1245,7 @@ int fit_host_chunked(m3d_ctx *ctx, int kind, const double *xyz, const double *nr
     pl.count = want;
     const uint32_t per = (ntiles + want - 1) / want;
     for (int i = 0; i <= want; ++i) pl.begin[i] = (uint32_t)std::min<size_t>(n, (size_t)per * i * kTile);
-    M3D_CUDA(ctx, c->xyz.reserve(sizeof(double) * 3 * n));
+    M3D_CUDA(ctx, c->xyz.reserve(sizeof(double) * (3 * n + (size_t)std::max(ctx->world, 1)))); /* + all-gather padding */
     M3D_CUDA(ctx, c->pts32.reserve(sizeof(float4) * n));
     M3D_CUDA(ctx, c->blob.reserve(sizeof(float4) * ((size_t)ntiles + want) * kBlobF4));
     M3D_CUDA(ctx, c->perm.reserve(sizeof(uint32_t) * ((size_t)ntiles + want) * kTile));
@@ -1247,6 +1261,8 @@ int fit_host_chunked(m3d_ctx *ctx, int kind, const double *xyz, const double *nr
     pl.pre_models = multi;
     pl.h_xyz = xyz;
     pl.d_xyz = c->xyz.as<double>();
+    static const bool no_shard = env_is("M3D_SHARD_UPLOAD", "0");
+    pl.shard_upload = !multi && !no_shard && exchange_has_nccl(ctx) && n >= ((size_t)1 << 16);
     CloudView v{c->xyz.as<double>(), dnrm, c->pts32.as<float4>(), pl.metas, (uint32_t)n, false};
     if (!multi) v.h_nrm = nrm; /* single chunk: the cylinder's sample normals are gathered on the host, behind the DMA */
     v.blob = c->blob.as<float4>();

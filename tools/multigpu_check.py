@@ -45,6 +45,9 @@ lattice = np.round(rng.uniform(-1, 1, (60, 3)), 0)
 flat = np.c_[rng.uniform(-1, 1, (5000, 2)), np.zeros(5000)]
 cases = [(kind, lambda c, kind=kind: c.ransac_fit_cloud(kind, cs if c is single else cm, 0.01, 12000, 1.0, seed=5), f"resident kind {kind}")
          for kind in (0, 1, 2)]
+odd_xyz, odd_nrm = synth.make_c2(n=70001, seed=10)  # 3 n not divisible by the rank count: ragged upload slices
+cases += [(kind, lambda c, kind=kind: c.ransac_fit(kind, odd_xyz, odd_nrm if kind == 2 else None, 0.01, 4000, 1.0, seed=6),
+           f"host buffers, 70001 points, kind {kind} (upload sharded over the ranks + all-gather)") for kind in (0, 1, 2)]
 cases += [(0, lambda c: c.ransac_fit(0, lattice, None, 0.3, 3000, 1.0, seed=2), "ties (lattice cloud)"),
           (0, lambda c: c.ransac_fit(0, flat, None, 0.01, 2000, 1.0, seed=4), "fitness 1 stops the loop")]
 for kind, run, name in cases:
