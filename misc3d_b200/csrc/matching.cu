@@ -625,8 +625,9 @@ static int match_impl(m3d_ctx *ctx, const double *src, size_t ns, const double *
     MatchScratch *sc = ctx->d_small.as<MatchScratch>();
 
     M3D_CUDA(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
-    M3D_CUDA(ctx, cudaMemcpyAsync(A.f64, src, fa, cudaMemcpyHostToDevice, ctx->stream));
-    M3D_CUDA(ctx, cudaMemcpyAsync(B.f64, dst, fb, cudaMemcpyHostToDevice, ctx->stream));
+    /* pageable descriptor arrays (numpy / Eigen) are staged through pinned memory piece by piece (context.cu) */
+    if (int rc = host_to_device(ctx, A.f64, src, fa, ctx->stream)) return rc;
+    if (int rc = host_to_device(ctx, B.f64, dst, fb, ctx->stream)) return rc;
     M3D_CUDA(ctx, cudaMemsetAsync(sc, 0, sizeof(MatchScratch), ctx->stream));
     if (fast) {
         M3D_CUDA(ctx, cudaMemsetAsync(sc->mn, 0xff, sizeof(sc->mn), ctx->stream));
