@@ -14,6 +14,8 @@ rc, m, inl, st = ctx.ransac_fit(0, xyz, None, 0.01, 1200, 1.0, seed=5)
 print("host fit", rc, len(inl))
 t = ctx.sample_table_device(3, 5000, 4, 3000)
 print("table", None if t is None else t.shape)
+t = ctx.sample_table_device(5, 1_000_000, 3, 40_000)   # long table: jump-ahead segments (mt_jump / mt_segments kernels)
+print("long table", None if t is None else t.shape, int(t.sum()) if t is not None else 0)
 rc, planes, labels, ms = ctx.segment_plane_iterative(synth.make_c3(30000, 5), 0.01, 100, 0.1, seed=2, labels32=True)
 print("seg", rc, len(planes))
 d = synth.make_surface_pair(n=3000, seed=2)
