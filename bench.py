@@ -436,11 +436,11 @@ def main():
             except Exception as e:  # the shim is optional on the bench box
                 extras["e2e_pybind"] = {"value": None, "error": str(e)[:200]}
         if world == 1:
-            # throughput of a caller that keeps two clouds in flight: two host threads, one context (own stream and
+            # throughput of a caller that keeps three clouds in flight: three host threads, one context (own stream and
             # scratch) each, the plain synchronous m3d_ransac_fit call in both -- the upload of one thread's cloud
             # overlaps the scoring of the other's.  Same work per step as `e2e` (which stays the one-call-at-a-time number).
             import threading
-            n_ctx = 2
+            n_ctx = max(2, int(os.environ.get("M3D_BENCH_CTXS", "3")))
             ctxs = [capi.Context(local_rank) for _ in range(n_ctx)]
             bufs = [torch.empty(N_POINTS, dtype=torch.int64).pin_memory().numpy().view(np.uint64) for _ in range(n_ctx)]
 
@@ -465,7 +465,7 @@ def main():
             barrier()
             dt = time.perf_counter() - t0
             extras["e2e_concurrent"] = {"value": 3.0 * H * steps_c / dt, "unit": "hypotheses/s", "contexts": n_ctx,
-                                        "api": "m3d_ransac_fit (host buffers, pinned) called from two host threads, "
+                                        "api": f"m3d_ransac_fit (host buffers, pinned) called from {n_ctx} host threads, "
                                                "one context each"}
             for c_ in ctxs:
                 c_.close()
