@@ -193,11 +193,23 @@ __global__ void __launch_bounds__(256) icp_match_kernel(const double *__restrict
             part[8 * blockIdx.x + k] = r;
         }
 }
-__global__ void icp_mean_kernel(const double *__restrict__ part, int nparts, uint32_t ns, IcpAcc *st) {
+/* sum of the per-block partials of quantity q by warp q: lane l adds parts l, l + 32, ... in order, then a fixed
+ * shuffle tree (deterministic); thread 0 finishes */
+template <int Q>
+__device__ __forceinline__ void reduce_parts(const double *__restrict__ part, int nparts, double *__restrict__ sh) {
+    const int q = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (q < Q) {
+        double a = 0;
+        for (int k = lane; k < nparts; k += 32) a += part[Q * k + q];
+        for (int o = 16; o; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+        if (lane == 0) sh[q] = a;
+    }
+    __syncthreads();
+}
+__global__ void __launch_bounds__(256) icp_mean_kernel(const double *__restrict__ part, int nparts, uint32_t ns, IcpAcc *st) {
+    __shared__ double r[8];
+    reduce_parts<8>(part, nparts, r);
     if (threadIdx.x != 0) return;
-    double r[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    for (int k = 0; k < nparts; ++k)
-        for (int q = 0; q < 8; ++q) r[q] += part[8 * k + q];
     const unsigned long long m = (unsigned long long)(r[0] + 0.5);
     st->n_corr = m;
     st->err2 = r[1];
@@ -242,15 +254,13 @@ __global__ void __launch_bounds__(256) icp_cov_kernel(const double *__restrict__
         }
 }
 /* update = umeyama(correspondences); T <- update * T */
-__global__ void icp_update_kernel(const double *__restrict__ part, int nparts, IcpAcc *st) {
+__global__ void __launch_bounds__(288) icp_update_kernel(const double *__restrict__ part, int nparts, IcpAcc *st) {
+    __shared__ double sg[9];
+    reduce_parts<9>(part, nparts, sg);
     if (threadIdx.x != 0) return;
     double sigma[3][3], sm[3], dm[3];
     for (int r = 0; r < 3; ++r)
-        for (int c = 0; c < 3; ++c) {
-            double a = 0;
-            for (int k = 0; k < nparts; ++k) a += part[9 * k + 3 * r + c];
-            sigma[r][c] = a;
-        }
+        for (int c = 0; c < 3; ++c) sigma[r][c] = sg[3 * r + c];
     for (int a = 0; a < 3; ++a) {
         sm[a] = st->mean[a];
         dm[a] = st->mean[3 + a];
@@ -398,7 +408,7 @@ int m3d_icp_point_to_point(m3d_ctx *ctx, const double *src_xyz, size_t ns, const
         icp_match_kernel<<<nb, 256, 0, ctx->stream>>>(d_src, NS, d_dst, G, max_distance * max_distance, B.corr.as<uint32_t>(),
                                                       B.part.as<double>());
         M3D_LAUNCHED(ctx);
-        icp_mean_kernel<<<1, 32, 0, ctx->stream>>>(B.part.as<double>(), nb, NS, st);
+        icp_mean_kernel<<<1, 256, 0, ctx->stream>>>(B.part.as<double>(), nb, NS, st);
         M3D_LAUNCHED(ctx);
         return M3D_OK;
     };
@@ -411,7 +421,7 @@ int m3d_icp_point_to_point(m3d_ctx *ctx, const double *src_xyz, size_t ns, const
         if (hs->n_corr == 0) break; /* nothing to estimate from (Open3D would return an identity update) */
         icp_cov_kernel<<<nb, 256, 0, ctx->stream>>>(d_src, NS, d_dst, B.corr.as<uint32_t>(), st, B.part.as<double>());
         M3D_LAUNCHED(ctx);
-        icp_update_kernel<<<1, 32, 0, ctx->stream>>>(B.part.as<double>(), nb, st);
+        icp_update_kernel<<<1, 288, 0, ctx->stream>>>(B.part.as<double>(), nb, st);
         M3D_LAUNCHED(ctx);
         icp_transform_kernel<<<nb, 256, 0, ctx->stream>>>(d_src, NS, st->update);
         M3D_LAUNCHED(ctx);

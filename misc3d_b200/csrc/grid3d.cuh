@@ -136,12 +136,16 @@ __global__ void __launch_bounds__(256) grid_bbox_kernel(const double *__restrict
         for (int c = 0; c < 6; ++c) part[6 * blockIdx.x + c] = sh[0][c];
     }
 }
-__global__ void grid_bbox_final_kernel(const double *__restrict__ part, int nparts, double *__restrict__ out) {
-    if (threadIdx.x >= 6) return;
-    const int c = threadIdx.x;
-    double r = part[c];
-    for (int k = 1; k < nparts; ++k) r = c < 3 ? fmin(r, part[6 * k + c]) : fmax(r, part[6 * k + c]);
-    out[c] = r;
+/* 192 threads: warp c reduces component c (min / max are exact whatever the order) */
+__global__ void __launch_bounds__(192) grid_bbox_final_kernel(const double *__restrict__ part, int nparts, double *__restrict__ out) {
+    const int c = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double r = c < 3 ? INFINITY : -INFINITY;
+    for (int k = lane; k < nparts; k += 32) r = c < 3 ? fmin(r, part[6 * k + c]) : fmax(r, part[6 * k + c]);
+    for (int o = 16; o; o >>= 1) {
+        const double v = __shfl_xor_sync(0xffffffffu, r, o);
+        r = c < 3 ? fmin(r, v) : fmax(r, v);
+    }
+    if (lane == 0) out[c] = r;
 }
 __global__ void __launch_bounds__(256) grid_count_kernel(const double *__restrict__ xyz, uint32_t n, Grid3 G,
                                                          uint32_t *__restrict__ cell_id, uint32_t *__restrict__ counts) {
@@ -172,7 +176,7 @@ inline int grid_build(m3d_ctx *ctx, const double *d_xyz, uint32_t n, double radi
     double *part = B.part.as<double>(), *d_box = part + 6 * (size_t)nb;
     grid_bbox_kernel<<<nb, 256, 0, ctx->stream>>>(d_xyz, n, part);
     M3D_LAUNCHED(ctx);
-    grid_bbox_final_kernel<<<1, 32, 0, ctx->stream>>>(part, nb, d_box);
+    grid_bbox_final_kernel<<<1, 192, 0, ctx->stream>>>(part, nb, d_box);
     M3D_LAUNCHED(ctx);
     double box[6];
     M3D_CUDA(ctx, cudaMemcpyAsync(box, d_box, sizeof box, cudaMemcpyDeviceToHost, ctx->stream));

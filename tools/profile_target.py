@@ -1,5 +1,5 @@
 """ncu target.  `ransac` (default): one warm + one measured RANSAC fit per primitive on the C2 cloud
-(10k hypotheses, 1M points).  `c4`: match_correspondence + compute_transformation_ransac at C4 size."""
+(10k hypotheses, 1M points).  `c4`: match_correspondence + compute_transformation_ransac at C4 size.  `feat`: FPFH + ICP at 200k points."""
 import os
 import sys
 
@@ -27,6 +27,17 @@ elif what == "stats":  # work counters of the scoring kernel (statistics build, 
         s["lane_slots"] = 32 * s["passes_1"] + 64 * s["passes_2"]
         s["lane_efficiency"] = s["cell_pairs"] / max(s["lane_slots"], 1)
         print(kind, st["score_ms"], json.dumps(s))
+elif what == "feat":  # FPFH (f3) + ICP (f4) at 200k points
+    import numpy as np
+    dp = synth.make_surface_pair(n=200000, seed=2, sigma=0.0005)
+    for rep in range(2):
+        f, ms = ctx.compute_fpfh(dp["src"], dp["src_nrm"], 0.03, 100)
+        print("fpfh", rep, ms)
+    T0 = dp["T_true"].copy()
+    T0[:3, 3] += 0.01
+    for rep in range(2):
+        T, fit, rmse, it = ctx.icp_point_to_point(dp["src"], dp["dst"], 0.02, T0, 30)
+        print("icp", rep, it, fit, rmse)
 else:
     d = synth.make_c4()
     for rep in range(3):
