@@ -304,17 +304,20 @@ __global__ void __launch_bounds__(THREADS + 32, CellCfg<THREADS>::kMinBlocks) sc
             if (lane == 0) surv_cnt[(k + 1) & 1] = 0;
             else surv_next[(k + 1) & 1] = 0;
         }
-        for (;;) {
-            uint32_t i0 = 0;
-            if (lane == 0) i0 = atomicAdd(&surv_next[k & 1], 4u);
-            i0 = __shfl_sync(fullmask, i0, 0);
-            if (i0 >= total) break;
+        /* four survivors per trip, dealt to the warps statically: every trip costs the same 4 x 32 cell tests, and a
+         * claim through a shared-memory cursor would put an atomic round trip in front of ~70 instructions of work */
+        static_assert(NH % 4 == 0, "survivor quads are read with one 64-bit load");
+        uint2 ids = make_uint2(0u, 0u);
+        if (4u * warp < total) ids = *reinterpret_cast<const uint2 *>(surv + 4u * warp);
+        for (uint32_t i0 = 4u * warp; i0 < total; i0 += 4u * WARPS) {
+            const uint32_t e[4] = {ids.x & 0xffffu, ids.x >> 16, ids.y & 0xffffu, ids.y >> 16};
+            if (i0 + 4u * WARPS < total) ids = *reinterpret_cast<const uint2 *>(surv + i0 + 4u * WARPS); /* next trip's */
 #pragma unroll
             for (int half = 0; half < 2; ++half) { /* two hypotheses per trip for instruction-level parallelism */
                 const uint32_t i = i0 + 2 * half;
                 if (i >= total) break;
-                const uint32_t h0 = surv[i];
-                const uint32_t h1 = (i + 1 < total) ? (uint32_t)surv[i + 1] : (uint32_t)NH;
+                const uint32_t h0 = e[2 * half];
+                const uint32_t h1 = (i + 1 < total) ? e[2 * half + 1] : (uint32_t)NH;
                 Fast<KIND> g0, g1;
                 CullP k0, k1;
                 load_fast_cull<KIND, NH>(hyp, h0, g0, k0);
@@ -350,11 +353,14 @@ __global__ void __launch_bounds__(THREADS + 32, CellCfg<THREADS>::kMinBlocks) sc
             ccnt[((k + 1) & 1) * kTileCells + lane] = 0;
             if (lane == 0) unit_next[(k + 1) & 1] = 0;
         }
-        for (;;) {
-            uint32_t u = 0;
-            if (lane == 0) u = atomicAdd(&unit_next[k & 1], 1u);
-            u = __shfl_sync(fullmask, u, 0);
-            if (u >= units) break;
+        /* units are claimed one ahead: the cursor's atomic round trip for the next unit is in flight while this one
+         * is evaluated (every warp ends up claiming one unit past the end; the cursor is reset per tile) */
+        uint32_t u = 0;
+        if (lane == 0) u = atomicAdd(&unit_next[k & 1], 1u);
+        u = __shfl_sync(fullmask, u, 0);
+        while (u < units) {
+            uint32_t u_next = 0;
+            if (lane == 0) u_next = atomicAdd(&unit_next[k & 1], 1u);
             const uint32_t c = __popc(__ballot_sync(fullmask, inc <= u)); /* first cell whose units reach past u */
             const uint32_t off = (u - __shfl_sync(fullmask, inc - mypass, c)) * 64;
             const uint32_t rem = __shfl_sync(fullmask, mycnt, c) - off;
@@ -407,6 +413,7 @@ __global__ void __launch_bounds__(THREADS + 32, CellCfg<THREADS>::kMinBlocks) sc
                 if (c0) atomicAdd(&scnt[h0], c0);
                 if (STATS) st_p1++;
             }
+            u = __shfl_sync(fullmask, u_next, 0);
         }
     };
 
