@@ -91,10 +91,13 @@ int m3d_probe_fp64_dfma(m3d_ctx *ctx, double *dfma_per_s);
  * from these. */
 int m3d_score_stats(m3d_ctx *ctx, uint64_t out[8]);
 
-/* -------- multi-GPU: hypothesis sharding.  rank r scores hypotheses
- * [r*ceil(H/R), (r+1)*ceil(H/R)) of the SAME global sample table; one all-gather of the per-
- * hypothesis inlier counts; then every rank replays the identical ordered scan, so results do
- * not depend on R. */
+/* -------- multi-GPU: hypothesis sharding.  Every rank calls the fit with the SAME cloud
+ * and parameters; a wave of hypotheses of the one global sample table is dealt to the ranks in cyclic
+ * blocks of 256 rows (m3d_shard_rows).  probability == 1: one all-gather of a 64-byte best record per
+ * rank; probability < 1: one all-gather of the per-hypothesis inlier counts per wave; then every rank
+ * finishes identically, so results do not depend on R.  With a communicator from m3d_ctx_init_nccl,
+ * m3d_ransac_fit also uploads the (replicated) host cloud cooperatively: rank r copies the r-th 1/R
+ * slice over its own PCIe link and the slices are all-gathered over NVLink. */
 #define M3D_NCCL_ID_BYTES 128
 int m3d_nccl_unique_id(char id[M3D_NCCL_ID_BYTES]);
 int m3d_ctx_init_nccl(m3d_ctx *ctx, const char id[M3D_NCCL_ID_BYTES], int rank, int world);
