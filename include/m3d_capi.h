@@ -295,6 +295,14 @@ int m3d_icp_point_to_point(m3d_ctx *ctx, const double *src_xyz, size_t ns, const
 int m3d_least_squares_transform(m3d_ctx *ctx, const double *src_xyz, const double *dst_xyz,
                                 size_t n, int with_scaling, double *T_out);
 
+/* Extension (the reference has no such step): LeastSquareSolver applied behind RANSACSolver --
+ * Eigen::umeyama (src/transform_estimation.cpp:49-66) over the correspondences (c0[i], c1[i]) that are inliers
+ * of T_in, |T_in s - d|^2 < threshold^2, taken in correspondence order.  T_in / T_out 4x4 row-major;
+ * *n_inliers (may be NULL) = pairs used.  Fewer than 3 inliers: T_out = T_in. */
+int m3d_registration_refit(m3d_ctx *ctx, const double *src_xyz, size_t ns, const double *dst_xyz, size_t nd,
+                           const size_t *c0, const size_t *c1, size_t m, const double *T_in, double threshold,
+                           int with_scaling, double *T_out, size_t *n_inliers);
+
 #ifdef __cplusplus
 }
 #endif

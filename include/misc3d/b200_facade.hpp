@@ -376,6 +376,23 @@ private:
     bool has_seed_ = false;
 };
 
+/* Extension (not in the reference): LeastSquareSolver applied behind RANSACSolver -- Umeyama over the correspondences
+ * that are inliers of T (|T s - d| < threshold), on the device.  Returns T unchanged when fewer than 3 are. */
+inline Matrix4d RefineOnInlierCorrespondences(const PointCloud &src, const PointCloud &dst,
+                                              const std::pair<std::vector<size_t>, std::vector<size_t>> &corres,
+                                              const Matrix4d &T, double threshold, bool scaling = false,
+                                              size_t *n_inliers = nullptr) {
+    if (corres.first.size() != corres.second.size()) LogError("Correspondence lists differ in length");
+    m3d_ctx *ctx = b200::DefaultContext();
+    Matrix4d out{};
+    const int rc = m3d_registration_refit(
+        ctx, src.points_.empty() ? nullptr : src.points_[0].data(), src.points_.size(),
+        dst.points_.empty() ? nullptr : dst.points_[0].data(), dst.points_.size(), corres.first.data(),
+        corres.second.data(), corres.first.size(), T.data(), threshold, scaling ? 1 : 0, out.data(), n_inliers);
+    if (rc != M3D_OK) b200::Raise(ctx);
+    return out;
+}
+
 /* The Open3D calls that surround the path in the reference's callers (examples/cpp/transform_estimation.cpp:20-33,
  * 82-86): not Misc3D API, offered so that descriptors and the refinement need not leave the GPU build. */
 /* open3d::pipelines::registration::ComputeFPFHFeature(cloud, KDTreeSearchParamHybrid(radius, max_nn)):

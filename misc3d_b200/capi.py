@@ -31,7 +31,7 @@ EXPORTS = [
     "m3d_cloud_upload", "m3d_cloud_from_device", "m3d_cloud_free", "m3d_cloud_size",
     "m3d_ransac_fit_cloud", "m3d_score_samples", "m3d_evaluate_model", "m3d_sample_table",
     "m3d_ordered_scan", "m3d_segment_plane_iterative", "m3d_match_correspondence", "m3d_nearest",
-    "m3d_ransac_registration", "m3d_least_squares_transform", "m3d_shard_rows", "m3d_sample_table_device", "m3d_score_stats",
+    "m3d_ransac_registration", "m3d_least_squares_transform", "m3d_registration_refit", "m3d_shard_rows", "m3d_sample_table_device", "m3d_score_stats",
     "m3d_knn_create", "m3d_knn_free", "m3d_knn_search", "m3d_segment_plane_iterative_u32",
     "m3d_compute_fpfh", "m3d_icp_point_to_point",
 ]
@@ -455,3 +455,21 @@ class Context:
         self._check(lib().m3d_least_squares_transform(self.h, _p(src), _p(dst), C.c_size_t(len(src)),
                                                       C.c_int(1 if with_scaling else 0), _p(T)))
         return T.reshape(4, 4).copy()
+
+    def registration_refit(self, src, dst, idx0, idx1, T, threshold, with_scaling=False):
+        """Extension: least-squares (Umeyama) refit of T on its inlier correspondences.
+        Returns (T_refit[4,4], n_inliers)."""
+        src = _f64(src).reshape(-1, 3)
+        dst = _f64(dst).reshape(-1, 3)
+        c0 = np.ascontiguousarray(idx0, dtype=np.uint64)
+        c1 = np.ascontiguousarray(idx1, dtype=np.uint64)
+        if len(c0) != len(c1):
+            raise ValueError("correspondence index arrays differ in length")
+        Tin = _f64(T).reshape(16)
+        Tout = np.zeros(16)
+        n_inl = C.c_size_t(0)
+        self._check(lib().m3d_registration_refit(self.h, _p(src), C.c_size_t(len(src)), _p(dst), C.c_size_t(len(dst)),
+                                                 _p(c0, C.c_size_t), _p(c1, C.c_size_t), C.c_size_t(len(c0)), _p(Tin),
+                                                 C.c_double(threshold), C.c_int(1 if with_scaling else 0), _p(Tout),
+                                                 C.byref(n_inl)))
+        return Tout.reshape(4, 4).copy(), int(n_inl.value)

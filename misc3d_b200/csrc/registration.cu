@@ -506,7 +506,78 @@ __global__ void lsq_final_kernel(const double *part, int nparts, uint32_t n, con
     for (int i = 0; i < 16; ++i) T[i] = Tl[i];
 }
 
+/* ---- refit on the inlier correspondences (LeastSquareSolver as the optional step behind RANSACSolver).
+ * One CTA: thread t owns a contiguous run of correspondences, so the selected pairs keep correspondence order
+ * (fixed-order sums downstream).  A pair is an inlier when |T s - d|^2 < thr^2 (Open3D's max_correspondence_distance
+ * test), T applied like pcd.Transform (divide by the homogeneous coordinate). */
+__global__ void __launch_bounds__(1024) refit_select_kernel(const double *__restrict__ src, const double *__restrict__ dst,
+                                                            const uint32_t *__restrict__ c0, const uint32_t *__restrict__ c1,
+                                                            uint32_t m, const double *__restrict__ T, double thr2,
+                                                            double *__restrict__ out_s, double *__restrict__ out_d,
+                                                            uint32_t *__restrict__ count) {
+    __shared__ uint32_t warp_tot[32];
+    double t[16];
+    for (int q = 0; q < 16; ++q) t[q] = T[q];
+    const uint32_t per = (m + blockDim.x - 1) / blockDim.x;
+    const uint32_t b = min(m, threadIdx.x * per), e = min(m, b + per);
+    auto inlier = [&](uint32_t i) {
+        const double *sp = src + 3 * (size_t)c0[i], *dp = dst + 3 * (size_t)c1[i];
+        const double x = sp[0], y = sp[1], z = sp[2];
+        const double w = ((t[12] * x + t[13] * y) + t[14] * z) + t[15];
+        const double dx = (((t[0] * x + t[1] * y) + t[2] * z) + t[3]) / w - dp[0];
+        const double dy = (((t[4] * x + t[5] * y) + t[6] * z) + t[7]) / w - dp[1];
+        const double dz = (((t[8] * x + t[9] * y) + t[10] * z) + t[11]) / w - dp[2];
+        return (dx * dx + dy * dy) + dz * dz < thr2;
+    };
+    uint32_t mine = 0;
+    for (uint32_t i = b; i < e; ++i) mine += inlier(i) ? 1u : 0u;
+    /* exclusive scan of `mine` over the block */
+    const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+    uint32_t inc = mine;
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += v;
+    }
+    if (lane == 31) warp_tot[wp] = inc;
+    __syncthreads();
+    if (wp == 0) {
+        uint32_t v = warp_tot[lane], r = v;
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t u = __shfl_up_sync(0xffffffffu, r, o);
+            if (lane >= o) r += u;
+        }
+        warp_tot[lane] = r - v; /* exclusive */
+        if (lane == 31) *count = r;
+    }
+    __syncthreads();
+    uint32_t pos = warp_tot[wp] + inc - mine;
+    for (uint32_t i = b; i < e; ++i)
+        if (inlier(i)) {
+            const double *sp = src + 3 * (size_t)c0[i], *dp = dst + 3 * (size_t)c1[i];
+            for (int a = 0; a < 3; ++a) {
+                out_s[3 * (size_t)pos + a] = sp[a];
+                out_d[3 * (size_t)pos + a] = dp[a];
+            }
+            ++pos;
+        }
+}
+
 /* ------------------------------------------------------------------------------ host side */
+/* Eigen::umeyama over n dense pairs already on the device; part = scratch of 10 nb + 32 doubles, the 4x4 result is
+ * left at part + 10 nb + 8 (row-major) */
+static int lsq_on_device(m3d_ctx *ctx, const double *d_s, const double *d_d, uint32_t n, int nb, int with_scaling, double *part) {
+    double *mean = part + 10 * (size_t)nb, *dT = mean + 8;
+    lsq_mean_kernel<<<nb, 256, 0, ctx->stream>>>(d_s, d_d, n, part);
+    M3D_LAUNCHED(ctx);
+    lsq_mean_final_kernel<<<1, 32, 0, ctx->stream>>>(part, nb, n, mean);
+    M3D_LAUNCHED(ctx);
+    lsq_cov_kernel<<<nb, 256, 0, ctx->stream>>>(d_s, d_d, n, mean, part);
+    M3D_LAUNCHED(ctx);
+    lsq_final_kernel<<<1, 32, 0, ctx->stream>>>(part, nb, n, mean, with_scaling, dT);
+    M3D_LAUNCHED(ctx);
+    return M3D_OK;
+}
+
 /* est_k update on improvement (Open3D): (int)ceil of a non-finite value is UB in the reference --
  * emulated as INT_MIN, which is what x86-64 yields */
 static int reg_update_limit(uint64_t good, size_t m, double confidence, int est_k) {
@@ -779,15 +850,60 @@ int m3d_least_squares_transform(m3d_ctx *ctx, const double *src_xyz, const doubl
     double *mean = part + 10 * (size_t)nb, *dT = mean + 8;
     M3D_CUDA(ctx, cudaMemcpyAsync(ctx->d_tmp0.p, src_xyz, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, ctx->stream));
     M3D_CUDA(ctx, cudaMemcpyAsync(ctx->d_tmp1.p, dst_xyz, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, ctx->stream));
-    lsq_mean_kernel<<<nb, 256, 0, ctx->stream>>>(ctx->d_tmp0.as<double>(), ctx->d_tmp1.as<double>(), (uint32_t)n, part);
-    M3D_LAUNCHED(ctx);
-    lsq_mean_final_kernel<<<1, 32, 0, ctx->stream>>>(part, nb, (uint32_t)n, mean);
-    M3D_LAUNCHED(ctx);
-    lsq_cov_kernel<<<nb, 256, 0, ctx->stream>>>(ctx->d_tmp0.as<double>(), ctx->d_tmp1.as<double>(), (uint32_t)n, mean, part);
-    M3D_LAUNCHED(ctx);
-    lsq_final_kernel<<<1, 32, 0, ctx->stream>>>(part, nb, (uint32_t)n, mean, with_scaling, dT);
-    M3D_LAUNCHED(ctx);
+    if (int rc = lsq_on_device(ctx, ctx->d_tmp0.as<double>(), ctx->d_tmp1.as<double>(), (uint32_t)n, nb, with_scaling, part)) return rc;
     M3D_CUDA(ctx, cudaMemcpyAsync(T_out, dT, sizeof(double) * 16, cudaMemcpyDeviceToHost, ctx->stream));
+    M3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return M3D_OK;
+}
+
+int m3d_registration_refit(m3d_ctx *ctx, const double *src_xyz, size_t ns, const double *dst_xyz, size_t nd,
+                           const size_t *c0, const size_t *c1, size_t m, const double *T_in, double threshold,
+                           int with_scaling, double *T_out, size_t *n_inliers) {
+    if (!ctx || !T_in || !T_out) return M3D_ERR_INVALID_ARG;
+    for (int i = 0; i < 16; ++i) T_out[i] = T_in[i];
+    if (n_inliers) *n_inliers = 0;
+    if (m == 0) return M3D_OK;
+    if (!src_xyz || !dst_xyz || !c0 || !c1) return ctx->fail(M3D_ERR_INVALID_ARG, "null array");
+    if (!(threshold > 0.0)) return ctx->fail(M3D_ERR_INVALID_ARG, "threshold must be positive");
+    if (m >= (1ull << 31) || ns >= (1ull << 32) || nd >= (1ull << 32))
+        return ctx->fail(M3D_ERR_INVALID_ARG, "too many points / correspondences");
+    for (size_t i = 0; i < m; ++i)
+        if (c0[i] >= ns || c1[i] >= nd) return ctx->fail(M3D_ERR_INVALID_ARG, "correspondence %zu out of range", i);
+    M3D_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int nb = std::max(1, std::min<int>(ctx->sm_count * 4, (int)((m + 255) / 256)));
+    M3D_CUDA(ctx, ctx->d_tmp0.reserve(sizeof(double) * 3 * m)); /* selected source points      */
+    M3D_CUDA(ctx, ctx->d_tmp1.reserve(sizeof(double) * 3 * m)); /* selected destination points */
+    M3D_CUDA(ctx, ctx->d_tmp2.reserve(sizeof(uint32_t) * 2 * m));
+    M3D_CUDA(ctx, ctx->d_tmp3.reserve(sizeof(double) * 3 * ns));
+    M3D_CUDA(ctx, ctx->d_tmp5.reserve(sizeof(double) * 3 * nd));
+    M3D_CUDA(ctx, ctx->d_part.reserve(sizeof(double) * (10 * (size_t)nb + 64)));
+    M3D_CUDA(ctx, ctx->h_small.reserve(64));
+    double *part = ctx->d_part.as<double>();
+    double *mean = part + 10 * (size_t)nb, *dT = mean + 8, *dTin = dT + 16;
+    uint32_t *d_count = reinterpret_cast<uint32_t *>(dTin + 16);
+    std::vector<uint32_t> hc(2 * m);
+    for (size_t i = 0; i < m; ++i) {
+        hc[i] = (uint32_t)c0[i];
+        hc[m + i] = (uint32_t)c1[i];
+    }
+    M3D_CUDA(ctx, cudaMemcpyAsync(ctx->d_tmp3.p, src_xyz, sizeof(double) * 3 * ns, cudaMemcpyHostToDevice, ctx->stream));
+    M3D_CUDA(ctx, cudaMemcpyAsync(ctx->d_tmp5.p, dst_xyz, sizeof(double) * 3 * nd, cudaMemcpyHostToDevice, ctx->stream));
+    M3D_CUDA(ctx, cudaMemcpyAsync(ctx->d_tmp2.p, hc.data(), sizeof(uint32_t) * 2 * m, cudaMemcpyHostToDevice, ctx->stream));
+    M3D_CUDA(ctx, cudaMemcpyAsync(dTin, T_in, sizeof(double) * 16, cudaMemcpyHostToDevice, ctx->stream));
+    refit_select_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->d_tmp3.as<double>(), ctx->d_tmp5.as<double>(),
+                                                     ctx->d_tmp2.as<uint32_t>(), ctx->d_tmp2.as<uint32_t>() + m, (uint32_t)m,
+                                                     dTin, threshold * threshold, ctx->d_tmp0.as<double>(),
+                                                     ctx->d_tmp1.as<double>(), d_count);
+    M3D_LAUNCHED(ctx);
+    uint32_t *h_count = ctx->h_small.as<uint32_t>();
+    M3D_CUDA(ctx, cudaMemcpyAsync(h_count, d_count, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    M3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); /* also: hc may go out of scope now */
+    const uint32_t k = *h_count;
+    if (n_inliers) *n_inliers = k;
+    if (k < 3) return M3D_OK; /* nothing to estimate from: the transformation is returned unchanged */
+    const int nbk = std::max(1, std::min<int>(nb, (int)((k + 255) / 256)));
+    if (int rc = lsq_on_device(ctx, ctx->d_tmp0.as<double>(), ctx->d_tmp1.as<double>(), k, nbk, with_scaling, part)) return rc;
+    M3D_CUDA(ctx, cudaMemcpyAsync(T_out, part + 10 * (size_t)nbk + 8, sizeof(double) * 16, cudaMemcpyDeviceToHost, ctx->stream));
     M3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return M3D_OK;
 }

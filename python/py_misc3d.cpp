@@ -276,7 +276,29 @@ PYBIND11_MODULE(py_misc3d, m) {
         "numpy arrays with shape (n, 3))",
         py::arg("src"), py::arg("dst"), py::arg("scaling") = false);
 
-    /* extensions (not in the reference's module): the Open3D steps its callers run around this path, on the GPU */
+    /* extensions (not in the reference's module) */
+    reg.def(
+        "refine_transformation_on_inliers",
+        [](const py::object &src, const py::object &dst,
+           const std::pair<std::vector<size_t>, std::vector<size_t>> &corres, const py::array_t<double> &T,
+           double threshold, bool scaling) {
+            PointCloud s = cloud_from_py(src), d = cloud_from_py(dst);
+            if (T.ndim() != 2 || T.shape(0) != 4 || T.shape(1) != 4) throw py::value_error("T must have shape (4, 4)");
+            Matrix4d Tin{};
+            for (int r = 0; r < 4; ++r)
+                for (int c = 0; c < 4; ++c) Tin.data()[4 * r + c] = T.at(r, c);
+            Matrix4d out;
+            {
+                py::gil_scoped_release nogil;
+                out = registration::RefineOnInlierCorrespondences(s, d, corres, Tin, threshold, scaling);
+            }
+            return mat4(out);
+        },
+        "Least-squares (Umeyama) refit of a transformation on the correspondences that are its inliers "
+        "(|T src - dst| < threshold), on the GPU",
+        py::arg("src"), py::arg("dst"), py::arg("corres"), py::arg("T"), py::arg("threshold") = 0.01,
+        py::arg("scaling") = false);
+    /* ... and the Open3D steps the reference's callers run around this path, on the GPU */
     reg.def(
         "compute_fpfh_feature",
         [](const py::object &pcd, double radius, int max_nn) {

@@ -86,3 +86,6 @@ def test_registration_chain(m3d, orc):
     assert T.shape == (4, 4) and np.linalg.norm(T - oT) <= 1e-5
     Tl = m3d.registration.compute_transformation_least_square(d["src"][o0.astype(int)], d["dst"][o1.astype(int)])
     assert np.linalg.norm(Tl - orc.umeyama(d["src"][o0.astype(int)], d["dst"][o1.astype(int)])) <= 1e-9
+    # extension: least-squares refit on the inlier correspondences of the RANSAC result
+    Tr = m3d.registration.refine_transformation_on_inliers(FakeO3DCloud(d["src"]), FakeO3DCloud(d["dst"]), corres, T, 0.02)
+    assert Tr.shape == (4, 4) and np.linalg.norm(Tr - d["T_true"]) <= np.linalg.norm(T - d["T_true"]) + 1e-12

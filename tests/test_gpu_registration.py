@@ -130,3 +130,30 @@ def test_gpu_agrees_with_the_independent_numpy_restatement(ctx, capi, orc):
     for k in ("best_index", "best_count", "evaluated", "stop_index"):
         assert gst[k] == st[k], (k, gst, st)
     np.testing.assert_allclose(gT, T, rtol=0, atol=1e-9)
+
+
+@pytest.mark.parametrize("scaling", [False, True])
+def test_refit_on_inlier_correspondences(ctx, capi, orc, scaling):
+    """extension f2: Umeyama over the correspondences that are inliers of T (correspondence order), against numpy"""
+    d = synth.make_c4(n=20000, seed=5)
+    i0, i1, ms = ctx.match_correspondence(d["src_feat"], d["dst_feat"])
+    rc, T, st = ctx.ransac_registration(d["src"], d["dst"], i0, i1, 0.02, 2000, 0.9, 1.0, 1)
+    assert rc == 1
+    T2, n_inl = ctx.registration_refit(d["src"], d["dst"], i0, i1, T, 0.02, scaling)
+    s = d["src"][i0.astype(np.int64)]
+    q = d["dst"][i1.astype(np.int64)]
+    p = s @ T[:3, :3].T + T[:3, 3]
+    d2 = ((p - q) ** 2).sum(1)
+    inl = d2 < 0.02 ** 2
+    near = np.abs(d2 - 0.02 ** 2) < 1e-12          # pairs a different operation order could flip
+    assert abs(int(inl.sum()) - n_inl) <= int(near.sum())
+    if not near.any():
+        oT = orc.umeyama(s[inl], q[inl], scaling)
+        assert np.linalg.norm(T2 - oT) <= 1e-9
+    # closer to the truth than the 3-point RANSAC estimate, and all of it a rigid (or similarity) transform
+    assert np.linalg.norm(T2 - d["T_true"]) <= np.linalg.norm(T - d["T_true"]) + 1e-12
+    # fewer than three inliers: the input comes back
+    T3, n3 = ctx.registration_refit(d["src"], d["dst"], i0, i1, np.eye(4), 1e-9, scaling)
+    assert n3 < 3 and np.array_equal(T3, np.eye(4))
+    T4, n4 = ctx.registration_refit(d["src"], d["dst"], i0[:0], i1[:0], T, 0.02, scaling)
+    assert n4 == 0 and np.array_equal(T4, T)
