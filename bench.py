@@ -414,6 +414,18 @@ def main():
         pg_buf = np.empty(N_POINTS, dtype=np.uint64)
         v, _ = timed_e2e(lambda seed: step_e2e(seed, pg_xyz, pg_nrm, pg_buf), n_warm=1)
         extras["e2e_pageable"] = {"value": v, "unit": "hypotheses/s", "api": "m3d_ransac_fit (host buffers, pageable numpy arrays)"}
+        # the same arrays page-locked in place by the library on first use (M3D_FLAG_REGISTER_HOST): what a caller that
+        # fits the same cloud repeatedly can ask for
+        def step_reg(seed):
+            for kind in KINDS:
+                ctx.ransac_fit(kind, pg_xyz, pg_nrm if kind == 2 else None, THR, H, 1.0, seed=seed + kind,
+                               inl_buf=pg_buf if want_inl else None, want_inliers=want_inl, flags=capi.FLAG_REGISTER_HOST)
+            return 0
+        v, _ = timed_e2e(step_reg, n_warm=1)
+        ctx.host_unregister_all()
+        extras["e2e_pageable_registered"] = {"value": v, "unit": "hypotheses/s",
+                                             "api": "m3d_ransac_fit (pageable numpy arrays, M3D_FLAG_REGISTER_HOST: "
+                                                    "page-locked in place on first use)"}
         if world == 1:
             try:   # the reference-facing python call: misc3d.common.fit_* (pybind11 shim over the C++ facade)
                 sys.path.insert(0, os.path.join(ROOT, "python"))

@@ -91,6 +91,9 @@ int m3d_probe_fp64_dfma(m3d_ctx *ctx, double *dfma_per_s);
  * from these. */
 int m3d_score_stats(m3d_ctx *ctx, uint64_t out[8]);
 
+/* drops every host-buffer registration made under M3D_FLAG_REGISTER_HOST (also done by m3d_ctx_destroy) */
+void m3d_host_unregister_all(m3d_ctx *ctx);
+
 /* -------- multi-GPU: hypothesis sharding.  Every rank calls the fit with the SAME cloud
  * and parameters; a wave of hypotheses of the one global sample table is dealt to the ranks in cyclic
  * blocks of 256 rows (m3d_shard_rows).  probability == 1: one all-gather of a 64-byte best record per
@@ -128,6 +131,11 @@ typedef struct m3d_ransac_params {
 #define M3D_FLAG_CHUNKED_UPLOAD 32u /* m3d_ransac_fit, pinned buffers, probability 1: score the cloud chunk by chunk behind
                                        its upload (experimental: measured slower than the default) */
 #define M3D_FLAG_PLAIN_UPLOAD 64u   /* m3d_ransac_fit: upload, prepare, then fit, all on one stream (the round-1 path) */
+#define M3D_FLAG_REGISTER_HOST 128u /* m3d_ransac_fit: page-lock the caller's (pageable) xyz buffer in place with
+                                      * cudaHostRegister the first time it is seen, so that this and later fits of the
+                                      * same buffer upload by DMA at the pinned rate.  The registration lives until
+                                      * m3d_host_unregister_all / m3d_ctx_destroy; THE CALLER KEEPS THE BUFFER ALLOCATED
+                                      * UNTIL THEN.  Without the flag pageable buffers are staged through pinned memory */
 #define M3D_FLAG_STATS 16u     /* run the counting build of the scoring kernel (slower); read with m3d_score_stats */
 
 typedef struct m3d_ransac_stats {

@@ -18,7 +18,7 @@ KSAMPLE = {PLANE: 3, SPHERE: 4, CYLINDER: 2}
 NPARAM = {PLANE: 4, SPHERE: 4, CYLINDER: 7}
 MATCH_FLANN, MATCH_ANNOY = 0, 1
 FLAG_EXACT_ONLY, FLAG_NO_REFIT, FLAG_DENSE, FLAG_CLASSIFY, FLAG_STATS = 1, 2, 4, 8, 16
-FLAG_CHUNKED_UPLOAD, FLAG_PLAIN_UPLOAD = 32, 64
+FLAG_CHUNKED_UPLOAD, FLAG_PLAIN_UPLOAD, FLAG_REGISTER_HOST = 32, 64, 128
 
 OK = 0
 ERR_INVALID_ARG, ERR_TOO_FEW_POINTS, ERR_PROBABILITY, ERR_NO_NORMALS = -1, -2, -3, -4
@@ -31,7 +31,7 @@ EXPORTS = [
     "m3d_cloud_upload", "m3d_cloud_from_device", "m3d_cloud_free", "m3d_cloud_size",
     "m3d_ransac_fit_cloud", "m3d_score_samples", "m3d_evaluate_model", "m3d_sample_table",
     "m3d_ordered_scan", "m3d_segment_plane_iterative", "m3d_match_correspondence", "m3d_nearest",
-    "m3d_ransac_registration", "m3d_least_squares_transform", "m3d_registration_refit", "m3d_shard_rows", "m3d_sample_table_device", "m3d_score_stats",
+    "m3d_ransac_registration", "m3d_least_squares_transform", "m3d_registration_refit", "m3d_host_unregister_all", "m3d_shard_rows", "m3d_sample_table_device", "m3d_score_stats",
     "m3d_knn_create", "m3d_knn_free", "m3d_knn_search", "m3d_segment_plane_iterative_u32",
     "m3d_compute_fpfh", "m3d_icp_point_to_point",
 ]
@@ -237,6 +237,10 @@ class Context:
         v = C.c_double(0)
         self._check(lib().m3d_probe_fp64_dfma(self.h, C.byref(v)))
         return float(v.value)
+
+    def host_unregister_all(self):
+        """drop the cudaHostRegister registrations made by fits with FLAG_REGISTER_HOST"""
+        lib().m3d_host_unregister_all(self.h)
 
     def score_stats(self):
         """work counters of the launches run with FLAG_STATS since the last call (m3d_score_stats)"""

@@ -347,10 +347,21 @@ int m3d_ctx_create_on_stream(int device, void *cuda_stream, m3d_ctx **out) {
     return ctx_create_impl(device, cuda_stream, false, out);
 }
 
+void m3d_host_unregister_all(m3d_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
+    for (auto &r : c->registered)
+        if (cudaHostUnregister(const_cast<void *>(r.first)) != cudaSuccess) cudaGetLastError();
+    c->registered.clear();
+}
+
 void m3d_ctx_destroy(m3d_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    m3d_host_unregister_all(c);
     if (c->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->nccl_comm);
     if (c->scratch_cloud) m3d_cloud_free(c->scratch_cloud);
     DevBuf *db[] = {&c->d_samples, &c->d_counts, &c->d_counts_all, &c->d_blk, &c->d_part, &c->d_small,

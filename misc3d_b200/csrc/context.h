@@ -10,6 +10,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <utility>
+#include <vector>
 
 #include "../../include/m3d_capi.h"
 
@@ -94,6 +96,7 @@ struct m3d_ctx {
 
     /* scratch (grow-only) */
     m3d::DevBuf d_samples, d_counts, d_counts_all, d_blk, d_part, d_small, d_inl, d_models, d_valid;
+    std::vector<std::pair<const void *, size_t>> registered; /* caller buffers page-locked under M3D_FLAG_REGISTER_HOST */
     m3d::DevBuf d_tmp0, d_tmp1, d_tmp2, d_tmp3, d_tmp4, d_tmp5, d_queue, d_tiles, d_rownrm, d_rowmap, d_recs, d_draw, d_mtjump;
     m3d::PinBuf h_samples, h_counts, h_small, h_stage, h_rownrm;
     m3d_cloud *scratch_cloud = nullptr; /* staging cloud of the host-buffer entry points */

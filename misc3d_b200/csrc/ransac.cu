@@ -1322,6 +1322,16 @@ int m3d_ransac_fit(m3d_ctx *ctx, int kind, const double *xyz, const double *nrm,
     if (int rc = check_params(ctx, kind, n, nrm != nullptr, p)) return rc;
     if (n >= (size_t)kInvalidBit) return ctx->fail(M3D_ERR_INVALID_ARG, "clouds of >= 2^31 points are not supported");
     M3D_CUDA(ctx, cudaSetDevice(ctx->device));
+    if ((p->flags & M3D_FLAG_REGISTER_HOST) && n) { /* page-lock the caller's cloud in place (once per buffer) */
+        cudaPointerAttributes at{};
+        if (cudaPointerGetAttributes(&at, xyz) != cudaSuccess) cudaGetLastError();
+        else if (at.type == cudaMemoryTypeUnregistered) {
+            if (cudaHostRegister(const_cast<double *>(xyz), sizeof(double) * 3 * n, cudaHostRegisterDefault) == cudaSuccess)
+                ctx->registered.emplace_back(xyz, sizeof(double) * 3 * n);
+            else
+                cudaGetLastError(); /* e.g. a read-only mapping: the staged upload still works */
+        }
+    }
     {
         const int rc = fit_host_chunked(ctx, kind, xyz, nrm, n, p, model_out, inl_out, n_inl, stats);
         if (rc != kRetryUnchunked) return rc;

@@ -581,3 +581,22 @@ def test_chunked_pinned_fit_falls_back_on_nonfinite_points(ctx, capi, orc):
     for flags in (0, capi.FLAG_CHUNKED_UPLOAD):
         rc, model, inl, st = ctx.ransac_fit(capi.PLANE, pxyz, None, 0.01, 300, 1.0, seed=2, flags=flags)
         assert rc == orc_rc and np.array_equal(inl, oinl) and st["best_index"] == ost["best_index"]
+
+
+def test_registered_host_buffer_fit_parity(ctx, capi, orc):
+    """M3D_FLAG_REGISTER_HOST: the caller's pageable cloud is page-locked in place on first use; same results, the
+    buffer counts as pinned afterwards, and the registrations are dropped on request"""
+    xyz, nrm = synth.make_c2(n=150000, seed=31)
+    xyz = xyz.copy()
+    for rep in range(2):
+        for kind in KINDS:
+            rc, model, inl, st = ctx.ransac_fit(kind, xyz, nrm if kind == 2 else None, 0.01, 3000, 1.0, seed=40 + kind,
+                                                flags=capi.FLAG_REGISTER_HOST)
+            orc_rc, omodel, oinl, ost = orc.ransac_fit(kind, xyz, nrm if kind == 2 else None, thr=0.01, max_it=3000,
+                                                       prob=1.0, seed=40 + kind)
+            assert rc == orc_rc and np.array_equal(inl, oinl)
+            assert st["best_index"] == ost["best_index"] and st["best_count"] == ost["best_count"]
+    ctx.host_unregister_all()
+    rc, model, inl2, st = ctx.ransac_fit(capi.PLANE, xyz, None, 0.01, 3000, 1.0, seed=40)   # staged path again
+    orc_rc, omodel, oinl, ost = orc.ransac_fit(capi.PLANE, xyz, None, thr=0.01, max_it=3000, prob=1.0, seed=40)
+    assert np.array_equal(inl2, oinl)
