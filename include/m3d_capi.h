@@ -297,6 +297,22 @@ int m3d_icp_point_to_point(m3d_ctx *ctx, const double *src_xyz, size_t ns, const
                            double max_distance, const double *T_init, int max_iteration, double relative_fitness,
                            double relative_rmse, double *T_out, double *fitness, double *inlier_rmse, int *iterations);
 
+/* Device-resident descriptors (the FPFH -> match_correspondence chain without the 2 x 52.8 MB round trip
+ * of examples/cpp/transform_estimation.cpp:20-33).  A handle owns dim x n float64 (column-major) in HBM.
+ *   m3d_fpfh_create      = m3d_compute_fpfh with the result left on the device
+ *   m3d_features_upload  = descriptors computed elsewhere (host, dim x n column-major)
+ *   m3d_match_features   = m3d_match_correspondence (ANNMatcher::Match) on two handles of the same context */
+typedef struct m3d_features m3d_features;
+int m3d_fpfh_create(m3d_ctx *ctx, const double *xyz, const double *nrm, size_t n, double radius, int max_nn,
+                    m3d_features **out, float *device_ms);
+int m3d_features_upload(m3d_ctx *ctx, const double *host, int dim, size_t n, m3d_features **out);
+int m3d_features_download(const m3d_features *f, double *out);
+size_t m3d_features_count(const m3d_features *f);
+int m3d_features_dim(const m3d_features *f);
+void m3d_features_free(m3d_features *f);
+int m3d_match_features(m3d_ctx *ctx, const m3d_features *a, const m3d_features *b, size_t *idx0, size_t *idx1,
+                       size_t *n_out, float *device_ms);
+
 /* Replaces LeastSquareSolver::Solve = Eigen::umeyama over all pairs
  * (src/transform_estimation.cpp:49-66).  src/dst: n x 3 float64 host.  n < 3 -> M3D_ERR_TOO_FEW_POINTS
  * (the reference throws "The number of points pair is less than 3.", transform_estimation.cpp:29-31). */

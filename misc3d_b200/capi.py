@@ -31,7 +31,8 @@ EXPORTS = [
     "m3d_cloud_upload", "m3d_cloud_from_device", "m3d_cloud_free", "m3d_cloud_size",
     "m3d_ransac_fit_cloud", "m3d_score_samples", "m3d_evaluate_model", "m3d_sample_table",
     "m3d_ordered_scan", "m3d_segment_plane_iterative", "m3d_match_correspondence", "m3d_nearest",
-    "m3d_ransac_registration", "m3d_least_squares_transform", "m3d_registration_refit", "m3d_host_unregister_all", "m3d_shard_rows", "m3d_sample_table_device", "m3d_score_stats",
+    "m3d_ransac_registration", "m3d_least_squares_transform", "m3d_registration_refit", "m3d_host_unregister_all", "m3d_fpfh_create", "m3d_features_upload",
+    "m3d_features_download", "m3d_features_count", "m3d_features_dim", "m3d_features_free", "m3d_match_features", "m3d_shard_rows", "m3d_sample_table_device", "m3d_score_stats",
     "m3d_knn_create", "m3d_knn_free", "m3d_knn_search", "m3d_segment_plane_iterative_u32",
     "m3d_compute_fpfh", "m3d_icp_point_to_point",
 ]
@@ -91,6 +92,14 @@ def lib():
         L.m3d_cloud_free.argtypes = [C.c_void_p]
         L.m3d_knn_free.restype = None
         L.m3d_knn_free.argtypes = [C.c_void_p]
+        L.m3d_features_free.restype = None
+        L.m3d_features_free.argtypes = [C.c_void_p]
+        L.m3d_features_count.restype = C.c_size_t
+        L.m3d_features_count.argtypes = [C.c_void_p]
+        L.m3d_features_dim.argtypes = [C.c_void_p]
+        L.m3d_features_download.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+        L.m3d_host_unregister_all.restype = None
+        L.m3d_host_unregister_all.argtypes = [C.c_void_p]
         L.m3d_last_error.argtypes = [C.c_void_p]
         L.m3d_ctx_stream.argtypes = [C.c_void_p]
         L.m3d_ctx_launch_count.argtypes = [C.c_void_p]
@@ -175,6 +184,36 @@ class Cloud:
         if self.handle:
             if getattr(self.ctx, "h", None):
                 lib().m3d_cloud_free(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Features:
+    """device-resident descriptors (m3d_features): dim x n float64 in HBM, owned by this object"""
+
+    def __init__(self, ctx, handle):
+        self.ctx, self.handle = ctx, handle
+        self.dim = int(lib().m3d_features_dim(handle))
+        self.n = int(lib().m3d_features_count(handle))
+        ctx._clouds.add(self)   # freed with the context at the latest, like clouds
+
+    def download(self):
+        """(dim, n) float64, Fortran order (what match_correspondence takes)"""
+        out = np.zeros((max(self.n, 1), self.dim))
+        rc = lib().m3d_features_download(self.handle, _p(out))
+        if rc != 0:
+            self.ctx._check(rc)
+        return np.asfortranarray(out[:self.n].T)
+
+    def free(self):
+        if self.handle:
+            if getattr(self.ctx, "h", None):
+                lib().m3d_features_free(self.handle)
             self.handle = None
 
     def __del__(self):
@@ -435,6 +474,34 @@ class Context:
         self._check(lib().m3d_compute_fpfh(self.h, _p(xyz), _p(nrm), C.c_size_t(n), C.c_double(radius), C.c_int(max_nn),
                                            _p(out), C.byref(ms)))
         return np.asfortranarray(out[:n].T), float(ms.value)
+
+    def fpfh_features(self, xyz, normals, radius, max_nn=100):
+        """m3d_fpfh_create: FPFH descriptors left on the device -> (Features, device_ms)"""
+        xyz = _f64(xyz).reshape(-1, 3)
+        nrm = None if normals is None else _f64(normals).reshape(-1, 3)
+        h = C.c_void_p()
+        ms = C.c_float(0)
+        self._check(lib().m3d_fpfh_create(self.h, _p(xyz), _p(nrm), C.c_size_t(len(xyz)), C.c_double(radius),
+                                          C.c_int(max_nn), C.byref(h), C.byref(ms)))
+        return Features(self, h), float(ms.value)
+
+    def upload_features(self, feat):
+        """(dim, n) float64 descriptors -> Features on the device"""
+        feat = np.asfortranarray(feat, dtype=np.float64)
+        dim, n = feat.shape
+        h = C.c_void_p()
+        self._check(lib().m3d_features_upload(self.h, _p(feat), C.c_int(dim), C.c_size_t(n), C.byref(h)))
+        return Features(self, h)
+
+    def match_features(self, fa, fb):
+        """m3d_match_features: match_correspondence on two device-resident descriptor sets -> (idx0, idx1, device_ms)"""
+        i0 = np.empty(max(fa.n, 1), dtype=np.uint64)
+        i1 = np.empty(max(fa.n, 1), dtype=np.uint64)
+        n_out = C.c_size_t(0)
+        ms = C.c_float(0)
+        self._check(lib().m3d_match_features(self.h, fa.handle, fb.handle, _p(i0, C.c_size_t), _p(i1, C.c_size_t),
+                                             C.byref(n_out), C.byref(ms)))
+        return i0[:n_out.value].copy(), i1[:n_out.value].copy(), float(ms.value)
 
     def icp_point_to_point(self, src, dst, max_distance, T_init=None, max_iteration=30, relative_fitness=1e-6,
                            relative_rmse=1e-6):

@@ -66,6 +66,13 @@ struct NcclApi; /* nccl_dl.cpp */
 
 }  // namespace m3d
 
+struct m3d_features { /* device-resident descriptors: dim x n float64, column-major (one column per point) */
+    m3d_ctx *ctx = nullptr;
+    int dim = 0;
+    size_t n = 0;
+    m3d::DevBuf data;
+};
+
 struct m3d_cloud {
     m3d_ctx *ctx = nullptr;
     size_t n = 0;

@@ -320,10 +320,97 @@ extern "C" void m3d_feat_scratch_free(m3d_feat_scratch *f) {
 
 extern "C" {
 
+/* FPFH of a host cloud into d_out (33 x n f64 on the device); events ev[0] (start) .. the caller records the end */
+static int fpfh_to_device(m3d_ctx *ctx, const double *xyz, const double *nrm, size_t n, double radius, int max_nn, double *d_out);
+
 int m3d_compute_fpfh(m3d_ctx *ctx, const double *xyz, const double *nrm, size_t n, double radius, int max_nn,
                      double *feat_out, float *device_ms) {
     if (!ctx || (n && (!xyz || !feat_out))) return M3D_ERR_INVALID_ARG;
     if (device_ms) *device_ms = 0;
+    if (int rc = fpfh_to_device(ctx, xyz, nrm, n, radius, max_nn, nullptr)) return rc;
+    if (n == 0) return M3D_OK;
+    FeatBufs &B = *feat_bufs(ctx);
+    M3D_CUDA(ctx, cudaMemcpyAsync(feat_out, B.out.p, sizeof(double) * 33 * n, cudaMemcpyDeviceToHost, ctx->stream));
+    M3D_CUDA(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
+    M3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (device_ms) cudaEventElapsedTime(device_ms, ctx->ev[0], ctx->ev[1]);
+    return M3D_OK;
+}
+
+/* ---- device-resident descriptors ("kept on device so descriptors never round-trip") */
+int m3d_fpfh_create(m3d_ctx *ctx, const double *xyz, const double *nrm, size_t n, double radius, int max_nn,
+                    m3d_features **out, float *device_ms) {
+    if (!ctx || !out || (n && !xyz)) return M3D_ERR_INVALID_ARG;
+    *out = nullptr;
+    if (device_ms) *device_ms = 0;
+    M3D_CUDA(ctx, cudaSetDevice(ctx->device));
+    m3d_features *f = new m3d_features();
+    f->ctx = ctx;
+    f->dim = 33;
+    f->n = n;
+    if (f->data.reserve(sizeof(double) * 33 * std::max<size_t>(n, 1)) != cudaSuccess) {
+        delete f;
+        cudaGetLastError();
+        return ctx->fail(M3D_ERR_CUDA, "cudaMalloc of %zu descriptors failed", n);
+    }
+    if (int rc = fpfh_to_device(ctx, xyz, nrm, n, radius, max_nn, f->data.as<double>())) {
+        f->data.release();
+        delete f;
+        return rc;
+    }
+    if (n) {
+        M3D_CUDA(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
+        M3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (device_ms) cudaEventElapsedTime(device_ms, ctx->ev[0], ctx->ev[1]);
+    }
+    *out = f;
+    return M3D_OK;
+}
+int m3d_features_upload(m3d_ctx *ctx, const double *host, int dim, size_t n, m3d_features **out) {
+    if (!ctx || !out || dim <= 0 || (n && !host)) return M3D_ERR_INVALID_ARG;
+    *out = nullptr;
+    M3D_CUDA(ctx, cudaSetDevice(ctx->device));
+    m3d_features *f = new m3d_features();
+    f->ctx = ctx;
+    f->dim = dim;
+    f->n = n;
+    const size_t bytes = sizeof(double) * (size_t)dim * n;
+    if (f->data.reserve(std::max<size_t>(bytes, 8)) != cudaSuccess) {
+        delete f;
+        cudaGetLastError();
+        return ctx->fail(M3D_ERR_CUDA, "cudaMalloc of %zu descriptors failed", n);
+    }
+    if (n) {
+        int rc = host_to_device(ctx, f->data.p, host, bytes, ctx->stream);
+        if (rc == M3D_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = ctx->fail(M3D_ERR_CUDA, "descriptor upload failed");
+        if (rc) {
+            f->data.release();
+            delete f;
+            return rc;
+        }
+    }
+    *out = f;
+    return M3D_OK;
+}
+int m3d_features_download(const m3d_features *f, double *out) {
+    if (!f || !f->ctx || (f->n && !out)) return M3D_ERR_INVALID_ARG;
+    m3d_ctx *ctx = f->ctx;
+    if (f->n == 0) return M3D_OK;
+    M3D_CUDA(ctx, cudaSetDevice(ctx->device));
+    M3D_CUDA(ctx, cudaMemcpyAsync(out, f->data.p, sizeof(double) * (size_t)f->dim * f->n, cudaMemcpyDeviceToHost, ctx->stream));
+    M3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return M3D_OK;
+}
+size_t m3d_features_count(const m3d_features *f) { return f ? f->n : 0; }
+int m3d_features_dim(const m3d_features *f) { return f ? f->dim : 0; }
+void m3d_features_free(m3d_features *f) {
+    if (!f) return;
+    if (f->ctx) cudaStreamSynchronize(f->ctx->stream);
+    f->data.release();
+    delete f;
+}
+
+static int fpfh_to_device(m3d_ctx *ctx, const double *xyz, const double *nrm, size_t n, double radius, int max_nn, double *d_out) {
     if (n && !nrm) return ctx->fail(M3D_ERR_NO_NORMALS, "Failed because input point cloud has no normal."); /* Feature.cpp */
     if (!(radius > 0) || max_nn < 1 || max_nn > kKnnCap)
         return ctx->fail(M3D_ERR_INVALID_ARG, "FPFH needs radius > 0 and 1 <= max_nn <= %d", kKnnCap);
@@ -339,7 +426,7 @@ int m3d_compute_fpfh(m3d_ctx *ctx, const double *xyz, const double *nrm, size_t 
     M3D_CUDA(ctx, B.nbr_d2.reserve(sizeof(double) * n * K));
     M3D_CUDA(ctx, B.nbr_cnt.reserve(sizeof(uint32_t) * n));
     M3D_CUDA(ctx, B.spfh.reserve(sizeof(double) * 33 * n));
-    M3D_CUDA(ctx, B.out.reserve(sizeof(double) * 33 * n));
+    if (!d_out) M3D_CUDA(ctx, B.out.reserve(sizeof(double) * 33 * n));
     M3D_CUDA(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
     if (int rc = host_to_device(ctx, B.xyz.p, xyz, sizeof(double) * 3 * n, ctx->stream)) return rc;
     M3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); /* one staging buffer for pageable sources */
@@ -354,12 +441,8 @@ int m3d_compute_fpfh(m3d_ctx *ctx, const double *xyz, const double *nrm, size_t 
                                              B.nbr_cnt.as<uint32_t>(), B.spfh.as<double>());
     M3D_LAUNCHED(ctx);
     fpfh_kernel<<<nb, 128, 0, ctx->stream>>>(N, K, B.nbr_idx.as<uint32_t>(), B.nbr_d2.as<double>(), B.nbr_cnt.as<uint32_t>(),
-                                             B.spfh.as<double>(), B.out.as<double>());
+                                             B.spfh.as<double>(), d_out ? d_out : B.out.as<double>());
     M3D_LAUNCHED(ctx);
-    M3D_CUDA(ctx, cudaMemcpyAsync(feat_out, B.out.p, sizeof(double) * 33 * n, cudaMemcpyDeviceToHost, ctx->stream));
-    M3D_CUDA(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
-    M3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    if (device_ms) cudaEventElapsedTime(device_ms, ctx->ev[0], ctx->ev[1]);
     return M3D_OK;
 }
 

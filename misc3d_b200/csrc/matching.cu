@@ -248,13 +248,13 @@ __device__ __forceinline__ double l2_groups4(const double *a, const double *b, i
  * rows (every database descriptor fetched from L2 serves kXR queries), blockIdx.y owns one of kXS
  * contiguous column ranges; partial winners go to (pd, pj)[slot][y] and nn_exact_merge_kernel
  * combines them in ascending column order.  list == nullptr: all rows */
-constexpr int kXR = 4, kXS = 8;
+constexpr int kXR = 16, kXS = 8;
 __global__ void __launch_bounds__(256) nn_exact_kernel(const double *__restrict__ A, const double *__restrict__ B,
                                                        uint32_t na, uint32_t nb, int dim,
                                                        const uint32_t *__restrict__ list,
                                                        const uint32_t *__restrict__ list_count,
                                                        double *__restrict__ pd, uint32_t *__restrict__ pj) {
-    extern __shared__ double qa[]; /* kXR x dim doubles */
+    extern __shared__ double qa[]; /* kXR x dim doubles (rows past the end: copies of row 0 of the group) */
     __shared__ double sd[kXR][8];
     __shared__ uint32_t sj[kXR][8];
     const uint32_t total = list ? *list_count : na;
@@ -264,9 +264,10 @@ __global__ void __launch_bounds__(256) nn_exact_kernel(const double *__restrict_
     for (uint32_t g = blockIdx.x; g < groups; g += gridDim.x) {
         const uint32_t nr = min((uint32_t)kXR, total - g * kXR);
         __syncthreads();
-        for (uint32_t e = threadIdx.x; e < nr * (uint32_t)dim; e += blockDim.x) {
+        for (uint32_t e = threadIdx.x; e < (uint32_t)kXR * (uint32_t)dim; e += blockDim.x) {
             const uint32_t r = e / dim, k = e % dim;
-            const uint32_t row = list ? list[g * kXR + r] : g * kXR + r;
+            const uint32_t rr = r < nr ? r : 0u;
+            const uint32_t row = list ? list[g * kXR + rr] : g * kXR + rr;
             qa[r * dim + k] = A[(size_t)row * dim + k];
         }
         __syncthreads();
@@ -277,18 +278,38 @@ __global__ void __launch_bounds__(256) nn_exact_kernel(const double *__restrict_
             best[r] = INFINITY;
             bj[r] = 0xffffffffu;
         }
+        /* thread = database column; the kXR query rows of the group share every loaded descriptor word (the kernel is
+         * bound by the fp64 pipe, not by loads).  Per row the sum is formed exactly as l2_groups4 does. */
         for (uint32_t j = j0 + threadIdx.x; j < j1; j += blockDim.x) {
             const double *b = B + (size_t)j * dim;
+            double acc[kXR];
 #pragma unroll
-            for (int r = 0; r < kXR; ++r) {
-                if ((uint32_t)r < nr) {
-                    const double d = l2_groups4(qa + r * dim, b, dim);
-                    if (d < best[r]) {
-                        best[r] = d;
-                        bj[r] = j;
-                    }
+            for (int r = 0; r < kXR; ++r) acc[r] = 0;
+            int d = 0;
+            for (; d + 3 < dim; d += 4) {
+                const double b0 = b[d], b1 = b[d + 1], b2 = b[d + 2], b3 = b[d + 3];
+#pragma unroll
+                for (int r = 0; r < kXR; ++r) {
+                    const double *a = qa + r * dim + d;
+                    const double d0 = ex::sub(a[0], b0), d1 = ex::sub(a[1], b1), d2 = ex::sub(a[2], b2), d3 = ex::sub(a[3], b3);
+                    acc[r] = ex::add(acc[r], ex::add(ex::add(ex::add(ex::mul(d0, d0), ex::mul(d1, d1)), ex::mul(d2, d2)),
+                                                     ex::mul(d3, d3)));
                 }
             }
+            for (; d < dim; ++d) {
+                const double b0 = b[d];
+#pragma unroll
+                for (int r = 0; r < kXR; ++r) {
+                    const double d0 = ex::sub(qa[r * dim + d], b0);
+                    acc[r] = ex::add(acc[r], ex::mul(d0, d0));
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < kXR; ++r)
+                if (acc[r] < best[r]) {
+                    best[r] = acc[r];
+                    bj[r] = j;
+                }
         }
 #pragma unroll
         for (int r = 0; r < kXR; ++r) {
@@ -560,6 +581,18 @@ static int nn_direction(m3d_ctx *ctx, const FeatDev &A, const FeatDev &B, int di
         cand_exact_kernel<<<ctx->sm_count * 2, 128, 0, ctx->stream>>>(A.f64, B.f64, dim, d_amb, d_amb_count, tb.cand,
                                                                      d_cand_count, d_nn, d_list2, d_list2_count);
         M3D_LAUNCHED(ctx);
+        if (getenv("M3D_MATCH_DEBUG")) { /* candidate statistics of the direction (tuning aid) */
+            cudaStreamSynchronize(ctx->stream);
+            uint32_t namb = 0, nl2 = 0;
+            cudaMemcpy(&namb, d_amb_count, 4, cudaMemcpyDeviceToHost);
+            cudaMemcpy(&nl2, d_list2_count, 4, cudaMemcpyDeviceToHost);
+            std::vector<uint32_t> cc(namb);
+            if (namb) cudaMemcpy(cc.data(), d_cand_count, 4 * (size_t)namb, cudaMemcpyDeviceToHost);
+            std::sort(cc.begin(), cc.end());
+            auto q = [&](double f) { return namb ? cc[(size_t)(f * (namb - 1))] : 0u; };
+            fprintf(stderr, "[m3d match] rows %u ambiguous %u overflow %u; candidates per ambiguous row: median %u p90 %u p99 %u max %u\n",
+                    A.count, namb, nl2, q(0.5), q(0.9), q(0.99), q(1.0));
+        }
         if (int rc = launch_exact(ctx, A, B, dim, d_list2, d_list2_count, d_nn)) return rc;
     } else if (path == 1) {
         const size_t smem = (size_t)3 * (KP + 1) * kMT * sizeof(float) + 3 * sizeof(uint64_t);
@@ -577,7 +610,7 @@ static int nn_direction(m3d_ctx *ctx, const FeatDev &A, const FeatDev &B, int di
 /* uploads both descriptor sets, builds the fp32 tiles; returns device handles in A, B */
 static int match_impl(m3d_ctx *ctx, const double *src, size_t ns, const double *dst, size_t nd, int dim,
                       bool both_directions, size_t *nn_out, size_t *idx0, size_t *idx1, size_t *n_out,
-                      float *device_ms) {
+                      float *device_ms, bool on_device = false) {
     if (!ctx || dim <= 0 || (ns && !src) || (nd && !dst)) return M3D_ERR_INVALID_ARG;
     if (ns >= (1ull << 31) || nd >= (1ull << 31)) return ctx->fail(M3D_ERR_INVALID_ARG, "more than 2^31 descriptors");
     M3D_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -601,15 +634,18 @@ static int match_impl(m3d_ctx *ctx, const double *src, size_t ns, const double *
     const size_t tb = path == 2 ? (size_t)2 * bt * tc::kRows * KPr * 2
                                 : (path == 1 ? sizeof(float) * (size_t)B.ntiles * (KP + 1) * kMT : 16);
     M3D_CUDA(ctx, ctx->d_tmp5.reserve(sizeof(float) * (ns + nd) + 64));
-    M3D_CUDA(ctx, ctx->d_tmp0.reserve(fa));
-    M3D_CUDA(ctx, ctx->d_tmp1.reserve(fb));
+    if (!on_device) {
+        M3D_CUDA(ctx, ctx->d_tmp0.reserve(fa));
+        M3D_CUDA(ctx, ctx->d_tmp1.reserve(fb));
+    }
     M3D_CUDA(ctx, ctx->d_tmp2.reserve(ta));
     M3D_CUDA(ctx, ctx->d_tmp3.reserve(tb));
     M3D_CUDA(ctx, ctx->d_tmp4.reserve(sizeof(uint32_t) * 2 * (ns + nd) + 64));
     M3D_CUDA(ctx, ctx->d_small.reserve(sizeof(MatchScratch) + 4096));
     M3D_CUDA(ctx, ctx->h_small.reserve(sizeof(MatchScratch) + 4096));
-    A.f64 = ctx->d_tmp0.as<double>();
-    B.f64 = ctx->d_tmp1.as<double>();
+    /* descriptors already on the device (m3d_features) are read in place */
+    A.f64 = on_device ? const_cast<double *>(src) : ctx->d_tmp0.as<double>();
+    B.f64 = on_device ? const_cast<double *>(dst) : ctx->d_tmp1.as<double>();
     A.tiles = ctx->d_tmp2.as<float>();
     B.tiles = ctx->d_tmp3.as<float>();
     A.tq = ctx->d_tmp2.as<__nv_bfloat16>();
@@ -626,8 +662,10 @@ static int match_impl(m3d_ctx *ctx, const double *src, size_t ns, const double *
 
     M3D_CUDA(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
     /* pageable descriptor arrays (numpy / Eigen) are staged through pinned memory piece by piece (context.cu) */
-    if (int rc = host_to_device(ctx, A.f64, src, fa, ctx->stream)) return rc;
-    if (int rc = host_to_device(ctx, B.f64, dst, fb, ctx->stream)) return rc;
+    if (!on_device) {
+        if (int rc = host_to_device(ctx, A.f64, src, fa, ctx->stream)) return rc;
+        if (int rc = host_to_device(ctx, B.f64, dst, fb, ctx->stream)) return rc;
+    }
     M3D_CUDA(ctx, cudaMemsetAsync(sc, 0, sizeof(MatchScratch), ctx->stream));
     if (fast) {
         M3D_CUDA(ctx, cudaMemsetAsync(sc->mn, 0xff, sizeof(sc->mn), ctx->stream));
@@ -714,6 +752,15 @@ int m3d_match_correspondence(m3d_ctx *ctx, const double *src, size_t ns, const d
     if (method != M3D_MATCH_FLANN && method != M3D_MATCH_ANNOY)
         return ctx->fail(M3D_ERR_INVALID_ARG, "unknown match method %d", method);
     return m3d::match_impl(ctx, src, ns, dst, nd, dim, true, nullptr, idx0, idx1, n_out, device_ms);
+}
+
+int m3d_match_features(m3d_ctx *ctx, const m3d_features *a, const m3d_features *b, size_t *idx0, size_t *idx1,
+                       size_t *n_out, float *device_ms) {
+    if (!ctx || !a || !b || !n_out || (a->n && (!idx0 || !idx1))) return M3D_ERR_INVALID_ARG;
+    if (a->dim != b->dim) return ctx->fail(M3D_ERR_INVALID_ARG, "descriptor sets of dimension %d and %d", a->dim, b->dim);
+    if (a->ctx != ctx || b->ctx != ctx) return ctx->fail(M3D_ERR_INVALID_ARG, "features belong to another context");
+    return m3d::match_impl(ctx, a->data.as<double>(), a->n, b->data.as<double>(), b->n, a->dim, true, nullptr, idx0, idx1,
+                           n_out, device_ms, true);
 }
 
 int m3d_nearest(m3d_ctx *ctx, const double *src, size_t ns, const double *dst, size_t nd, int dim, size_t *nn,

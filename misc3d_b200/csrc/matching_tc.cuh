@@ -202,7 +202,8 @@ struct TcArgs {
     uint32_t *cand_count;       /* [slots]                                                              */
     uint32_t col_splits;        /* gridDim.y: each CTA scans 1/col_splits of the database tiles         */
 };
-constexpr int kCandCap = 32;
+constexpr int kCandCap = 256; /* rows with more columns inside the error bound go to the full fp64 search: real FPFH
+                                  * descriptors cluster (near-identical patches), 32 sent most rows there */
 
 /* one tile of the top-2 scan: 128 fp32 keys of this thread's row (4 x 32 TMEM columns) */
 template <int G>

@@ -67,3 +67,28 @@ def test_feature_to_icp_chain_recovers_the_transform(ctx, capi):
     assert rc == 1 and np.linalg.norm(T - d["T_true"]) < 0.05
     T2, fit, rmse, it = ctx.icp_point_to_point(d["src"], d["dst"], 0.02, T, 30)
     assert fit > 0.99 and rmse < 0.002 and np.linalg.norm(T2 - d["T_true"]) < 2e-3
+
+
+def test_device_resident_feature_chain(ctx, capi, orc):
+    """f3: FPFH left on the device and matched there == the host round-trip chain, bit for bit"""
+    d = synth.make_surface_pair(n=6000, seed=3)
+    fa_host, _ = ctx.compute_fpfh(d["src"], d["src_nrm"], 0.1, 60)
+    fb_host, _ = ctx.compute_fpfh(d["dst"], d["dst_nrm"], 0.1, 60)
+    fa, ms_a = ctx.fpfh_features(d["src"], d["src_nrm"], 0.1, 60)
+    fb, ms_b = ctx.fpfh_features(d["dst"], d["dst_nrm"], 0.1, 60)
+    assert (fa.dim, fa.n) == (33, 6000) and ms_a > 0
+    np.testing.assert_array_equal(fa.download(), fa_host)
+    np.testing.assert_array_equal(fb.download(), fb_host)
+    i0, i1, _ = ctx.match_correspondence(fa_host, fb_host)
+    j0, j1, _ = ctx.match_features(fa, fb)
+    np.testing.assert_array_equal(i0, j0)
+    np.testing.assert_array_equal(i1, j1)
+    # descriptors computed elsewhere: upload once, match on the device
+    ua, ub = ctx.upload_features(fa_host), ctx.upload_features(fb_host)
+    k0, k1, _ = ctx.match_features(ua, ub)
+    np.testing.assert_array_equal(i0, k0)
+    np.testing.assert_array_equal(i1, k1)
+    with pytest.raises(capi.M3DError):
+        ctx.match_features(ua, ctx.upload_features(np.zeros((5, 10))))   # dimensions differ
+    for f in (fa, fb, ua, ub):
+        f.free()

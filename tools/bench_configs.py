@@ -77,6 +77,27 @@ dp = synth.make_surface_pair(n=200000, seed=2, sigma=0.0005)
 t, (f, ms) = timed(lambda: ctx.compute_fpfh(dp["src"], dp["src_nrm"], 0.03, 100), 2)
 emit(config="f3 compute_fpfh 200k pts, radius 0.03, max_nn 100 (e2e host buffers: 4.8 MB x2 up, 52.8 MB down)", gpu_ms=1e3 * t,
      device_ms=ms)
+# the chain FPFH(src) + FPFH(dst) + match_correspondence: through host buffers (descriptors come back and go up again)
+# and with the descriptors left on the device (m3d_fpfh_create / m3d_match_features)
+def chain_host():
+    fa, _ = ctx.compute_fpfh(dp["src"], dp["src_nrm"], 0.03, 100)
+    fb, _ = ctx.compute_fpfh(dp["dst"], dp["dst_nrm"], 0.03, 100)
+    return ctx.match_correspondence(fa, fb)
+
+
+def chain_device():
+    fa, _ = ctx.fpfh_features(dp["src"], dp["src_nrm"], 0.03, 100)
+    fb, _ = ctx.fpfh_features(dp["dst"], dp["dst_nrm"], 0.03, 100)
+    out = ctx.match_features(fa, fb)
+    fa.free()
+    fb.free()
+    return out
+
+
+th, (h0, h1, _) = timed(chain_host, 2)
+td, (d0, d1, _) = timed(chain_device, 2)
+emit(config="f3 chain: FPFH x2 + match_correspondence, 200k points each", gpu_ms_host_round_trip=1e3 * th,
+     gpu_ms_device_resident=1e3 * td, gpu_ms=1e3 * td, matches=int(len(d0)), identical=bool(np.array_equal(h0, d0) and np.array_equal(h1, d1)))
 T0 = dp["T_true"].copy()
 T0[:3, 3] += 0.01
 t, (T, fit, rmse, it) = timed(lambda: ctx.icp_point_to_point(dp["src"], dp["dst"], 0.02, T0, 30), 2)

@@ -33,6 +33,12 @@ elif what == "feat":  # FPFH (f3) + ICP (f4) at 200k points
     for rep in range(2):
         f, ms = ctx.compute_fpfh(dp["src"], dp["src_nrm"], 0.03, 100)
         print("fpfh", rep, ms)
+    if len(sys.argv) > 2 and sys.argv[2] == "chain":   # FPFH x2 -> match on the device (real descriptors)
+        fa, _ = ctx.fpfh_features(dp["src"], dp["src_nrm"], 0.03, 100)
+        fb, _ = ctx.fpfh_features(dp["dst"], dp["dst_nrm"], 0.03, 100)
+        i0, i1, ms = ctx.match_features(fa, fb)
+        print("chain match", ms, len(i0), float(np.mean(dp["perm"][i1.astype(np.int64)] == i0.astype(np.int64))) if len(i0) else 0)
+        sys.exit(0)
     T0 = dp["T_true"].copy()
     T0[:3, 3] += 0.01
     for rep in range(2):
