@@ -94,8 +94,8 @@ def chain_device():
     return out
 
 
-th, (h0, h1, _) = timed(chain_host, 2)
-td, (d0, d1, _) = timed(chain_device, 2)
+th, (h0, h1, _) = timed(chain_host, 3)
+td, (d0, d1, _) = timed(chain_device, 3)
 emit(config="f3 chain: FPFH x2 + match_correspondence, 200k points each", gpu_ms_host_round_trip=1e3 * th,
      gpu_ms_device_resident=1e3 * td, gpu_ms=1e3 * td, matches=int(len(d0)), identical=bool(np.array_equal(h0, d0) and np.array_equal(h1, d1)))
 T0 = dp["T_true"].copy()
