@@ -316,6 +316,53 @@ namespace registration {
 
 enum class MatchMethod { FLANN = 0, ANNOY = 1 }; /* correspondence_matching.h:14-17 */
 
+/* Extension: descriptors that live on the device (m3d_features) -- FPFH computed there and matched there, without the
+ * 2 x 52.8 MB host round trip of the reference's callers (examples/cpp/transform_estimation.cpp:20-33). */
+class DeviceFeature {
+public:
+    DeviceFeature() = default;
+    DeviceFeature(const DeviceFeature &) = delete;
+    DeviceFeature &operator=(const DeviceFeature &) = delete;
+    DeviceFeature(DeviceFeature &&o) noexcept : h_(o.h_) { o.h_ = nullptr; }
+    DeviceFeature &operator=(DeviceFeature &&o) noexcept {
+        if (this != &o) {
+            m3d_features_free(h_);
+            h_ = o.h_;
+            o.h_ = nullptr;
+        }
+        return *this;
+    }
+    ~DeviceFeature() { m3d_features_free(h_); }
+    /* open3d::pipelines::registration::ComputeFPFHFeature(cloud, KDTreeSearchParamHybrid(radius, max_nn)) */
+    static DeviceFeature FPFH(const PointCloud &cloud, double radius, int max_nn = 100) {
+        if (!cloud.HasNormals() && cloud.HasPoints()) LogError("Failed because input point cloud has no normal.");
+        m3d_ctx *ctx = b200::DefaultContext();
+        DeviceFeature f;
+        const size_t n = cloud.points_.size();
+        if (m3d_fpfh_create(ctx, n ? cloud.points_[0].data() : nullptr, n ? cloud.normals_[0].data() : nullptr, n, radius,
+                            max_nn, &f.h_, nullptr) != M3D_OK)
+            b200::Raise(ctx);
+        return f;
+    }
+    static DeviceFeature Upload(const FeatureMatrix &m) {
+        m3d_ctx *ctx = b200::DefaultContext();
+        DeviceFeature f;
+        if (m3d_features_upload(ctx, m.data, m.dim, m.count, &f.h_) != M3D_OK) b200::Raise(ctx);
+        return f;
+    }
+    int Dimension() const { return m3d_features_dim(h_); }
+    size_t Num() const { return m3d_features_count(h_); }
+    std::vector<double> Download() const { /* dim x n, column-major (usable as FeatureMatrix{dim, n, data}) */
+        std::vector<double> out((size_t)Dimension() * Num());
+        if (h_ && !out.empty() && m3d_features_download(h_, out.data()) != M3D_OK) b200::Raise(b200::DefaultContext());
+        return out;
+    }
+    const m3d_features *handle() const { return h_; }
+
+private:
+    m3d_features *h_ = nullptr;
+};
+
 class ANNMatcher { /* correspondence_matching.h:67-91 */
 public:
     ANNMatcher() : method_(MatchMethod::FLANN), n_trees_(4) {}
@@ -334,6 +381,21 @@ public:
                                                 (int)method_, n_trees_, out.first.data(), out.second.data(), &n_out,
                                                 nullptr);
         if (rc != M3D_OK) b200::Raise(ctx);
+        out.first.resize(n_out);
+        out.second.resize(n_out);
+        return out;
+    }
+
+    /* extension: both descriptor sets already on the device */
+    std::pair<std::vector<size_t>, std::vector<size_t>> Match(const DeviceFeature &src, const DeviceFeature &dst) const {
+        m3d_ctx *ctx = b200::DefaultContext();
+        std::pair<std::vector<size_t>, std::vector<size_t>> out;
+        out.first.resize(src.Num());
+        out.second.resize(src.Num());
+        size_t n_out = 0;
+        if (!src.handle() || !dst.handle()) LogError("Empty device feature");
+        if (m3d_match_features(ctx, src.handle(), dst.handle(), out.first.data(), out.second.data(), &n_out, nullptr) != M3D_OK)
+            b200::Raise(ctx);
         out.first.resize(n_out);
         out.second.resize(n_out);
         return out;

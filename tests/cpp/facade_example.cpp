@@ -4,6 +4,7 @@
 // file, fits a plane with a fixed seed, segments planes, prints the results as text.
 #include <misc3d/common/ransac.h>
 #include <misc3d/logging.h>
+#include <misc3d/registration/correspondence_matching.h>
 #include <misc3d/segmentation/iterative_plane_segmentation.h>
 
 #include <cstdio>
@@ -54,6 +55,23 @@ int main(int argc, char **argv) {
         std::printf("\n");
         const int kh = knn.SearchHybrid(q, dist.empty() ? 1.0 : dist.back(), 5, idx, dist); /* drops the last one (knn.cpp:129) */
         std::printf("hybrid %d\n", kh);
+    }
+
+    { /* ANNMatcher on host descriptors and (extension) on descriptors uploaded to the device: same answer.  The
+       * "descriptors" are the first 2000 points (dim 3) against themselves shifted by one */
+        const size_t m = pc.points_.size() < 2000 ? pc.points_.size() : 2000;
+        std::vector<double> a(3 * m), b(3 * m);
+        for (size_t i = 0; i < m; ++i)
+            for (int c = 0; c < 3; ++c) {
+                a[3 * i + c] = pc.points_[i][c];
+                b[3 * i + c] = pc.points_[(i + 1) % m][c];
+            }
+        misc3d::registration::ANNMatcher matcher(misc3d::registration::MatchMethod::FLANN);
+        const misc3d::FeatureMatrix fa{3, m, a.data()}, fb{3, m, b.data()};
+        const auto host = matcher.Match(fa, fb);
+        const auto da = misc3d::registration::DeviceFeature::Upload(fa), db = misc3d::registration::DeviceFeature::Upload(fb);
+        const auto dev = matcher.Match(da, db);
+        std::printf("devmatch %d %zu %d\n", host == dev ? 1 : 0, dev.first.size(), da.Download() == a ? 1 : 0);
     }
 
     try { /* the reference throws std::runtime_error from LogError (ransac.h:483-485) */

@@ -66,3 +66,5 @@ def test_reference_style_caller_matches_compiled_reference(tmp_path, capi):
     assert int(knn[1]) == 5 and [int(v) for v in knn[2::2]] == order.tolist()
     np.testing.assert_allclose([float(v) for v in knn[3::2]], d[order], rtol=1e-12, atol=1e-15)
     assert next(ln for ln in lines if ln[0] == "hybrid")[1] == "4"
+    dm = next(ln for ln in lines if ln[0] == "devmatch")
+    assert dm[1] == "1" and int(dm[2]) > 1000 and dm[3] == "1"   # device-resident descriptors: same matches, same bits
