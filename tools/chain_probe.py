@@ -1,5 +1,10 @@
-import sys, time
-sys.path.insert(0, "/root/repo")
+"""Component timing of the registration front end at 200k points: FPFH of both clouds + match_correspondence, with the
+descriptors left on the device (m3d_fpfh_create / m3d_match_features) and through host buffers.  Wall ms (device ms)."""
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from misc3d_b200 import capi, synth
 ctx = capi.Context(0)
 dp = synth.make_surface_pair(n=200000, seed=2, sigma=0.0005)
