@@ -148,6 +148,14 @@ FArray feature_from_py(const py::object &o) {
 
 std::pair<std::vector<size_t>, std::vector<size_t>> match(const py::object &src, const py::object &dst,
                                                          const registration::MatchMethod &method, int n_trees) {
+    if (py::isinstance<registration::DeviceFeature>(src) && py::isinstance<registration::DeviceFeature>(dst)) {
+        /* extension: both descriptor sets already on the device */
+        const auto &da = src.cast<const registration::DeviceFeature &>();
+        const auto &db = dst.cast<const registration::DeviceFeature &>();
+        registration::ANNMatcher matcher(method, n_trees);
+        py::gil_scoped_release nogil;
+        return matcher.Match(da, db);
+    }
     FArray a = feature_from_py(src), b = feature_from_py(dst);
     registration::ANNMatcher matcher(method, n_trees);
     FeatureMatrix fa{(int)a.shape(0), (size_t)a.shape(1), a.data()};
@@ -299,6 +307,28 @@ PYBIND11_MODULE(py_misc3d, m) {
         py::arg("src"), py::arg("dst"), py::arg("corres"), py::arg("T"), py::arg("threshold") = 0.01,
         py::arg("scaling") = false);
     /* ... and the Open3D steps the reference's callers run around this path, on the GPU */
+    py::class_<registration::DeviceFeature>(reg, "DeviceFeature",
+                                            "descriptors that live on the GPU: accepted by match_correspondence (both arguments)")
+        .def("dimension", &registration::DeviceFeature::Dimension)
+        .def("num", &registration::DeviceFeature::Num)
+        .def_property_readonly(
+            "data",
+            [](const registration::DeviceFeature &f) {
+                std::vector<double> v = f.Download();
+                py::array_t<double, py::array::f_style> a({(py::ssize_t)f.Dimension(), (py::ssize_t)f.Num()});
+                if (!v.empty()) std::memcpy(a.mutable_data(), v.data(), sizeof(double) * v.size());
+                return a;
+            },
+            "(dim, n) float64 copy on the host (like open3d's Feature.data)");
+    reg.def(
+        "compute_fpfh_feature_device",
+        [](const py::object &pcd, double radius, int max_nn) {
+            PointCloud pc = cloud_from_py(pcd);
+            py::gil_scoped_release nogil;
+            return registration::DeviceFeature::FPFH(pc, radius, max_nn);
+        },
+        "compute_fpfh_feature with the (33, n) result left on the GPU as a DeviceFeature", py::arg("pcd"), py::arg("radius"),
+        py::arg("max_nn") = 100);
     reg.def(
         "compute_fpfh_feature",
         [](const py::object &pcd, double radius, int max_nn) {

@@ -89,3 +89,25 @@ def test_registration_chain(m3d, orc):
     # extension: least-squares refit on the inlier correspondences of the RANSAC result
     Tr = m3d.registration.refine_transformation_on_inliers(FakeO3DCloud(d["src"]), FakeO3DCloud(d["dst"]), corres, T, 0.02)
     assert Tr.shape == (4, 4) and np.linalg.norm(Tr - d["T_true"]) <= np.linalg.norm(T - d["T_true"]) + 1e-12
+
+
+def test_feature_extensions_host_and_device(m3d, orc):
+    """extensions of the shim: FPFH on the GPU as an ndarray and as a DeviceFeature; match_correspondence takes either;
+    registration_icp"""
+    d = synth.make_surface_pair(n=5000, seed=6)
+    src, dst = FakeO3DCloud(d["src"], d["src_nrm"]), FakeO3DCloud(d["dst"], d["dst_nrm"])
+    fa = m3d.registration.compute_fpfh_feature(src, 0.1, 60)
+    fb = m3d.registration.compute_fpfh_feature(dst, 0.1, 60)
+    assert fa.shape == (33, 5000) and fa.flags.f_contiguous
+    ofa = orc.fpfh(d["src"], d["src_nrm"], 0.1, 60)
+    assert np.mean(np.abs(fa - ofa) > 1e-9) < 1e-3            # isolated histogram-edge flips only (DESIGN 4.7)
+    da = m3d.registration.compute_fpfh_feature_device(src, 0.1, 60)
+    db = m3d.registration.compute_fpfh_feature_device(dst, 0.1, 60)
+    assert (da.dimension(), da.num()) == (33, 5000)
+    np.testing.assert_array_equal(da.data, fa)
+    host = m3d.registration.match_correspondence(fa, fb)
+    dev = m3d.registration.match_correspondence(da, db)
+    assert host == dev and len(host[0]) > 200
+    T = m3d.registration.compute_transformation_ransac(src, dst, dev, 0.02, 4000, 0.9, seed=1)
+    T_icp, fitness, rmse, iterations = m3d.registration.registration_icp(src, dst, 0.02, T, 30)
+    assert fitness > 0.9 and np.linalg.norm(T_icp - d["T_true"]) < 5e-3

@@ -72,6 +72,8 @@ def test_argument_names_and_defaults(m3d):
         ("edge_length_threshold", "0.9"), ("seed", "None")]
     # py_registration.cpp:12-31: (src, dst, scaling=False), point clouds or (n, 3) arrays
     assert _sig(m3d.registration.compute_transformation_least_square) == [("src", None), ("dst", None), ("scaling", "False")]
+    assert _sig(m3d.registration.compute_fpfh_feature_device) == [("pcd", None), ("radius", None), ("max_nn", "100")]
+    assert hasattr(m3d.registration, "DeviceFeature")
     assert _sig(m3d.registration.refine_transformation_on_inliers) == [
         ("src", None), ("dst", None), ("corres", None), ("T", None), ("threshold", "0.01"), ("scaling", "False")]
 
