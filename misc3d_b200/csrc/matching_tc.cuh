@@ -26,12 +26,6 @@
 
 #include <cstdint>
 
-#ifndef M3D_TC_EXP
-#define M3D_TC_EXP 0
-#endif
-#ifndef M3D_TC2_EXP
-#define M3D_TC2_EXP 0
-#endif
 
 namespace m3d {
 namespace tc {
@@ -360,17 +354,9 @@ __global__ void __launch_bounds__(192, 1) nn_top2_tc_kernel(const TcArgs a) {
             for (int rb = 0; rb < kRB; ++rb) {
                 float v[4][32];
                 const uint32_t tbase = tmem_base + ((q * 32u) << 16) + (uint32_t)(buf * kRB + rb) * 128u;
-#if M3D_TC_EXP != 1 /* timing experiment 1: no TMEM loads at all (wrong results) */
 #pragma unroll
                 for (int g = 0; g < 4; ++g) tmem_ld32(tbase + 32u * g, v[g]); /* four loads in flight */
                 tmem_ld_wait();
-#else
-                (void)tbase;
-#pragma unroll
-                for (int g = 0; g < 4; ++g)
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) v[g][i] = 1e30f;
-#endif
                 if (rb == kRB - 1) { /* the buffer pair is free as soon as the values sit in registers */
                     tc_fence_before();
                     __syncwarp();
@@ -524,13 +510,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTc2Threads, 1) nn_t
             for (uint32_t t = 0; t < ntb; ++t) {
                 const int st = t % kB2Stages;
                 mbar_wait(&b_empty[st], ((t / kB2Stages) & 1) ^ 1);
-#if M3D_TC2_EXP == 2 /* timing experiment (wrong results): 512 bytes per stage instead of a half tile */
-                tma_load_1d(Bs + (size_t)st * half_bytes, reinterpret_cast<const unsigned char *>(a.Bd), 512, &b_full[st]);
-#else
                 tma_load_1d(Bs + (size_t)st * half_bytes,
                             reinterpret_cast<const unsigned char *>(a.Bd) + ((size_t)(tb0 + t) * 2 + crank) * half_bytes,
                             half_bytes, &b_full[st]);
-#endif
             }
         }
     } else if (warp == 1) {
@@ -547,11 +529,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTc2Threads, 1) nn_t
                 const uint32_t b0 = smem_u32(Bs + (size_t)st * half_bytes);
                 const uint32_t a0 = smem_u32(As);
                 const uint32_t d0 = tmem_base + (uint32_t)buf * 128u;
-#if M3D_TC2_EXP == 3 /* timing experiment (wrong results): one MMA per tile */
-                for (int ks = 0; ks < 1; ++ks)
-#else
                 for (int ks = 0; ks < nk; ++ks)
-#endif
                     umma2_bf16(d0, umma_desc(a0 + ks * 2 * kChunkBytes, kChunkBytes),
                                umma_desc(b0 + ks * 2 * (kChunkBytes / 2), kChunkBytes / 2), idesc, ks > 0 ? 1u : 0u);
                 umma2_commit(&b_empty[st], 0x3); /* the slot is free in BOTH CTAs once these MMAs have read it */
@@ -593,15 +571,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTc2Threads, 1) nn_t
                 if (crank == 0) mbar_arrive(&t_empty[buf]);
                 else mbar_arrive_remote(&t_empty[buf], 0);
             }
-#if M3D_TC2_EXP == 1 /* timing experiment (wrong results): no scan of the keys */
-            m1 = fminf(m1, v[0][lane & 31]);
-#else
             if (CAND) {
                 if (my < nslots) collect_tile<2>(v, jbase, ncol, cutv, a.cand + (size_t)my * kCandCap, a.cand_count + my, half * 64u);
             } else {
                 scan_tile<2>(v, jbase, ncol, m1, m2, i1, half * 64u);
             }
-#endif
         }
         if (!CAND) { /* merge the two column halves of every row (through the idle operand ring) */
             float4 *xch = reinterpret_cast<float4 *>(Bs);

@@ -404,24 +404,10 @@ __device__ __forceinline__ void fast_eval2(const Fast2<KIND> &g, const float4 p,
     unpack2(t, t0, t1);
 }
 
-/* inner-loop bookkeeping: provisional inlier count (sign bit of v) and min |v|.
- * M3D_EXP selects timing experiments (wrong results!): 1 = no min tracking, 2 = no count,
- * 3 = count through the FMA pipe (IMAD.HI) */
-#ifndef M3D_EXP
-#define M3D_EXP 0
-#endif
+/* inner-loop bookkeeping: provisional inlier count (sign bit of v) and min |v| */
 __device__ __forceinline__ void accumulate_v(float v, uint32_t &clo, float &mn) {
-#if M3D_EXP == 1
-    clo += __float_as_uint(v) >> 31;
-#elif M3D_EXP == 2
-    mn = fminf(mn, fabsf(v));
-#elif M3D_EXP == 3
-    clo = __umulhi(__float_as_uint(v), 2u) + clo;
-    mn = fminf(mn, fabsf(v));
-#else
     clo += __float_as_uint(v) >> 31;
     mn = fminf(mn, fabsf(v));
-#endif
 }
 
 template <int KIND>

@@ -1,4 +1,4 @@
-"""timing-only run of m3d_nearest at C4 size (for the -DM3D_TC_EXP experiments: results are not checked)"""
+"""timing-only run of m3d_nearest at C4 size (results are not checked; used for the tensor-core timing experiments recorded in DESIGN.md section 8)"""
 import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)

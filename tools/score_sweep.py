@@ -57,7 +57,7 @@ def run():
 
 
 def raw():
-    """wall-clock of m3d_score_samples only (no self-check): for the M3D_EXP timing experiments"""
+    """wall-clock of m3d_score_samples only (no self-check)"""
     import time
     import numpy as np
     from misc3d_b200 import capi, synth
