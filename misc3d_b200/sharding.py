@@ -109,3 +109,13 @@ def torch_exchange(group=None, device=None):
         return 0
 
     return fn
+
+
+def upload_slice(n_points, rank, world):
+    """the part of a replicated n x 3 float64 cloud rank `rank` copies to its GPU in a multi-rank host-buffer fit
+    (csrc/ransac.cu ChunkPlan::issue_copies): (offset, length, slice size) in doubles.  All slices have the same size S
+    (the all-gather's count); the last ones may be shorter or empty."""
+    tot = 3 * int(n_points)
+    s = (tot + world - 1) // world
+    off = s * rank
+    return off, (min(s, tot - off) if off < tot else 0), s

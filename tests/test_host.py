@@ -316,3 +316,19 @@ def test_mt_jump_table_matches_generator():
     polys = gen.build()
     for p, g in enumerate(polys, 1):
         assert int.from_bytes(table[p - 1].astype("<u4").tobytes(), "little") == g, p
+
+
+def test_cooperative_upload_slices_tile_the_cloud():
+    """multi-rank host-buffer fit: the slices the ranks upload cover the cloud exactly once, whatever the divisibility,
+    and fit the all-gather buffer of 3 n + world doubles"""
+    from misc3d_b200 import sharding
+    for n in (65536, 70001, 1_000_000, 999_983):
+        for world in (2, 3, 4, 8):
+            covered = 0
+            for r in range(world):
+                off, length, s = sharding.upload_slice(n, r, world)
+                assert off == covered or length == 0
+                covered += length
+                assert off + length <= 3 * n
+                assert s * world <= 3 * n + world - 1   # the receive buffer holds world x S doubles (3 n + world reserved)
+            assert covered == 3 * n
