@@ -25,6 +25,17 @@ i0, i1, _ = ctx.match_correspondence(f, g)
 rc, T, st = ctx.ransac_registration(d["src"], d["dst"], i0, i1, 0.02, 2000, 0.9, 0.999, 1)
 T2, fit, rmse, it = ctx.icp_point_to_point(d["src"], d["dst"], 0.05, T, 10)
 print("chain", len(i0), rc, fit, it)
+# device-resident descriptors, the refit extension, and the full fp64 search (16 rows per group) on every row
+fa, _ = ctx.fpfh_features(d["src"], d["src_nrm"], 0.15, 40)
+fb, _ = ctx.fpfh_features(d["dst"], d["dst_nrm"], 0.15, 40)
+j0, j1, _ = ctx.match_features(fa, fb)
+T3, n_in = ctx.registration_refit(d["src"], d["dst"], i0, i1, T, 0.02)
+import numpy as np   # noqa: E402
+wide = np.asfortranarray(np.random.default_rng(1).uniform(0, 1, (200, 300)))   # dim 200: the fp64-only path
+k0, k1, _ = ctx.match_correspondence(wide, wide[:, ::-1].copy(order="F"))
+print("device chain", len(j0), bool((j0 == i0).all()), n_in, len(k0))
+fa.free()
+fb.free()
 idx, dist, cnt = ctx.knn_search(f[:, :500], f[:, :20], 5)
 print("knn", cnt[:5])
 ctx.close()
