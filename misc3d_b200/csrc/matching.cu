@@ -572,7 +572,8 @@ static int nn_direction(m3d_ctx *ctx, const FeatDev &A, const FeatDev &B, int di
         tb.slot_cut = d_slot_cut;
         tb.cand = ctx->d_queue.as<uint32_t>();
         tb.cand_count = d_cand_count;
-        tb.col_splits = 8;
+        static const int splits_env = getenv("M3D_MATCH_SPLITS") ? atoi(getenv("M3D_MATCH_SPLITS")) : 0;
+        tb.col_splits = splits_env > 0 ? (uint32_t)splits_env : 16u; /* 2: 144 ms, 4: 128, 8: 122, 16: 118, 32: 117 (200k FPFH descriptors) */
         if (two)
             tc::nn_top2_tc2_kernel<true><<<dim3(atiles, tb.col_splits), tc::kTc2Threads, smem2, ctx->stream>>>(tb);
         else
